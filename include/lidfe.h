@@ -1,0 +1,190 @@
+/*
+ * lidfe.h -- C ABI of the B200-native speech-lid front-end (liblidfe.so).
+ *
+ * Drop-in boundary for ONE path of kouyt5/speech-lid: raw 16 kHz waveform -> kaldi log-mel
+ * fbank / MFCC -> SpecAugment masks -> CMVN -> (rows, n_out) features.  Each entry point names
+ * the reference interface it replaces ("ref:" = path in the reference tree, "ta:" = path inside the
+ * torchaudio package the reference calls; the reference has no native code, its "FFI" is the Python
+ * call boundary of lid/audio_processor.py, so the binding a maintainer adds is a ctypes stub --
+ * INTEGRATION.md shows it).
+ *
+ * Conventions
+ *   - Plain C types only.  Pointers named *_dev are DEVICE pointers owned by the caller (PyTorch
+ *     tensors' data_ptr()); *_host are host pointers.  `stream` is a cudaStream_t passed as void*.
+ *   - Return value: 0 = OK; < 0 = contract error (LIDFE_E_*); > 0 = a cudaError_t.  Nothing throws,
+ *     nothing calls exit().  lidfe_strerror() maps any return value to text.
+ *   - A handle is immutable after lidfe_create(); a plan is immutable after lidfe_plan_create().
+ *     All device work is enqueued asynchronously on `stream`; no call synchronises the device
+ *     except lidfe_create / lidfe_plan_create (table upload).
+ *   - There is no CPU implementation behind this ABI.  Without a CUDA device every compute entry
+ *     point returns a cudaError_t.
+ */
+#ifndef LIDFE_H_
+#define LIDFE_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIDFE_ABI_VERSION 1
+
+/* error codes (negative) */
+#define LIDFE_OK 0
+#define LIDFE_E_NULL -1        /* required pointer is NULL */
+#define LIDFE_E_CONFIG -2      /* unsupported configuration (sample rate, frame geometry, n_mels ...) */
+#define LIDFE_E_SHORT -3       /* an utterance is shorter than one frame (ta: compliance/kaldi.py:142 asserts) */
+#define LIDFE_E_OFFSETS -4     /* offsets not monotone / overlapping / negative */
+#define LIDFE_E_ARG -5         /* bad scalar argument (B <= 0, ld < n_out, unknown mode ...) */
+#define LIDFE_E_MELBANK -6     /* mel bank row is empty, non-contiguous beyond limits or too wide */
+#define LIDFE_E_NOMEM -7       /* host allocation failed */
+
+/* input sample types */
+#define LIDFE_IN_F32 0
+#define LIDFE_IN_I16 1         /* int16 PCM, converted in-kernel as (float)s * in_scale */
+
+/* cmvn modes of lidfe_featurize */
+#define LIDFE_CMVN_NONE 0          /* ref behaviour: features leave the kernel un-normalised */
+#define LIDFE_CMVN_PER_UTT 1       /* per utterance, per output dim: (x - mean_t) / (std_t + 1e-9), unbiased */
+#define LIDFE_CMVN_APPLY_GLOBAL 2  /* normalise in the fbank epilogue with caller-supplied global sums */
+#define LIDFE_CMVN_ACCUM_GLOBAL 3  /* write raw features, add [sum, sumsq, count] to stats_out_dev */
+
+typedef struct lidfe_ctx* lidfe_handle;
+typedef struct lidfe_plan_s* lidfe_plan;
+
+/*
+ * Front-end configuration.  Mirrors the argument set the reference passes to
+ * torchaudio.compliance.kaldi.fbank (ref: lid/audio_processor.py:41-69; ta: compliance/kaldi.py:514-541).
+ * Supported geometry this round: sample_rate 16000, frame_len 400, frame_shift 160, fft_len 512,
+ * 4 <= n_mels <= 80, n_ceps 0 (fbank) or 1..n_mels (MFCC).  Anything else -> LIDFE_E_CONFIG (the survey
+ * asks for a loud error rather than silent mis-framing at other rates).
+ */
+typedef struct {
+  int sample_rate;   /* 16000 */
+  int frame_len;     /* 400  = int(sr * 25 ms)                                  */
+  int frame_shift;   /* 160  = int(sr * 10 ms)                                  */
+  int fft_len;       /* 512  = next power of two (round_to_power_of_two=True)   */
+  int n_mels;        /* 80                                                       */
+  int n_ceps;        /* 0 -> log-mel fbank; >0 -> MFCC with n_ceps coefficients  */
+  float preemph;     /* 1.0 in the reference's call (per frame, replicate-left)  */
+  int remove_dc;     /* 1                                                        */
+  float log_floor;   /* 1.1920929e-07 (FLT_EPSILON)                              */
+  int in_dtype;      /* LIDFE_IN_F32 | LIDFE_IN_I16                              */
+  float in_scale;    /* multiplier applied to int16 samples (ignored for f32)    */
+} lidfe_config;
+
+/* -- lifetime ------------------------------------------------------------------------------------- */
+
+/*
+ * Replaces the per-call table construction inside kaldi.fbank / kaldi.mfcc
+ * (ta: compliance/kaldi.py:86-113 window, :436-511 mel banks, :648-666 DCT + lifter).
+ * The caller builds the tables with the same fp32 host arithmetic as the reference and passes them in:
+ *   window_host  [frame_len]
+ *   melbank_host [n_mels][fft_len/2 + 1]   dense, row-major; sparsified inside
+ *   dct_host     [n_mels][n_ceps]          or NULL when n_ceps == 0
+ *   lifter_host  [n_ceps]                  or NULL (no liftering)
+ * Uploads constant tables to the current device; allocates nothing else.
+ */
+int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window_host,
+                 const float* melbank_host, const float* dct_host, const float* lifter_host);
+int lidfe_destroy(lidfe_handle h);
+
+/* Number of frames kaldi's snip_edges=True framing yields (ta: compliance/kaldi.py:63-67):
+ * 1 + (n - frame_len) / frame_shift, or 0 when n < frame_len.  Host helper, integer-exact. */
+long long lidfe_num_frames(long long n_samples, const lidfe_config* cfg);
+
+/* Output feature dimension: n_ceps if n_ceps > 0 else n_mels. */
+int lidfe_out_dim(lidfe_handle h);
+
+/* -- plan: the segment-offset table of one batch -------------------------------------------------- */
+
+/*
+ * Replaces MergedDataset.collate_fn's padding bookkeeping (ref: lid/raw_datasets.py:345-365) and the
+ * per-utterance Python loop around wav2mel (ref: lid/raw_datasets.py:270-305).
+ *   wav_offsets_host [B]  first sample of utterance i inside the packed waveform buffer (in samples)
+ *   wav_lengths_host [B]  number of samples of utterance i  (>= frame_len, else LIDFE_E_SHORT)
+ *   out_rows_host    [B]  output row of frame 0 of utterance i.  Packed: prefix sum of frame counts.
+ *                         Padded (B, T_max, n_out): i * T_max.
+ *   pad_rows_host    [B]  or NULL: rows [out_rows[i] + T_i, out_rows[i] + pad_rows[i]) are zero-filled by
+ *                         the kernel (pad_sequence's zeros) -- no separate memset / pad pass.
+ * Utterances whose offset is a multiple of 16 bytes are staged by TMA bulk copies; others fall back to
+ * element loads (slower, same results).
+ */
+int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* wav_offsets_host,
+                      const long long* wav_lengths_host, const long long* out_rows_host,
+                      const long long* pad_rows_host);
+int lidfe_plan_destroy(lidfe_plan p);
+long long lidfe_plan_total_frames(lidfe_plan p);
+long long lidfe_plan_num_tiles(lidfe_plan p);
+/* frames of utterance i (host copy of what the kernel will produce) */
+long long lidfe_plan_frames(lidfe_plan p, int i);
+
+/* -- the hot path --------------------------------------------------------------------------------- */
+
+/*
+ * Replaces, for a whole batch in one call:
+ *   wav2mel(x, use_kaildi=True)            ref: lid/audio_processor.py:8-69   (n_ceps == 0)
+ *   torchaudio.compliance.kaldi.mfcc       ta: compliance/kaldi.py:669-813    (n_ceps > 0; not in the reference)
+ *   spectrogram_augment(mask application)  ref: lid/audio_processor.py:225-227; ta: functional/functional.py:885-958
+ *   CMVN                                   commented out at ref: lid/audio_processor.py:66-68 (our definition)
+ *   collate_fn padding                     ref: lid/raw_datasets.py:347-350
+ *
+ *   wav_dev       packed samples (float32 or int16 per cfg.in_dtype)
+ *   out_dev       [rows][out_ld] float32, out_ld >= n_out
+ *   masks_dev     int32 [B][n_masks][4] = (t0, t1, f0, f1): frames [t0,t1) and dims [f0,f1) of utterance i are
+ *                 set to 0.0 after normalisation; NULL / n_masks == 0 -> no masking.  The integer bounds are drawn
+ *                 on the host from the same RNG stream as the reference, so application is bit-exact.
+ *   cmvn_mode     LIDFE_CMVN_*
+ *   stats_in_dev  double [2*n_out + 1] = sum_d, sumsq_d, count  (APPLY_GLOBAL), else NULL
+ *   stats_out_dev double [2*n_out + 1] accumulated with atomics (ACCUM_GLOBAL), else NULL.  Caller zeroes it.
+ * With ACCUM_GLOBAL masks are ignored (they are applied by lidfe_cmvn_apply after the all-reduce).
+ */
+int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
+                    const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
+                    double* stats_out_dev, void* stream);
+
+/*
+ * Second pass of global CMVN: feats = (feats - mean) / (std + 1e-9) in place, then masks.
+ * stats_dev is the all-reduced [2*n_out + 1] vector.  (Global CMVN has no reference implementation.)
+ */
+int lidfe_cmvn_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long ld, const int* masks_dev,
+                     int n_masks, const double* stats_dev, void* stream);
+
+/*
+ * Standalone SpecAugment application (ref: lid/audio_processor.py:225-227; ta: functional/functional.py:885-958):
+ * zero-fill frames [t0,t1) and dims [f0,f1) of every utterance of the plan, in place.  Used by the
+ * single-utterance spectrogram_augment() wrapper; lidfe_featurize applies the same table in its epilogue.
+ */
+int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long ld, const int* masks_dev, int n_masks,
+                     void* stream);
+
+/*
+ * Waveform-level stages that precede framing, per utterance of the plan, float32 in -> float32 out
+ * (out-of-place: wav_out_dev must not alias wav_in_dev; the reference's wav_augment mutates its input, the
+ * Python wrapper restores that behaviour by copying back):
+ *   normalize != 0 : normalize_wav  (x - mean) / (std + 1e-6), unbiased std     ref: lid/audio_processor.py:108-115
+ *   dither   != 0  : x += dither * noise_dev[i]   (noise = the U[0,1) draw)     ref: lid/audio_processor.py:129
+ *   preemph  != 0  : y[0] = x[0]; y[n] = x[n] - preemph * x[n-1]                ref: lid/audio_processor.py:131-134
+ * noise_dev may be NULL when dither == 0.  Offsets/lengths are the plan's.
+ */
+int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,
+                      float dither, const float* noise_dev, float preemph, void* stream);
+
+/* -- measurement --------------------------------------------------------------------------------
+ * Between lidfe_profile_begin and lidfe_profile_end every lidfe_featurize call brackets its fused fbank kernel with
+ * a CUDA event pair on the launching stream (up to max_launches calls).  lidfe_profile_end synchronises on them and
+ * returns the per-launch durations in milliseconds (bench.py's roofline leg).  Not thread-safe per handle. */
+int lidfe_profile_begin(lidfe_handle h, int max_launches);
+int lidfe_profile_end(lidfe_handle h, float* ms_host, int capacity, int* n_out);
+
+/* -- misc ----------------------------------------------------------------------------------------- */
+const char* lidfe_strerror(int rc);
+int lidfe_abi_version(void);
+/* kernels launched by this library in this process so far (bench.py reports it as gpu_launches) */
+long long lidfe_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDFE_H_ */

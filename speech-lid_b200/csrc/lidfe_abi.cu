@@ -1,0 +1,464 @@
+// lidfe_abi.cu -- C ABI (include/lidfe.h) over the sm_100a kernels in lidfe_kernels.cuh.
+// Host side only builds constant tables / the per-batch tile table and launches kernels; there is no
+// CPU compute path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "../../include/lidfe.h"
+#include "lidfe_kernels.cuh"
+
+using namespace lidfe;
+
+struct lidfe_ctx {
+  lidfe_config cfg;
+  int device;
+  int num_sms;
+  int n_out;
+  int mel_maxt;
+  int band_taps[kBands];
+  // device tables
+  float* d_window;
+  float2* d_tw1;
+  float2* d_tw2;
+  float* d_melw;
+  int* d_k0;
+  float* d_dct;
+  float* d_lifter;
+  size_t smem_bytes;
+  int grid_cap;   // resident CTAs of the fbank kernel on this device
+  // optional per-launch timing of the fbank kernel (bench.py's roofline leg)
+  std::vector<cudaEvent_t>* prof_events;
+  int prof_used;
+};
+
+struct lidfe_plan_s {
+  lidfe_ctx* ctx;
+  int B;
+  long long total_frames;
+  long long n_tiles;
+  std::vector<long long> frames;
+  Tile* d_tiles;
+  long long* d_frames;    // [B]
+  long long* d_offsets;   // [B]
+  long long* d_lengths;   // [B]
+  double* d_utt_stats;    // [B][2][n_out]
+};
+
+static std::atomic<long long> g_launches{0};
+
+#define CU_TRY(expr)                      \
+  do {                                    \
+    cudaError_t e__ = (expr);             \
+    if (e__ != cudaSuccess) {             \
+      cudaGetLastError();                 \
+      return static_cast<int>(e__);       \
+    }                                     \
+  } while (0)
+
+template <typename T>
+static cudaError_t upload(T** dst, const T* src, size_t n) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+typedef void (*fbank_fn)(const FbankParams);
+static fbank_fn pick_kernel(const lidfe_config& c) {
+  const bool mfcc = c.n_ceps > 0;
+  if (c.in_dtype == LIDFE_IN_I16) return mfcc ? fbank_kernel<short, true> : fbank_kernel<short, false>;
+  return mfcc ? fbank_kernel<float, true> : fbank_kernel<float, false>;
+}
+static size_t smem_for(const lidfe_config& c, int maxt) {
+  const size_t base = (c.in_dtype == LIDFE_IN_I16) ? SmemLayout<short>::off_melw : SmemLayout<float>::off_melw;
+  size_t extra = static_cast<size_t>(kBands) * maxt * 16;
+  if (c.n_ceps > 0) extra += static_cast<size_t>(c.n_mels) * c.n_ceps + c.n_ceps;
+  return base + extra * sizeof(float);
+}
+
+extern "C" {
+
+int lidfe_abi_version(void) { return LIDFE_ABI_VERSION; }
+long long lidfe_launch_count(void) { return g_launches.load(); }
+
+const char* lidfe_strerror(int rc) {
+  switch (rc) {
+    case LIDFE_OK: return "ok";
+    case LIDFE_E_NULL: return "lidfe: required pointer is NULL";
+    case LIDFE_E_CONFIG: return "lidfe: unsupported front-end configuration (need 16 kHz, 400/160/512 framing, 4<=n_mels<=80)";
+    case LIDFE_E_SHORT: return "lidfe: utterance shorter than one frame (choose a window size that is [2, len])";
+    case LIDFE_E_OFFSETS: return "lidfe: bad segment offsets";
+    case LIDFE_E_ARG: return "lidfe: bad argument";
+    case LIDFE_E_MELBANK: return "lidfe: mel bank row empty or wider than supported";
+    case LIDFE_E_NOMEM: return "lidfe: host allocation failed";
+    default: break;
+  }
+  if (rc > 0) return cudaGetErrorString(static_cast<cudaError_t>(rc));
+  return "lidfe: unknown error";
+}
+
+long long lidfe_num_frames(long long n_samples, const lidfe_config* cfg) {
+  if (!cfg || cfg->frame_len <= 0 || cfg->frame_shift <= 0) return 0;
+  if (n_samples < cfg->frame_len) return 0;
+  return 1 + (n_samples - cfg->frame_len) / cfg->frame_shift;
+}
+
+int lidfe_out_dim(lidfe_handle h) { return h ? h->n_out : 0; }
+
+int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window_host, const float* melbank_host,
+                 const float* dct_host, const float* lifter_host) {
+  if (!out || !cfg || !window_host || !melbank_host) return LIDFE_E_NULL;
+  *out = nullptr;
+  if (cfg->sample_rate != 16000 || cfg->frame_len != kFrameLen || cfg->frame_shift != kFrameShift ||
+      cfg->fft_len != kFftLen || cfg->n_mels < 4 || cfg->n_mels > kMaxMels || cfg->n_ceps < 0 ||
+      cfg->n_ceps > cfg->n_mels || (cfg->in_dtype != LIDFE_IN_F32 && cfg->in_dtype != LIDFE_IN_I16) ||
+      !(cfg->preemph >= 0.f && cfg->preemph <= 1.f))
+    return LIDFE_E_CONFIG;
+  if (cfg->n_ceps > 0 && !dct_host) return LIDFE_E_NULL;
+
+  lidfe_ctx* c = new (std::nothrow) lidfe_ctx();
+  if (!c) return LIDFE_E_NOMEM;
+  memset(c, 0, sizeof(*c));
+  c->cfg = *cfg;
+  c->n_out = cfg->n_ceps > 0 ? cfg->n_ceps : cfg->n_mels;
+
+  // ---- sparsify the dense bank: per mel bin the first non-zero FFT bin and a contiguous run of taps
+  std::vector<int> k0(kMaxMels, 0), cnt(kMaxMels, 0);
+  int maxt = 1;
+  for (int m = 0; m < cfg->n_mels; ++m) {
+    const float* row = melbank_host + static_cast<size_t>(m) * kBins;
+    int first = -1, last = -1;
+    for (int k = 0; k < kBins; ++k)
+      if (row[k] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first < 0) {
+      delete c;
+      return LIDFE_E_MELBANK;
+    }
+    k0[m] = first;
+    cnt[m] = last - first + 1;
+    if (cnt[m] > 64) {
+      delete c;
+      return LIDFE_E_MELBANK;
+    }
+    if (cnt[m] > maxt) maxt = cnt[m];
+  }
+  c->mel_maxt = maxt;
+  std::vector<float> melw(static_cast<size_t>(kBands) * maxt * 16, 0.f);
+  for (int b = 0; b < kBands; ++b) {
+    c->band_taps[b] = 0;
+    for (int t = 0; t < 16; ++t) {
+      const int m = t + 16 * b;
+      if (m >= cfg->n_mels) continue;
+      if (cnt[m] > c->band_taps[b]) c->band_taps[b] = cnt[m];
+      for (int i = 0; i < cnt[m]; ++i)
+        melw[(static_cast<size_t>(b) * maxt + i) * 16 + t] = melbank_host[static_cast<size_t>(m) * kBins + k0[m] + i];
+    }
+  }
+
+  // ---- twiddles, rounded once from fp64
+  std::vector<float2> tw1(256), tw2(128);
+  const double kPi = 3.14159265358979323846;
+  for (int K1 = 0; K1 < 16; ++K1)
+    for (int t = 0; t < 16; ++t) {
+      const double a = -2.0 * kPi * static_cast<double>(K1 * t) / 256.0;
+      tw1[K1 * 16 + t] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+    }
+  for (int i = 0; i < 8; ++i)
+    for (int t = 0; t < 16; ++t) {
+      const double a = -2.0 * kPi * static_cast<double>(t + 16 * i) / 512.0;
+      tw2[i * 16 + t] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+    }
+  std::vector<float> window(512, 0.f);
+  for (int i = 0; i < kFrameLen; ++i) window[i] = window_host[i];
+  std::vector<float> lifter(cfg->n_ceps > 0 ? cfg->n_ceps : 1, 1.f);
+  if (cfg->n_ceps > 0 && lifter_host)
+    for (int i = 0; i < cfg->n_ceps; ++i) lifter[i] = lifter_host[i];
+
+  cudaError_t e = cudaGetDevice(&c->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
+  if (e == cudaSuccess) e = upload(&c->d_window, window.data(), window.size());
+  if (e == cudaSuccess) e = upload(&c->d_tw1, tw1.data(), tw1.size());
+  if (e == cudaSuccess) e = upload(&c->d_tw2, tw2.data(), tw2.size());
+  if (e == cudaSuccess) e = upload(&c->d_melw, melw.data(), melw.size());
+  if (e == cudaSuccess) e = upload(&c->d_k0, k0.data(), k0.size());
+  if (e == cudaSuccess && cfg->n_ceps > 0)
+    e = upload(&c->d_dct, dct_host, static_cast<size_t>(cfg->n_mels) * cfg->n_ceps);
+  if (e == cudaSuccess) e = upload(&c->d_lifter, lifter.data(), lifter.size());
+  if (e == cudaSuccess) {
+    c->smem_bytes = smem_for(*cfg, maxt);
+    fbank_fn fn = pick_kernel(*cfg);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes));
+    if (e == cudaSuccess) {
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, c->smem_bytes);
+      if (e == cudaSuccess) {
+        if (per_sm < 1) per_sm = 1;
+        c->grid_cap = per_sm * c->num_sms;
+      }
+    }
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    lidfe_destroy(c);
+    return static_cast<int>(e);
+  }
+  *out = c;
+  return LIDFE_OK;
+}
+
+int lidfe_destroy(lidfe_handle h) {
+  if (!h) return LIDFE_E_NULL;
+  cudaFree(h->d_window);
+  cudaFree(h->d_tw1);
+  cudaFree(h->d_tw2);
+  cudaFree(h->d_melw);
+  cudaFree(h->d_k0);
+  cudaFree(h->d_dct);
+  cudaFree(h->d_lifter);
+  delete h;
+  return LIDFE_OK;
+}
+
+int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* wav_offsets_host,
+                      const long long* wav_lengths_host, const long long* out_rows_host,
+                      const long long* pad_rows_host) {
+  if (!h || !out || !wav_offsets_host || !wav_lengths_host || !out_rows_host) return LIDFE_E_NULL;
+  *out = nullptr;
+  if (B <= 0) return LIDFE_E_ARG;
+  const size_t in_elt = (h->cfg.in_dtype == LIDFE_IN_I16) ? 2 : 4;
+  std::vector<Tile> tiles;
+  std::vector<long long> frames(B);
+  long long total = 0;
+  for (int i = 0; i < B; ++i) {
+    if (wav_offsets_host[i] < 0 || out_rows_host[i] < 0) return LIDFE_E_OFFSETS;
+    const long long T = lidfe_num_frames(wav_lengths_host[i], &h->cfg);
+    if (T <= 0) return LIDFE_E_SHORT;
+    if (T > 0x7fffffffLL) return LIDFE_E_ARG;
+    frames[i] = T;
+    total += T;
+    const bool aligned = ((static_cast<unsigned long long>(wav_offsets_host[i]) * in_elt) % 16ull) == 0ull;
+    for (long long f = 0; f < T; f += kTileFrames) {
+      Tile tl;
+      tl.wav_off = wav_offsets_host[i] + f * kFrameShift;
+      tl.out_row = out_rows_host[i] + f;
+      tl.nframes = static_cast<int>((T - f) < kTileFrames ? (T - f) : kTileFrames);
+      tl.utt = i;
+      tl.t0 = static_cast<int>(f);
+      tl.aux = aligned ? 1 : 0;
+      tiles.push_back(tl);
+    }
+    if (pad_rows_host) {
+      if (pad_rows_host[i] < T) return LIDFE_E_OFFSETS;
+      for (long long r = T; r < pad_rows_host[i]; r += 4 * kTileFrames) {
+        Tile tl;
+        tl.wav_off = 0;
+        tl.out_row = out_rows_host[i] + r;
+        tl.nframes = 0;
+        tl.utt = i;
+        tl.t0 = static_cast<int>(r);
+        const long long left = pad_rows_host[i] - r;
+        tl.aux = static_cast<int>(left < 4 * kTileFrames ? left : 4 * kTileFrames);
+        tiles.push_back(tl);
+      }
+    }
+  }
+  // int16 bulk copies also need the tile's own offset 16B aligned: 160 samples * 2 B = 320 B -> ok.
+  lidfe_plan_s* p = new (std::nothrow) lidfe_plan_s();
+  if (!p) return LIDFE_E_NOMEM;
+  p->ctx = h;
+  p->B = B;
+  p->total_frames = total;
+  p->n_tiles = static_cast<long long>(tiles.size());
+  p->frames = frames;
+  p->d_tiles = nullptr;
+  p->d_frames = nullptr;
+  p->d_offsets = nullptr;
+  p->d_lengths = nullptr;
+  p->d_utt_stats = nullptr;
+  cudaError_t e = upload(&p->d_tiles, tiles.data(), tiles.size());
+  if (e == cudaSuccess) e = upload(&p->d_frames, frames.data(), frames.size());
+  if (e == cudaSuccess) e = upload(&p->d_offsets, wav_offsets_host, static_cast<size_t>(B));
+  if (e == cudaSuccess) e = upload(&p->d_lengths, wav_lengths_host, static_cast<size_t>(B));
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_stats), static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    lidfe_plan_destroy(p);
+    return static_cast<int>(e);
+  }
+  *out = p;
+  return LIDFE_OK;
+}
+
+int lidfe_plan_destroy(lidfe_plan p) {
+  if (!p) return LIDFE_E_NULL;
+  cudaFree(p->d_tiles);
+  cudaFree(p->d_frames);
+  cudaFree(p->d_offsets);
+  cudaFree(p->d_lengths);
+  cudaFree(p->d_utt_stats);
+  delete p;
+  return LIDFE_OK;
+}
+long long lidfe_plan_total_frames(lidfe_plan p) { return p ? p->total_frames : 0; }
+long long lidfe_plan_num_tiles(lidfe_plan p) { return p ? p->n_tiles : 0; }
+long long lidfe_plan_frames(lidfe_plan p, int i) { return (p && i >= 0 && i < p->B) ? p->frames[i] : 0; }
+
+static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, const int* masks, int n_masks,
+                        const double* utt_stats, const double* glob_stats, cudaStream_t st) {
+  ApplyParams A;
+  A.feats = feats;
+  A.ld = ld;
+  A.tiles = p->d_tiles;
+  A.n_tiles = static_cast<int>(p->n_tiles);
+  A.n_out = h->n_out;
+  A.masks = masks;
+  A.n_masks = masks ? n_masks : 0;
+  A.utt_stats = utt_stats;
+  A.utt_frames = p->d_frames;
+  A.glob_stats = glob_stats;
+  A.normalize = (utt_stats || glob_stats) ? 1 : 0;
+  long long grid = p->n_tiles;
+  const long long cap = static_cast<long long>(h->num_sms) * 8;
+  if (grid > cap) grid = cap;
+  cmvn_apply_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(A);
+  g_launches.fetch_add(1);
+  CU_TRY(cudaGetLastError());
+  return LIDFE_OK;
+}
+
+int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
+                    const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
+                    double* stats_out_dev, void* stream) {
+  if (!h || !p || !wav_dev || !out_dev) return LIDFE_E_NULL;
+  if (p->ctx != h) return LIDFE_E_ARG;
+  if (out_ld < h->n_out || cmvn_mode < 0 || cmvn_mode > 3 || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
+  if (cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL && !stats_in_dev) return LIDFE_E_NULL;
+  if (cmvn_mode == LIDFE_CMVN_ACCUM_GLOBAL && !stats_out_dev) return LIDFE_E_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  FbankParams P;
+  memset(&P, 0, sizeof(P));
+  P.wav = wav_dev;
+  P.out = out_dev;
+  P.out_ld = out_ld;
+  P.tiles = p->d_tiles;
+  P.n_tiles = static_cast<int>(p->n_tiles);
+  P.window = h->d_window;
+  P.tw1 = h->d_tw1;
+  P.tw2 = h->d_tw2;
+  P.mel_w = h->d_melw;
+  P.mel_k0 = h->d_k0;
+  P.dct = h->d_dct;
+  P.lifter = h->d_lifter;
+  P.mel_maxt = h->mel_maxt;
+  for (int b = 0; b < kBands; ++b) P.band_taps[b] = h->band_taps[b];
+  P.n_mels = h->cfg.n_mels;
+  P.n_ceps = h->cfg.n_ceps;
+  P.n_out = h->n_out;
+  P.preemph = h->cfg.preemph;
+  P.log_floor = h->cfg.log_floor;
+  P.in_scale = h->cfg.in_scale;
+  P.remove_dc = h->cfg.remove_dc;
+  P.masks = masks_dev;
+  P.n_masks = masks_dev ? n_masks : 0;
+  P.mode = cmvn_mode;
+  P.stats_in = stats_in_dev;
+  P.stats_out = stats_out_dev;
+  P.utt_stats = p->d_utt_stats;
+
+  if (cmvn_mode == LIDFE_CMVN_PER_UTT)
+    CU_TRY(cudaMemsetAsync(p->d_utt_stats, 0, static_cast<size_t>(p->B) * 2 * h->n_out * sizeof(double), st));
+
+  long long grid = p->n_tiles < h->grid_cap ? p->n_tiles : h->grid_cap;
+  if (grid < 1) grid = 1;
+  fbank_fn fn = pick_kernel(h->cfg);
+  const bool prof = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
+  if (prof) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
+  fn<<<static_cast<unsigned>(grid), kThreads, h->smem_bytes, st>>>(P);
+  g_launches.fetch_add(1);
+  CU_TRY(cudaGetLastError());
+  if (prof) {
+    CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used + 1], st));
+    h->prof_used += 2;
+  }
+
+  if (cmvn_mode == LIDFE_CMVN_PER_UTT)
+    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, p->d_utt_stats, nullptr, st);
+  return LIDFE_OK;
+}
+
+int lidfe_cmvn_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long ld, const int* masks_dev, int n_masks,
+                     const double* stats_dev, void* stream) {
+  if (!h || !p || !feats_dev || !stats_dev) return LIDFE_E_NULL;
+  if (p->ctx != h || ld < h->n_out || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, stats_dev, static_cast<cudaStream_t>(stream));
+}
+
+int lidfe_profile_begin(lidfe_handle h, int max_launches) {
+  if (!h) return LIDFE_E_NULL;
+  if (max_launches <= 0 || h->prof_events) return LIDFE_E_ARG;
+  h->prof_events = new (std::nothrow) std::vector<cudaEvent_t>(static_cast<size_t>(max_launches) * 2);
+  if (!h->prof_events) return LIDFE_E_NOMEM;
+  h->prof_used = 0;
+  for (auto& ev : *h->prof_events) CU_TRY(cudaEventCreate(&ev));
+  return LIDFE_OK;
+}
+
+int lidfe_profile_end(lidfe_handle h, float* ms_host, int capacity, int* n_out) {
+  if (!h || !n_out) return LIDFE_E_NULL;
+  if (!h->prof_events) return LIDFE_E_ARG;
+  const int n = h->prof_used / 2;
+  int rc = LIDFE_OK;
+  for (int i = 0; i < n && rc == LIDFE_OK; ++i) {
+    cudaError_t e = cudaEventSynchronize((*h->prof_events)[2 * i + 1]);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, (*h->prof_events)[2 * i], (*h->prof_events)[2 * i + 1]);
+    if (e != cudaSuccess) rc = static_cast<int>(e);
+    if (ms_host && i < capacity) ms_host[i] = ms;
+  }
+  for (auto& ev : *h->prof_events) cudaEventDestroy(ev);
+  delete h->prof_events;
+  h->prof_events = nullptr;
+  h->prof_used = 0;
+  *n_out = n;
+  return rc;
+}
+
+int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long ld, const int* masks_dev, int n_masks,
+                     void* stream) {
+  if (!h || !p || !feats_dev || !masks_dev) return LIDFE_E_NULL;
+  if (p->ctx != h || ld < h->n_out || n_masks < 1 || n_masks > kMaxMasks) return LIDFE_E_ARG;
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,
+                      float dither, const float* noise_dev, float preemph, void* stream) {
+  if (!h || !p || !wav_in_dev || !wav_out_dev) return LIDFE_E_NULL;
+  if (p->ctx != h || wav_in_dev == wav_out_dev) return LIDFE_E_ARG;
+  if (dither != 0.f && !noise_dev) return LIDFE_E_NULL;
+  WaveParams W;
+  W.in = wav_in_dev;
+  W.out = wav_out_dev;
+  W.offsets = p->d_offsets;
+  W.lengths = p->d_lengths;
+  W.normalize = normalize;
+  W.dither = dither;
+  W.noise = noise_dev;
+  W.preemph = preemph;
+  wave_stages_kernel<<<static_cast<unsigned>(p->B), 512, 0, static_cast<cudaStream_t>(stream)>>>(W);
+  g_launches.fetch_add(1);
+  CU_TRY(cudaGetLastError());
+  return LIDFE_OK;
+}
+
+}  // extern "C"

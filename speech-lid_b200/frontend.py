@@ -1,0 +1,336 @@
+"""Batched, on-device front-end: packed waveforms -> (B, T_max, n_out) features + wav_percents.
+
+This is the host side of the drop-in: it keeps the feature contract of
+``MergedDataset.collate_fn`` (ref: lid/raw_datasets.py:345-365 -- zero padded ``(B, T_max, n_mels)``
+batch plus ``wav_percents = T_i / T_max``) and of ``wav2mel(use_kaildi=True)``
+(ref: lid/audio_processor.py:41-69), and calls the sm_100a kernels through the C ABI in
+``include/lidfe.h``.  PyTorch is only used for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib, tables
+
+CMVN_MODES = {"none": _lib.CMVN_NONE, "utt": _lib.CMVN_PER_UTT, "global_apply": _lib.CMVN_APPLY_GLOBAL,
+              "global_accum": _lib.CMVN_ACCUM_GLOBAL}
+LOG_FLOOR = float(torch.finfo(torch.float32).eps)   # ta: compliance/kaldi.py:22
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _ll_array(values: Sequence[int]):
+    return (C.c_longlong * len(values))(*[int(v) for v in values])
+
+
+@dataclass
+class Plan:
+    """Segment-offset table of one batch (host copy + the device-side tile table inside ``handle``)."""
+    handle: int
+    lengths: List[int]          # samples per utterance
+    offsets: List[int]          # first sample of each utterance inside the packed buffer
+    frames: List[int]           # frames per utterance (kaldi snip_edges)
+    out_rows: List[int]         # output row of frame 0 of each utterance
+    rows: int                   # rows of the output matrix
+    t_max: int                  # longest utterance in frames
+    padded: bool                # (B, T_max, n_out) layout if True, packed (sum T_i, n_out) otherwise
+    total_samples: int          # length of the packed buffer (including alignment gaps)
+    _owner: "FrontEnd" = None
+
+    @property
+    def batch(self) -> int:
+        return len(self.lengths)
+
+    @property
+    def total_frames(self) -> int:
+        return sum(self.frames)
+
+    @property
+    def wav_percents(self) -> torch.Tensor:
+        """T_i / T_max as float32 -- ref: lid/raw_datasets.py:353-354"""
+        return torch.tensor([f / self.t_max for f in self.frames], dtype=torch.float32)
+
+    def close(self) -> None:
+        if self.handle:
+            _lib.load_library().lidfe_plan_destroy(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FrontEnd:
+    """Kaldi-compatible fbank / MFCC + SpecAugment + CMVN on one B200.
+
+    Parameters mirror the ones ``MergedDataset`` forwards to ``wav2mel``
+    (ref: lid/raw_datasets.py:196-210,282-291): ``win_length`` / ``hop_length`` in seconds, ``n_mels``,
+    ``sr``.  ``preemph`` is the per-frame Kaldi coefficient (1.0 in the reference's call,
+    ref: lid/audio_processor.py:60).  ``n_ceps > 0`` selects the MFCC epilogue
+    (ta: compliance/kaldi.py:669-813; the reference itself has no MFCC).
+    """
+
+    def __init__(self, n_mels: int = 80, n_ceps: int = 0, sr: int = 16000, win_length: float = 0.025,
+                 hop_length: float = 0.01, preemph: float = 1.0, cepstral_lifter: float = 22.0,
+                 remove_dc: bool = True, in_dtype: torch.dtype = torch.float32, in_scale: float = 1.0,
+                 device: Union[str, torch.device, None] = None):
+        self.lib = _lib.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("speech_lid_b200.FrontEnd needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if in_dtype not in (torch.float32, torch.int16):
+            raise ValueError("in_dtype must be torch.float32 or torch.int16")
+        # seconds -> milliseconds -> samples exactly as the reference + torchaudio do
+        # (ref: lid/audio_processor.py:50-51; ta: compliance/kaldi.py:138-140)
+        frame_len = int(sr * int(1000 * win_length) * 0.001)
+        frame_shift = int(sr * int(1000 * hop_length) * 0.001)
+        fft_len = 1 if frame_len == 0 else 2 ** (frame_len - 1).bit_length()
+        self.cfg = _lib.LidfeConfig(sample_rate=int(sr), frame_len=frame_len, frame_shift=frame_shift,
+                                    fft_len=fft_len, n_mels=int(n_mels), n_ceps=int(n_ceps),
+                                    preemph=float(preemph), remove_dc=int(bool(remove_dc)),
+                                    log_floor=LOG_FLOOR, in_dtype=_lib.IN_I16 if in_dtype == torch.int16 else _lib.IN_F32,
+                                    in_scale=float(in_scale))
+        self.in_dtype = in_dtype
+        self.n_mels, self.n_ceps = int(n_mels), int(n_ceps)
+        self.n_out = self.n_ceps if self.n_ceps > 0 else self.n_mels
+        self.frame_len, self.frame_shift = frame_len, frame_shift
+        self.align = 8 if in_dtype == torch.int16 else 4     # samples per 16 bytes (TMA bulk copy granularity)
+        if frame_len != 400 or frame_shift != 160 or int(sr) != 16000:
+            _lib.check(_lib.E_CONFIG)
+        window = tables.povey_window(frame_len).contiguous()
+        banks = tables.mel_banks(self.n_mels, fft_len, float(sr)).contiguous()
+        dct = tables.dct_matrix(self.n_ceps, self.n_mels).contiguous() if self.n_ceps > 0 else None
+        lift = tables.lifter(self.n_ceps, cepstral_lifter).contiguous() if self.n_ceps > 0 else None
+        self._tables = (window, banks, dct, lift)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lidfe_create(C.byref(h), C.byref(self.cfg), _ptr(window), _ptr(banks), _ptr(dct),
+                                             _ptr(lift)))
+        self.handle = h.value
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.lidfe_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ measurement hooks
+    def profile_begin(self, max_launches: int) -> None:
+        _lib.check(self.lib.lidfe_profile_begin(self.handle, int(max_launches)))
+
+    def profile_end(self) -> List[float]:
+        """Per-launch durations (ms) of the fused fbank kernel since profile_begin()."""
+        cap = 1 << 16
+        buf = (C.c_float * cap)()
+        n = C.c_int(0)
+        _lib.check(self.lib.lidfe_profile_end(self.handle, buf, cap, C.byref(n)))
+        return [float(buf[i]) for i in range(min(n.value, cap))]
+
+    # ------------------------------------------------------------------ frame arithmetic
+    def num_frames(self, n_samples: int) -> int:
+        """1 + (N - 400) // 160 (0 if N < 400)          ta: compliance/kaldi.py:63-67"""
+        return int(self.lib.lidfe_num_frames(int(n_samples), C.byref(self.cfg)))
+
+    # ------------------------------------------------------------------ planning / packing
+    def make_plan(self, lengths: Sequence[int], padded: bool = True,
+                  offsets: Optional[Sequence[int]] = None, t_max: Optional[int] = None) -> Plan:
+        """Build the segment-offset table for utterances of ``lengths`` samples.  ``offsets`` default to a
+        packing that starts every utterance on a 16-byte boundary (so each tile is one TMA bulk copy)."""
+        lengths = [int(n) for n in lengths]
+        if offsets is None:
+            offsets, pos = [], 0
+            for n in lengths:
+                offsets.append(pos)
+                pos += (n + self.align - 1) // self.align * self.align
+            total = pos
+        else:
+            offsets = [int(o) for o in offsets]
+            total = max(o + n for o, n in zip(offsets, lengths)) if lengths else 0
+        frames = [self.num_frames(n) for n in lengths]
+        for n, f in zip(lengths, frames):
+            if f <= 0:
+                _lib.check(_lib.E_SHORT)
+        if t_max is None:
+            t_max = max(frames)
+        elif t_max < max(frames):
+            raise ValueError("t_max smaller than the longest utterance")
+        if padded:
+            out_rows = [i * t_max for i in range(len(lengths))]
+            rows = len(lengths) * t_max
+            pad_rows = _ll_array([t_max] * len(lengths))
+        else:
+            out_rows, acc = [], 0
+            for f in frames:
+                out_rows.append(acc)
+                acc += f
+            rows = acc
+            pad_rows = None
+        ph = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lidfe_plan_create(self.handle, C.byref(ph), len(lengths), _ll_array(offsets),
+                                                  _ll_array(lengths), _ll_array(out_rows), pad_rows))
+        return Plan(handle=ph.value, lengths=lengths, offsets=offsets, frames=frames, out_rows=out_rows,
+                    rows=rows, t_max=t_max, padded=padded, total_samples=total, _owner=self)
+
+    def pack(self, wavs: Sequence[torch.Tensor], plan: Plan, pinned: Optional[torch.Tensor] = None,
+             stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """Copy a list of (N_i,) / (1, N_i) waveforms (host or device) into one packed device buffer laid out
+        by ``plan``.  Host inputs go through one pinned staging buffer and one H2D copy."""
+        flat = []
+        for w in wavs:
+            if w.dim() == 2:
+                w = w[0]        # channel=-1 -> first channel     ta: compliance/kaldi.py:135-137
+            flat.append(w)
+        if all(w.is_cuda for w in flat):
+            packed = torch.zeros(plan.total_samples, dtype=self.in_dtype, device=self.device)
+            for w, o, n in zip(flat, plan.offsets, plan.lengths):
+                packed[o:o + n].copy_(w.to(self.in_dtype), non_blocking=True)
+            return packed
+        if pinned is None or pinned.numel() < plan.total_samples:
+            pinned = torch.zeros(plan.total_samples, dtype=self.in_dtype).pin_memory()
+        for w, o, n in zip(flat, plan.offsets, plan.lengths):
+            pinned[o:o + n].copy_(w.to(self.in_dtype))
+        return pinned[:plan.total_samples].to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ the hot path
+    def featurize_packed(self, packed: torch.Tensor, plan: Plan, out: Optional[torch.Tensor] = None,
+                         masks: Optional[torch.Tensor] = None, cmvn: str = "none",
+                         stats_in: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
+                         stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """Launch the fused kernel(s) on device-resident packed samples.  Returns ``out``:
+        (B, T_max, n_out) if the plan is padded, (sum T_i, n_out) otherwise."""
+        if packed.dtype != self.in_dtype or not packed.is_cuda or not packed.is_contiguous():
+            raise ValueError("packed must be a contiguous CUDA tensor of dtype %s" % self.in_dtype)
+        if packed.numel() < plan.total_samples:
+            raise ValueError("packed buffer shorter than the plan's extent")
+        if out is None:
+            shape = (plan.batch, plan.t_max, self.n_out) if plan.padded else (plan.rows, self.n_out)
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        if out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous() or out.numel() < plan.rows * self.n_out:
+            raise ValueError("out must be a contiguous float32 CUDA tensor with rows*n_out elements")
+        n_masks = 0
+        if masks is not None:
+            if masks.dtype != torch.int32 or masks.dim() != 3 or masks.shape[0] != plan.batch or masks.shape[2] != 4:
+                raise ValueError("masks must be int32 [B, n_masks, 4]")
+            masks = masks.to(self.device).contiguous()
+            n_masks = masks.shape[1]
+            if n_masks == 0:
+                masks = None
+        for s in (stats_in, stats_out):
+            if s is not None and (s.dtype != torch.float64 or s.numel() != 2 * self.n_out + 1 or not s.is_cuda):
+                raise ValueError("stats tensors must be float64 CUDA tensors of 2*n_out+1 elements")
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lidfe_featurize(self.handle, plan.handle, packed.data_ptr(), out.data_ptr(),
+                                                self.n_out, _ptr(masks), n_masks, CMVN_MODES[cmvn],
+                                                _ptr(stats_in), _ptr(stats_out), st.cuda_stream))
+        return out
+
+    def cmvn_apply(self, feats: torch.Tensor, plan: Plan, stats: torch.Tensor,
+                   masks: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """Second pass of global CMVN, in place: (x - mean) / (std + 1e-9) from the all-reduced sums, then masks."""
+        n_masks = 0
+        if masks is not None:
+            masks = masks.to(self.device).contiguous()
+            n_masks = masks.shape[1]
+            if n_masks == 0:
+                masks = None
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lidfe_cmvn_apply(self.handle, plan.handle, feats.data_ptr(), self.n_out, _ptr(masks),
+                                                 n_masks, stats.data_ptr(), st.cuda_stream))
+        return feats
+
+    def mask_apply(self, feats: torch.Tensor, plan: Plan, masks: torch.Tensor,
+                   stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """Zero-fill [t0,t1) x [f0,f1) bands in place (SpecAugment application, ref: lid/audio_processor.py:225-227)."""
+        masks = masks.to(self.device).contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lidfe_mask_apply(self.handle, plan.handle, feats.data_ptr(), self.n_out,
+                                                 masks.data_ptr(), masks.shape[1], st.cuda_stream))
+        return feats
+
+    def wave_stages(self, packed: torch.Tensor, plan: Plan, normalize: bool = False, dither: float = 0.0,
+                    noise: Optional[torch.Tensor] = None, preemph: float = 0.0,
+                    stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """normalize_wav / dither / 0.97 pre-emphasis over every utterance of a packed float32 buffer
+        (ref: lid/audio_processor.py:108-115,129-134).  Returns a new packed buffer."""
+        if packed.dtype != torch.float32:
+            raise ValueError("wave_stages works on float32 samples")
+        out = torch.zeros_like(packed)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lidfe_wave_stages(self.handle, plan.handle, packed.data_ptr(), out.data_ptr(),
+                                                  int(normalize), float(dither), _ptr(noise), float(preemph),
+                                                  st.cuda_stream))
+        return out
+
+    def featurize_host(self, host_in: torch.Tensor, plan: Plan, host_out: torch.Tensor,
+                       masks: Optional[torch.Tensor] = None, cmvn: str = "none", chunks: int = 4) -> torch.Tensor:
+        """Host-buffer entry (what a CPU-side caller of the reference's ``wav2mel`` sees): ``host_in`` is the packed
+        waveform buffer laid out by ``plan`` in (ideally pinned) host memory, ``host_out`` receives the padded
+        ``(B, T_max, n_out)`` batch.  The batch is cut into ``chunks`` groups of utterances, each on its own stream, so
+        the H2D copy of one group, the kernels of the previous one and the D2H copy of the one before overlap
+        (PCIe is full duplex).  Returns ``host_out`` after synchronising."""
+        if not plan.padded:
+            raise ValueError("featurize_host needs a padded plan")
+        if cmvn not in ("none", "utt"):
+            raise ValueError("featurize_host supports cmvn 'none' or 'utt' (global CMVN needs the all-reduce in between)")
+        B = plan.batch
+        chunks = max(1, min(chunks, B))
+        key = (plan.handle, chunks)
+        cache = self.__dict__.setdefault("_host_cache", {})
+        st = cache.get(key)
+        if st is None:
+            bounds = [(B * c) // chunks for c in range(chunks + 1)]
+            st = []
+            for c in range(chunks):
+                a, b = bounds[c], bounds[c + 1]
+                base = plan.offsets[a]
+                end = plan.offsets[b] if b < B else plan.total_samples
+                sub = self.make_plan(plan.lengths[a:b], padded=True, offsets=[o - base for o in plan.offsets[a:b]],
+                                     t_max=plan.t_max)
+                st.append(dict(a=a, b=b, base=base, end=end, plan=sub, stream=torch.cuda.Stream(self.device),
+                               dev_in=torch.empty(end - base, dtype=self.in_dtype, device=self.device),
+                               dev_out=torch.empty((b - a, plan.t_max, self.n_out), dtype=torch.float32, device=self.device),
+                               dev_masks=None))
+            cache.clear()          # one cached pipeline at a time
+            cache[key] = st
+        cur = torch.cuda.current_stream(self.device)
+        for c in st:
+            s = c["stream"]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                c["dev_in"].copy_(host_in[c["base"]:c["end"]], non_blocking=True)
+                m = None
+                if masks is not None and masks.shape[1] > 0:
+                    m = masks[c["a"]:c["b"]].to(self.device, non_blocking=True)
+                self.featurize_packed(c["dev_in"], c["plan"], out=c["dev_out"], masks=m, cmvn=cmvn, stream=s)
+                host_out[c["a"]:c["b"]].copy_(c["dev_out"], non_blocking=True)
+        for c in st:
+            c["stream"].synchronize()
+        return host_out
+
+    def featurize(self, wavs: Sequence[torch.Tensor], masks: Optional[torch.Tensor] = None, cmvn: str = "none",
+                  padded: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The batched public entry: list of waveforms -> ``(feats, wav_percents)`` with the collate contract
+        (ref: lid/raw_datasets.py:345-365).  ``feats`` stays on the device -- that is where the model consumes it."""
+        lengths = [int(w.shape[-1]) for w in wavs]
+        plan = self.make_plan(lengths, padded=padded)
+        packed = self.pack(wavs, plan)
+        out = self.featurize_packed(packed, plan, masks=masks, cmvn=cmvn)
+        return out, plan.wav_percents     # plan teardown (cudaFree) waits for the launched work

@@ -1,0 +1,70 @@
+"""Host-side constant tables, built once per FrontEnd with the same fp32 torch CPU arithmetic the
+reference runs on every call, so the device kernels read bit-identical tables.
+
+ta: = path inside torchaudio (the library the reference's ``_kaidi_wav2mel`` calls,
+ref: lid/audio_processor.py:41-69).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def povey_window(frame_len: int) -> torch.Tensor:
+    """Kaldi's default window: hann(periodic=False) ** 0.85.   ta: compliance/kaldi.py:98-100"""
+    return torch.hann_window(frame_len, periodic=False, dtype=torch.float32).pow(0.85)
+
+
+def _mel(freq):
+    return 1127.0 * math.log(1.0 + freq / 700.0)
+
+
+def mel_banks(n_mels: int, fft_len: int, sample_rate: float, low_freq: float = 20.0,
+              high_freq: float = 0.0) -> torch.Tensor:
+    """Dense (n_mels, fft_len/2 + 1) triangular filters on the Kaldi mel scale, vtln_warp = 1, last
+    (Nyquist) column zero.                                        ta: compliance/kaldi.py:436-511,621-630
+
+    The expression order below is the one torchaudio evaluates (python floats for the scalar edges,
+    fp32 tensors for everything broadcast), which is what fixes the fp32 rounding of every weight."""
+    if n_mels <= 3:
+        raise AssertionError("Must have at least 3 mel bins")
+    nyquist = 0.5 * sample_rate
+    if high_freq <= 0.0:
+        high_freq += nyquist
+    if not (0.0 <= low_freq < nyquist and 0.0 < high_freq <= nyquist and low_freq < high_freq):
+        raise AssertionError("Bad values in options: low-freq {} and high-freq {} vs. nyquist {}".format(
+            low_freq, high_freq, nyquist))
+    bin_width = sample_rate / fft_len
+    lo, hi = _mel(low_freq), _mel(high_freq)
+    step = (hi - lo) / (n_mels + 1)
+    idx = torch.arange(n_mels).unsqueeze(1)
+    left_edge = lo + idx * step
+    peak = lo + (idx + 1.0) * step
+    right_edge = lo + (idx + 2.0) * step
+    fft_mel = (1127.0 * (1.0 + (bin_width * torch.arange(fft_len / 2)) / 700.0).log()).unsqueeze(0)
+    rising = (fft_mel - left_edge) / (peak - left_edge)
+    falling = (right_edge - fft_mel) / (right_edge - peak)
+    tri = torch.max(torch.zeros(1), torch.min(rising, falling))
+    return torch.nn.functional.pad(tri, (0, 1), mode="constant", value=0).contiguous()
+
+
+def dct_matrix(n_ceps: int, n_mels: int) -> torch.Tensor:
+    """(n_mels, n_ceps) orthonormal DCT-II whose first column is sqrt(1/n_mels).
+    ta: compliance/kaldi.py:648-658, functional/functional.py:636-667"""
+    pos = torch.arange(float(n_mels))
+    order = torch.arange(float(n_mels)).unsqueeze(1)
+    basis = torch.cos(math.pi / float(n_mels) * (pos + 0.5) * order)
+    basis[0] *= 1.0 / math.sqrt(2.0)
+    basis *= math.sqrt(2.0 / float(n_mels))
+    basis = basis.t().clone()
+    basis[:, 0] = math.sqrt(1 / float(n_mels))
+    return basis[:, :n_ceps].contiguous()
+
+
+def lifter(n_ceps: int, cepstral_lifter: float) -> torch.Tensor:
+    """1 + 0.5 L sin(pi i / L); ones when L == 0.               ta: compliance/kaldi.py:661-666,793-796"""
+    if cepstral_lifter == 0.0:
+        return torch.ones(n_ceps, dtype=torch.float32)
+    i = torch.arange(n_ceps)
+    return (1.0 + 0.5 * cepstral_lifter * torch.sin(math.pi * i / cepstral_lifter)).to(torch.float32)
