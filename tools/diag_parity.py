@@ -28,3 +28,13 @@ for kind, gen in (("noise", O.synth_noise), ("speech", O.synth_speechlike)):
         print(kind, seed, json.dumps(r))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/diag_parity.json", "w"), indent=1)
+# RMS view of the same comparison
+for kind, gen in (("noise", O.synth_noise),):
+    for seed in range(3):
+        x = gen(128000, 10 + seed)
+        got = fe.featurize([x])[0][0].cpu().double()
+        ref = O.kaldi_fbank(x).double(); tru = O.truth64_fbank(x)
+        for a, b in ((0, 3), (3, 10), (10, 80)):
+            print("rms", kind, seed, (a, b), "gpu %.3g ref %.3g gpu-vs-ref %.3g" % (
+                (got - tru)[:, a:b].pow(2).mean().sqrt(), (ref - tru)[:, a:b].pow(2).mean().sqrt(),
+                (got - ref)[:, a:b].pow(2).mean().sqrt()))
