@@ -97,6 +97,14 @@ long long lidfe_num_frames(long long n_samples, const lidfe_config* cfg);
 /* Output feature dimension: n_ceps if n_ceps > 0 else n_mels. */
 int lidfe_out_dim(lidfe_handle h);
 
+/*
+ * Host-only helper (no device needed): how lidfe_create sparsifies a dense (n_mels x 257) bank.  For every mel bin
+ * its first non-zero FFT bin, its tap count, and the (possibly earlier) first tap the kernel reads so that the 16
+ * lanes of a band hit 16 distinct shared-memory bank pairs; band_taps_out[5] = tap steps per band of 16 bins.
+ */
+int lidfe_mel_plan(int n_mels, const float* melbank_host, int* first_bin_out, int* num_taps_out, int* start_out,
+                   int* band_taps_out);
+
 /* -- plan: the segment-offset table of one batch -------------------------------------------------- */
 
 /*

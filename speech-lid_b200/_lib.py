@@ -20,7 +20,7 @@ EXPORTS = (
     "lidfe_create", "lidfe_destroy", "lidfe_num_frames", "lidfe_out_dim", "lidfe_plan_create",
     "lidfe_plan_destroy", "lidfe_plan_total_frames", "lidfe_plan_num_tiles", "lidfe_plan_frames",
     "lidfe_featurize", "lidfe_cmvn_apply", "lidfe_wave_stages", "lidfe_mask_apply", "lidfe_strerror",
-    "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end",
+    "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_mel_plan",
 )
 
 
@@ -82,6 +82,9 @@ def load_library() -> C.CDLL:
     lib.lidfe_profile_begin.restype = i32
     lib.lidfe_profile_end.argtypes = [vp, C.POINTER(C.c_float), i32, C.POINTER(C.c_int)]
     lib.lidfe_profile_end.restype = i32
+    pi = C.POINTER(C.c_int)
+    lib.lidfe_mel_plan.argtypes = [i32, vp, pi, pi, pi, pi]
+    lib.lidfe_mel_plan.restype = i32
     lib.lidfe_strerror.argtypes = [i32]
     lib.lidfe_strerror.restype = C.c_char_p
     lib.lidfe_abi_version.argtypes = []

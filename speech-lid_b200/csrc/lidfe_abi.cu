@@ -21,8 +21,8 @@ struct lidfe_ctx {
   int device;
   int num_sms;
   int n_out;
-  int mel_maxt;
   int band_taps[kBands];
+  int std_mel;    // band_taps == kStdTaps -> fully unrolled mel loop
   // device tables
   float* d_window;
   float2* d_tw1;
@@ -46,6 +46,8 @@ struct lidfe_plan_s {
   std::vector<long long> frames;
   Tile* d_tiles;
   long long* d_frames;    // [B]
+  long long* d_out_rows;  // [B]
+  long long max_frames;
   long long* d_offsets;   // [B]
   long long* d_lengths;   // [B]
   double* d_utt_stats;    // [B][2][n_out]
@@ -70,16 +72,104 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 }
 
 typedef void (*fbank_fn)(const FbankParams);
-static fbank_fn pick_kernel(const lidfe_config& c) {
-  const bool mfcc = c.n_ceps > 0;
-  if (c.in_dtype == LIDFE_IN_I16) return mfcc ? fbank_kernel<short, true> : fbank_kernel<short, false>;
-  return mfcc ? fbank_kernel<float, true> : fbank_kernel<float, false>;
+template <typename TIn>
+static fbank_fn pick_kernel_t(bool mfcc, bool std_mel) {
+  if (mfcc) return std_mel ? fbank_kernel<TIn, true, true> : fbank_kernel<TIn, true, false>;
+  return std_mel ? fbank_kernel<TIn, false, true> : fbank_kernel<TIn, false, false>;
 }
-static size_t smem_for(const lidfe_config& c, int maxt) {
+static fbank_fn pick_kernel(const lidfe_ctx* c) {
+  const bool mfcc = c->cfg.n_ceps > 0;
+  return c->cfg.in_dtype == LIDFE_IN_I16 ? pick_kernel_t<short>(mfcc, c->std_mel != 0)
+                                         : pick_kernel_t<float>(mfcc, c->std_mel != 0);
+}
+static size_t smem_for(const lidfe_config& c, int total_taps) {
   const size_t base = (c.in_dtype == LIDFE_IN_I16) ? SmemLayout<short>::off_melw : SmemLayout<float>::off_melw;
-  size_t extra = static_cast<size_t>(kBands) * maxt * 16;
+  size_t extra = static_cast<size_t>(total_taps) * 16;
   if (c.n_ceps > 0) extra += static_cast<size_t>(c.n_mels) * c.n_ceps + c.n_ceps;
   return base + extra * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Mel tap placement.  In the kernel the 16 lanes of a half-warp read, at tap step i, the power pairs P[start_t + i]
+// (8 bytes each) of "their" filter of the band.  Two lanes collide in shared memory when their starts differ but are
+// congruent mod 16 (same bank pair, different address).  A filter with cnt taps can start anywhere in
+// [k0 + cnt - T, k0] when the band runs T >= cnt steps (leading / trailing weights are zero), so for each band we look
+// for the smallest T and a set of starts without such collisions (lanes sharing the SAME start are a broadcast).
+// Small bounded search: residue classes are claimed by a start value; a lane may evict a class if every evicted lane
+// can be re-seated (depth <= 3).
+// ------------------------------------------------------------------------------------------------------------------
+struct TapPlacer {
+  int lo[16], hi[16], choice[16], n;
+  int cls_start[16];                 // start value owning residue class r, or -1
+  std::vector<int> cls_lanes[16];
+
+  bool place(int l, int depth, unsigned banned) {
+    for (int s = hi[l]; s >= lo[l]; --s) {
+      const int r = s & 15;
+      if (banned & (1u << r)) continue;
+      if (cls_start[r] < 0) { cls_start[r] = s; cls_lanes[r].assign(1, l); choice[l] = s; return true; }
+      if (cls_start[r] == s) { cls_lanes[r].push_back(l); choice[l] = s; return true; }
+    }
+    if (depth >= 3) return false;
+    for (int s = hi[l]; s >= lo[l]; --s) {
+      const int r = s & 15;
+      if (banned & (1u << r)) continue;
+      const int old_start = cls_start[r];
+      const std::vector<int> old_lanes = cls_lanes[r];
+      cls_start[r] = s; cls_lanes[r].assign(1, l); choice[l] = s;
+      bool ok = true;
+      std::vector<int> seated;
+      for (int x : old_lanes) {
+        if (place(x, depth + 1, banned | (1u << r))) seated.push_back(x);
+        else { ok = false; break; }
+      }
+      if (ok) return true;
+      for (int x : seated) {             // undo
+        const int rr = choice[x] & 15;
+        std::vector<int>& v = cls_lanes[rr];
+        for (size_t q = 0; q < v.size(); ++q) if (v[q] == x) { v.erase(v.begin() + q); break; }
+        if (v.empty()) cls_start[rr] = -1;
+      }
+      cls_start[r] = old_start; cls_lanes[r] = old_lanes;
+      for (int x : old_lanes) choice[x] = old_start;
+    }
+    return false;
+  }
+  bool run() {
+    for (int r = 0; r < 16; ++r) { cls_start[r] = -1; cls_lanes[r].clear(); }
+    for (int l = 0; l < n; ++l) if (!place(l, 0, 0u)) return false;
+    return true;
+  }
+};
+
+// starts[m], band_taps[b] for all bands; falls back to start = k0 (correct, bank-conflicted) if the search fails
+static void place_taps(int n_mels, const int* k0, const int* cnt, int* starts, int* band_taps) {
+  for (int b = 0; b < kBands; ++b) {
+    band_taps[b] = 0;
+    const int m0 = 16 * b, m1 = (n_mels < m0 + 16) ? n_mels : m0 + 16;
+    if (m1 <= m0) continue;
+    int mx = 0;
+    for (int m = m0; m < m1; ++m) mx = cnt[m] > mx ? cnt[m] : mx;
+    bool done = false;
+    for (int T = mx; T <= mx + 8 && !done; ++T) {
+      TapPlacer tp;
+      tp.n = m1 - m0;
+      for (int m = m0; m < m1; ++m) {
+        const int l = k0[m] + cnt[m] - T;
+        tp.lo[m - m0] = l > 0 ? l : 0;
+        tp.hi[m - m0] = k0[m];
+      }
+      if (tp.run()) {
+        for (int m = m0; m < m1; ++m) starts[m] = tp.choice[m - m0];
+        band_taps[b] = T;
+        done = true;
+      }
+    }
+    if (!done) {
+      for (int m = m0; m < m1; ++m) starts[m] = k0[m];
+      band_taps[b] = mx;
+    }
+  }
 }
 
 extern "C" {
@@ -110,6 +200,32 @@ long long lidfe_num_frames(long long n_samples, const lidfe_config* cfg) {
 }
 
 int lidfe_out_dim(lidfe_handle h) { return h ? h->n_out : 0; }
+
+int lidfe_mel_plan(int n_mels, const float* melbank_host, int* first_bin_out, int* num_taps_out, int* start_out,
+                   int* band_taps_out) {
+  if (!melbank_host || !first_bin_out || !num_taps_out || !start_out || !band_taps_out) return LIDFE_E_NULL;
+  if (n_mels < 4 || n_mels > kMaxMels) return LIDFE_E_CONFIG;
+  std::vector<int> k0(kMaxMels, 0), cnt(kMaxMels, 0), starts(kMaxMels, 0);
+  for (int m = 0; m < n_mels; ++m) {
+    const float* row = melbank_host + static_cast<size_t>(m) * kBins;
+    int first = -1, last = -1;
+    for (int k = 0; k < kBins; ++k)
+      if (row[k] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first < 0 || last - first + 1 > 64) return LIDFE_E_MELBANK;
+    k0[m] = first;
+    cnt[m] = last - first + 1;
+  }
+  place_taps(n_mels, k0.data(), cnt.data(), starts.data(), band_taps_out);
+  for (int m = 0; m < n_mels; ++m) {
+    first_bin_out[m] = k0[m];
+    num_taps_out[m] = cnt[m];
+    start_out[m] = starts[m];
+  }
+  return LIDFE_OK;
+}
 
 int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window_host, const float* melbank_host,
                  const float* dct_host, const float* lifter_host) {
@@ -151,18 +267,33 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
     }
     if (cnt[m] > maxt) maxt = cnt[m];
   }
-  c->mel_maxt = maxt;
-  std::vector<float> melw(static_cast<size_t>(kBands) * maxt * 16, 0.f);
+  (void)maxt;
+  // per band b (output dims t + 16 b): [taps_b][16] weights, bands back to back, filter m's taps starting at
+  // starts[m] <= k0[m] (see place_taps).  The kernel leaves the power bins scaled by 4 (it skips the 1/2 of the
+  // real-FFT split), so the weights carry the exact factor 1/4.
+  std::vector<int> starts(kMaxMels, 0);
+  place_taps(cfg->n_mels, k0.data(), cnt.data(), starts.data(), c->band_taps);
+  int total_taps = 0;
+  c->std_mel = 1;
   for (int b = 0; b < kBands; ++b) {
-    c->band_taps[b] = 0;
-    for (int t = 0; t < 16; ++t) {
-      const int m = t + 16 * b;
-      if (m >= cfg->n_mels) continue;
-      if (cnt[m] > c->band_taps[b]) c->band_taps[b] = cnt[m];
-      for (int i = 0; i < cnt[m]; ++i)
-        melw[(static_cast<size_t>(b) * maxt + i) * 16 + t] = melbank_host[static_cast<size_t>(m) * kBins + k0[m] + i];
+    if (c->band_taps[b] != std_taps(b)) c->std_mel = 0;
+    total_taps += c->band_taps[b];
+  }
+  std::vector<float> melw(static_cast<size_t>(total_taps > 0 ? total_taps : 1) * 16, 0.f);
+  {
+    int off = 0;
+    for (int b = 0; b < kBands; ++b) {
+      for (int t = 0; t < 16; ++t) {
+        const int m = t + 16 * b;
+        if (m >= cfg->n_mels) continue;
+        for (int i = 0; i < cnt[m]; ++i)
+          melw[(static_cast<size_t>(off) + (k0[m] - starts[m]) + i) * 16 + t] =
+              0.25f * melbank_host[static_cast<size_t>(m) * kBins + k0[m] + i];
+      }
+      off += c->band_taps[b];
     }
   }
+  k0 = starts;   // the kernel's per-filter first tap
 
   // ---- twiddles, rounded once from fp64
   std::vector<float2> tw1(256), tw2(128);
@@ -177,7 +308,7 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
       const double a = -2.0 * kPi * static_cast<double>(t + 16 * i) / 512.0;
       tw2[i * 16 + t] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
     }
-  std::vector<float> window(512, 0.f);
+  std::vector<float> window(416, 0.f);
   for (int i = 0; i < kFrameLen; ++i) window[i] = window_host[i];
   std::vector<float> lifter(cfg->n_ceps > 0 ? cfg->n_ceps : 1, 1.f);
   if (cfg->n_ceps > 0 && lifter_host)
@@ -194,8 +325,8 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
     e = upload(&c->d_dct, dct_host, static_cast<size_t>(cfg->n_mels) * cfg->n_ceps);
   if (e == cudaSuccess) e = upload(&c->d_lifter, lifter.data(), lifter.size());
   if (e == cudaSuccess) {
-    c->smem_bytes = smem_for(*cfg, maxt);
-    fbank_fn fn = pick_kernel(*cfg);
+    c->smem_bytes = smem_for(*cfg, total_taps);
+    fbank_fn fn = pick_kernel(c);
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes));
     if (e == cudaSuccess) {
       int per_sm = 0;
@@ -281,11 +412,15 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   p->frames = frames;
   p->d_tiles = nullptr;
   p->d_frames = nullptr;
+  p->d_out_rows = nullptr;
+  p->max_frames = 0;
+  for (int i = 0; i < B; ++i) p->max_frames = frames[i] > p->max_frames ? frames[i] : p->max_frames;
   p->d_offsets = nullptr;
   p->d_lengths = nullptr;
   p->d_utt_stats = nullptr;
   cudaError_t e = upload(&p->d_tiles, tiles.data(), tiles.size());
   if (e == cudaSuccess) e = upload(&p->d_frames, frames.data(), frames.size());
+  if (e == cudaSuccess) e = upload(&p->d_out_rows, out_rows_host, static_cast<size_t>(B));
   if (e == cudaSuccess) e = upload(&p->d_offsets, wav_offsets_host, static_cast<size_t>(B));
   if (e == cudaSuccess) e = upload(&p->d_lengths, wav_lengths_host, static_cast<size_t>(B));
   if (e == cudaSuccess)
@@ -303,6 +438,7 @@ int lidfe_plan_destroy(lidfe_plan p) {
   if (!p) return LIDFE_E_NULL;
   cudaFree(p->d_tiles);
   cudaFree(p->d_frames);
+  cudaFree(p->d_out_rows);
   cudaFree(p->d_offsets);
   cudaFree(p->d_lengths);
   cudaFree(p->d_utt_stats);
@@ -318,19 +454,18 @@ static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, 
   ApplyParams A;
   A.feats = feats;
   A.ld = ld;
-  A.tiles = p->d_tiles;
-  A.n_tiles = static_cast<int>(p->n_tiles);
   A.n_out = h->n_out;
   A.masks = masks;
   A.n_masks = masks ? n_masks : 0;
   A.utt_stats = utt_stats;
   A.utt_frames = p->d_frames;
+  A.utt_out_row = p->d_out_rows;
   A.glob_stats = glob_stats;
   A.normalize = (utt_stats || glob_stats) ? 1 : 0;
-  long long grid = p->n_tiles;
-  const long long cap = static_cast<long long>(h->num_sms) * 8;
-  if (grid > cap) grid = cap;
-  cmvn_apply_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(A);
+  const long long chunks = (p->max_frames + kApplyRows - 1) / kApplyRows;
+  if (chunks > 65535) return LIDFE_E_ARG;
+  dim3 grid(static_cast<unsigned>(p->B), static_cast<unsigned>(chunks));
+  cmvn_apply_kernel<<<grid, 256, 0, st>>>(A);
   g_launches.fetch_add(1);
   CU_TRY(cudaGetLastError());
   return LIDFE_OK;
@@ -360,13 +495,13 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   P.mel_k0 = h->d_k0;
   P.dct = h->d_dct;
   P.lifter = h->d_lifter;
-  P.mel_maxt = h->mel_maxt;
   for (int b = 0; b < kBands; ++b) P.band_taps[b] = h->band_taps[b];
   P.n_mels = h->cfg.n_mels;
   P.n_ceps = h->cfg.n_ceps;
   P.n_out = h->n_out;
   P.preemph = h->cfg.preemph;
   P.log_floor = h->cfg.log_floor;
+  P.log_of_floor = logf(h->cfg.log_floor);
   P.in_scale = h->cfg.in_scale;
   P.remove_dc = h->cfg.remove_dc;
   P.masks = masks_dev;
@@ -381,7 +516,7 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
 
   long long grid = p->n_tiles < h->grid_cap ? p->n_tiles : h->grid_cap;
   if (grid < 1) grid = 1;
-  fbank_fn fn = pick_kernel(h->cfg);
+  fbank_fn fn = pick_kernel(h);
   const bool prof = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
   if (prof) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
   fn<<<static_cast<unsigned>(grid), kThreads, h->smem_bytes, st>>>(P);

@@ -5,12 +5,16 @@
 //   zero-pad to 512 -> |rfft|^2 -> sparse triangular mel -> log(max(., eps)) [-> DCT + lifter] ->
 //   [global CMVN] -> [SpecAugment zero-fill] -> out, plus per-utterance / global sum & sum-of-squares.
 //
-// Mapping: one persistent CTA of 8 warps loops over tiles of <= 32 consecutive frames of one utterance.
-// The tile's 160*F+240 samples are staged into shared memory by ONE TMA bulk copy (cp.async.bulk +
-// mbarrier), double buffered so the next tile's copy overlaps this tile's math.  A half-warp (16 lanes)
-// owns one frame: the 512-point real FFT is a 256-point complex FFT of z[n] = x[2n] + i x[2n+1] done as
-// 16 x 16 (two in-register radix-4x4 16-point DFTs per lane, one shared-memory transpose in between),
-// followed by the real-FFT split which pairs lane t with lane 16-t through warp shuffles.
+// Mapping (v2, "frame-pair packed"): a persistent CTA of 4 warps walks a contiguous range of tiles of <= 16
+// consecutive frames of one utterance.  A tile's 160*F+240 samples are staged into shared memory by ONE TMA
+// bulk copy (cp.async.bulk + mbarrier), double buffered so the next tile's copy overlaps this tile's math.
+// A half-warp (16 lanes) owns TWO adjacent frames (A, B) and carries them as the two halves of Blackwell's
+// packed f32x2 registers: every add / mul / fma of the FFT is one FADD2 / FMUL2 / FFMA2 for both frames, and
+// every table value (window, twiddles, mel weights) is loaded once and broadcast to both.  The 512-point real
+// FFT is a 256-point complex FFT of z[n] = x[2n] + i x[2n+1] done as 16 x 16 (two in-register radix-4x4
+// 16-point DFTs per lane, one shared-memory transpose in between) followed by the real-FFT split, which pairs
+// lane t with lane 16-t through warp shuffles.  Shared-memory wavefronts + shuffles (one shared pipe,
+// 1 wavefront/clk/SM measured) are the binding resource, not FP32 issue: see DESIGN.md.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,18 +25,23 @@ constexpr int kFrameLen = 400;
 constexpr int kFrameShift = 160;
 constexpr int kFftLen = 512;
 constexpr int kBins = kFftLen / 2 + 1;            // 257
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kFramesPerRound = kWarps * 2;       // one frame per half-warp
-constexpr int kTileFrames = 32;
-constexpr int kTileSamples = kFrameShift * kTileFrames + (kFrameLen - kFrameShift);   // 5360
+constexpr int kTileFrames = kWarps * 4;           // two frames per half-warp
+constexpr int kTileSamples = kFrameShift * kTileFrames + (kFrameLen - kFrameShift);   // 2800
 constexpr int kTileSamplesPad = kTileSamples + 32;
 constexpr int kMaxMels = 80;
-constexpr int kBands = kMaxMels / 16;             // lane t owns mel bins t + 16*b
-constexpr int kRowStride = 18;                    // float2 per transpose row (16 + 2 pad -> LDS.128 conflict free)
-constexpr int kScratchFloats = 16 * kRowStride * 2;   // 576 floats per frame
-constexpr int kLogmelOff = 272;                   // log-mel staging (MFCC) lives after the 257 power bins
+constexpr int kBands = kMaxMels / 16;             // lane t owns output dims t + 16*b
+constexpr int kRowStride = 18;                    // (A,B) pairs per transpose row: 16 + 2 pad -> LDS.128 conflict free
+constexpr int kPlaneFloats = 16 * kRowStride * 2; // one plane (re or im) of a frame pair: 576 floats
+constexpr int kScratchFloats = 2 * kPlaneFloats;  // per half-warp: re plane + im plane (reused for the power bins)
+constexpr int kLogmelOff = 640;                   // MFCC log-mel staging (80 pairs) behind the 257 power pairs
+constexpr int kValsOff = 960;                     // final feature pairs parked for the statistics pass (80 pairs)
 constexpr int kMaxMasks = 8;
+constexpr int kTileCache = 48;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
+// taps per band of the 80-mel / 16 kHz / 512 Kaldi bank
+// (after the host shifts each filter's first tap so that the 16 lanes of a band read 16 distinct bank pairs)
+__host__ __device__ constexpr int std_taps(int b) { return b == 0 ? 3 : b == 1 ? 5 : b == 2 ? 6 : b == 3 ? 10 : 17; }
 
 struct Tile {
   long long wav_off;    // first sample of the tile's first frame in the packed buffer
@@ -50,17 +59,16 @@ struct FbankParams {
   const Tile* tiles;
   int n_tiles;
   // constant tables (device)
-  const float* window;      // [512] zero padded
+  const float* window;      // [416] zero padded
   const float2* tw1;        // [16][16]  W256^(K1*t)
   const float2* tw2;        // [8][16]   W512^(t+16i)
-  const float* mel_w;       // [kBands][maxt][16]
+  const float* mel_w;       // per band, [taps_b][16] (x 0.25: the power bins are left scaled by 4)
   const int* mel_k0;        // [kBands*16]
   const float* dct;         // [n_mels][n_ceps]
   const float* lifter;      // [n_ceps] (ones when no liftering)
-  int mel_maxt;             // taps stride per band
-  int band_taps[kBands];    // max taps per band
+  int band_taps[kBands];    // taps per band
   int n_mels, n_ceps, n_out;
-  float preemph, log_floor, in_scale;
+  float preemph, log_floor, log_of_floor, in_scale;   // log_of_floor = logf(log_floor), rounded on the host
   int remove_dc;
   // epilogue
   const int* masks;         // [B][n_masks][4]
@@ -104,62 +112,96 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
-__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// (a.x + i a.y) * (w.x + i w.y)
-__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-  return make_float2(fmaf(a.x, w.x, -(a.y * w.y)), fmaf(a.x, w.y, a.y * w.x));
+// ---- packed f32x2 arithmetic: .x = frame A, .y = frame B (SASS: FADD2 / FMUL2 / FFMA2) ---------------
+typedef float2 f2;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 bc(float s) { return make_float2(s, s); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+
+// (R + iI) *= (wr + i wi), both frames at once, one scalar twiddle
+__device__ __forceinline__ void cmul2(f2& R, f2& I, float wr, float wi) {
+  const f2 nr = fma2(R, bc(wr), mul2(I, bc(-wi)));
+  const f2 ni = fma2(R, bc(wi), mul2(I, bc(wr)));
+  R = nr;
+  I = ni;
 }
 
-// forward 4-point DFT, outputs in natural order
-__device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float2& a3) {
-  float2 t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = a1 - a3;
-  a0 = t0 + t2;
-  a2 = t0 - t2;
-  a1 = make_float2(t1.x + t3.y, t1.y - t3.x);
-  a3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+// forward 4-point DFT on (R,I) pairs, outputs in natural order
+__device__ __forceinline__ void radix4(f2& r0, f2& i0, f2& r1, f2& i1, f2& r2, f2& i2, f2& r3, f2& i3) {
+  const f2 t0r = add2(r0, r2), t0i = add2(i0, i2), t1r = sub2(r0, r2), t1i = sub2(i0, i2);
+  const f2 t2r = add2(r1, r3), t2i = add2(i1, i3), t3r = sub2(r1, r3), t3i = sub2(i1, i3);
+  r0 = add2(t0r, t2r);
+  i0 = add2(t0i, t2i);
+  r2 = sub2(t0r, t2r);
+  i2 = sub2(t0i, t2i);
+  r1 = add2(t1r, t3i);
+  i1 = sub2(t1i, t3r);
+  r3 = sub2(t1r, t3i);
+  i3 = add2(t1i, t3r);
 }
-// same with a3 == 0 on input (zero padding of the 400-sample frame to 512)
-__device__ __forceinline__ void radix4_z3(float2& a0, float2& a1, float2& a2, float2& a3) {
-  float2 t0 = a0 + a2, t1 = a0 - a2;
-  float2 t = a1;
-  a0 = t0 + t;
-  a2 = t0 - t;
-  a1 = make_float2(t1.x + t.y, t1.y - t.x);
-  a3 = make_float2(t1.x - t.y, t1.y + t.x);
+// same with input 3 == 0 (zero padding of the 400-sample frame to 512)
+__device__ __forceinline__ void radix4_z3(f2& r0, f2& i0, f2& r1, f2& i1, f2& r2, f2& i2, f2& r3, f2& i3) {
+  const f2 t0r = add2(r0, r2), t0i = add2(i0, i2), t1r = sub2(r0, r2), t1i = sub2(i0, i2);
+  const f2 ur = r1, ui = i1;
+  r0 = add2(t0r, ur);
+  i0 = add2(t0i, ui);
+  r2 = sub2(t0r, ur);
+  i2 = sub2(t0i, ui);
+  r1 = add2(t1r, ui);
+  i1 = sub2(t1i, ur);
+  r3 = sub2(t1r, ui);
+  i3 = add2(t1i, ur);
 }
 
-// forward 16-point DFT in registers: 4x4 radix-4.  In: v[n] natural.  Out: v[p] = X[rev4(p)],
-// rev4(p) = (p >> 2) + 4 * (p & 3).  kTailZero: v[13], v[14], v[15] are known zeros.
+// forward 16-point DFT in registers: 4x4 radix-4.  In: natural order.  Out: position p holds X[rev4(p)],
+// rev4(p) = (p >> 2) + 4 * (p & 3).  kTailZero: inputs 13, 14, 15 are known zeros.
 template <bool kTailZero>
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+__device__ __forceinline__ void fft16(f2 (&R)[16], f2 (&I)[16]) {
   constexpr float kC1 = 0.92387953251128674f;   // cos(pi/8)
   constexpr float kS1 = 0.38268343236508977f;   // sin(pi/8)
   constexpr float kH = 0.70710678118654752f;    // sqrt(1/2)
-  radix4(v[0], v[4], v[8], v[12]);
+  radix4(R[0], I[0], R[4], I[4], R[8], I[8], R[12], I[12]);
   if (kTailZero) {
-    radix4_z3(v[1], v[5], v[9], v[13]);
-    radix4_z3(v[2], v[6], v[10], v[14]);
-    radix4_z3(v[3], v[7], v[11], v[15]);
+    radix4_z3(R[1], I[1], R[5], I[5], R[9], I[9], R[13], I[13]);
+    radix4_z3(R[2], I[2], R[6], I[6], R[10], I[10], R[14], I[14]);
+    radix4_z3(R[3], I[3], R[7], I[7], R[11], I[11], R[15], I[15]);
   } else {
-    radix4(v[1], v[5], v[9], v[13]);
-    radix4(v[2], v[6], v[10], v[14]);
-    radix4(v[3], v[7], v[11], v[15]);
+    radix4(R[1], I[1], R[5], I[5], R[9], I[9], R[13], I[13]);
+    radix4(R[2], I[2], R[6], I[6], R[10], I[10], R[14], I[14]);
+    radix4(R[3], I[3], R[7], I[7], R[11], I[11], R[15], I[15]);
   }
-  // v[n2 + 4*k1] *= W16^(n2*k1)
-  v[5] = cmul(v[5], make_float2(kC1, -kS1));                               // W^1
-  v[9] = make_float2((v[9].x + v[9].y) * kH, (v[9].y - v[9].x) * kH);      // W^2
-  v[13] = cmul(v[13], make_float2(kS1, -kC1));                             // W^3
-  v[6] = make_float2((v[6].x + v[6].y) * kH, (v[6].y - v[6].x) * kH);      // W^2
-  v[10] = make_float2(v[10].y, -v[10].x);                                  // W^4 = -i
-  v[14] = make_float2((v[14].y - v[14].x) * kH, -(v[14].x + v[14].y) * kH);  // W^6
-  v[7] = cmul(v[7], make_float2(kS1, -kC1));                               // W^3
-  v[11] = make_float2((v[11].y - v[11].x) * kH, -(v[11].x + v[11].y) * kH);  // W^6
-  v[15] = cmul(v[15], make_float2(-kC1, kS1));                             // W^9
-  radix4(v[0], v[1], v[2], v[3]);
-  radix4(v[4], v[5], v[6], v[7]);
-  radix4(v[8], v[9], v[10], v[11]);
-  radix4(v[12], v[13], v[14], v[15]);
+  // element n2 + 4*k1 *= W16^(n2*k1)
+  cmul2(R[5], I[5], kC1, -kS1);                                            // W^1
+  {                                                                        // W^2 = h(1 - i)
+    const f2 r = mul2(add2(R[9], I[9]), bc(kH)), i = mul2(sub2(I[9], R[9]), bc(kH));
+    R[9] = r; I[9] = i;
+  }
+  cmul2(R[13], I[13], kS1, -kC1);                                          // W^3
+  {
+    const f2 r = mul2(add2(R[6], I[6]), bc(kH)), i = mul2(sub2(I[6], R[6]), bc(kH));
+    R[6] = r; I[6] = i;
+  }
+  {                                                                        // W^4 = -i
+    const f2 r = I[10], i = neg2(R[10]);
+    R[10] = r; I[10] = i;
+  }
+  {                                                                        // W^6 = h(-1 - i)
+    const f2 r = mul2(sub2(I[14], R[14]), bc(kH)), i = mul2(add2(R[14], I[14]), bc(-kH));
+    R[14] = r; I[14] = i;
+  }
+  cmul2(R[7], I[7], kS1, -kC1);                                            // W^3
+  {
+    const f2 r = mul2(sub2(I[11], R[11]), bc(kH)), i = mul2(add2(R[11], I[11]), bc(-kH));
+    R[11] = r; I[11] = i;
+  }
+  cmul2(R[15], I[15], -kC1, kS1);                                          // W^9
+  radix4(R[0], I[0], R[1], I[1], R[2], I[2], R[3], I[3]);
+  radix4(R[4], I[4], R[5], I[5], R[6], I[6], R[7], I[7]);
+  radix4(R[8], I[8], R[9], I[9], R[10], I[10], R[11], I[11]);
+  radix4(R[12], I[12], R[13], I[13], R[14], I[14], R[15], I[15]);
 }
 __host__ __device__ constexpr int rev4(int p) { return (p >> 2) + 4 * (p & 3); }
 
@@ -168,15 +210,13 @@ struct InTraits;
 template <>
 struct InTraits<float> {
   static __device__ __forceinline__ float2 ld2(const float* p, float) { return *reinterpret_cast<const float2*>(p); }
-  static __device__ __forceinline__ float ld1(const float* p, float) { return *p; }
 };
 template <>
 struct InTraits<short> {
   static __device__ __forceinline__ float2 ld2(const short* p, float s) {
-    short2 v = *reinterpret_cast<const short2*>(p);
+    const short2 v = *reinterpret_cast<const short2*>(p);
     return make_float2(static_cast<float>(v.x) * s, static_cast<float>(v.y) * s);
   }
-  static __device__ __forceinline__ float ld1(const short* p, float s) { return static_cast<float>(*p) * s; }
 };
 
 // shared-memory carve-up (dynamic)
@@ -185,110 +225,154 @@ struct SmemLayout {
   static constexpr int kInBytes = ((kTileSamplesPad * (int)sizeof(TIn)) + 127) / 128 * 128;
   static constexpr int off_in0 = 0;
   static constexpr int off_in1 = kInBytes;
-  static constexpr int off_scratch = 2 * kInBytes;                                 // [kFramesPerRound][576] floats
-  static constexpr int off_window = off_scratch + kFramesPerRound * kScratchFloats * 4;   // [512]
-  static constexpr int off_tw1 = off_window + 512 * 4;                             // [16][16] float2
+  static constexpr int off_scratch = 2 * kInBytes;                                 // [2*kWarps][kScratchFloats] floats
+  static constexpr int off_window = off_scratch + 2 * kWarps * kScratchFloats * 4; // [416]
+  static constexpr int off_tw1 = off_window + 416 * 4;                             // [16][16] float2
   static constexpr int off_tw2 = off_tw1 + 256 * 8;                                // [8][16] float2
   static constexpr int off_k0 = off_tw2 + 128 * 8;                                 // [80] int
-  static constexpr int off_norm = off_k0 + kMaxMels * 4;                           // [2][80] float mean, inv_std
-  static constexpr int off_stats = off_norm + 2 * kMaxMels * 4;                    // [2 bufs][2][80] float
-  static constexpr int off_gstats = off_stats + 4 * kMaxMels * 4;                  // [2*80+1] double (8B aligned)
-  static constexpr int off_masks = off_gstats + (2 * kMaxMels + 2) * 8;            // [kMaxMasks][4] int
+  static constexpr int off_norm = off_k0 + kMaxMels * 4;                           // [80] float2 (mean, inv_std)
+  static constexpr int off_acc = off_norm + kMaxMels * 8;                          // [2*80+2] double
+  static constexpr int off_masks = off_acc + (2 * kMaxMels + 2) * 8;               // [kMaxMasks][4] int
   static constexpr int off_bar = off_masks + kMaxMasks * 16;                       // 2 mbarriers
-  static constexpr int off_melw = off_bar + 16;                                    // [kBands][maxt][16] float, then dct, lifter
+  static constexpr int off_tiles = off_bar + 16;                                   // [kTileCache] Tile descriptors
+  static constexpr int off_melw = off_tiles + kTileCache * 32;                                    // sum(band_taps)*16 floats, then dct, lifter
 };
 
 // ------------------------------------------------------------------------------------------------
 // the fused front-end kernel
 // ------------------------------------------------------------------------------------------------
-template <typename TIn, bool kMfcc>
-__global__ void __launch_bounds__(kThreads, 2) fbank_kernel(const __grid_constant__ FbankParams P) {
+template <typename TIn, bool kMfcc, bool kStdMel>
+__global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constant__ FbankParams P) {
   using L = SmemLayout<TIn>;
   extern __shared__ __align__(128) unsigned char smem[];
-  TIn* sm_in[2] = {reinterpret_cast<TIn*>(smem + L::off_in0), reinterpret_cast<TIn*>(smem + L::off_in1)};
-  float* sm_scratch = reinterpret_cast<float*>(smem + L::off_scratch);
-  float* sm_window = reinterpret_cast<float*>(smem + L::off_window);
-  float2* sm_tw1 = reinterpret_cast<float2*>(smem + L::off_tw1);
-  float2* sm_tw2 = reinterpret_cast<float2*>(smem + L::off_tw2);
-  int* sm_k0 = reinterpret_cast<int*>(smem + L::off_k0);
-  float* sm_norm = reinterpret_cast<float*>(smem + L::off_norm);
-  float* sm_stats = reinterpret_cast<float*>(smem + L::off_stats);
-  double* sm_gstats = reinterpret_cast<double*>(smem + L::off_gstats);
-  int* sm_masks = reinterpret_cast<int*>(smem + L::off_masks);
-  uint64_t* sm_bar = reinterpret_cast<uint64_t*>(smem + L::off_bar);
-  float* sm_melw = reinterpret_cast<float*>(smem + L::off_melw);
-  float* sm_dct = sm_melw + kBands * P.mel_maxt * 16;
-  float* sm_lifter = sm_dct + (kMfcc ? P.n_mels * P.n_ceps : 0);
+  TIn* const sm_in0 = reinterpret_cast<TIn*>(smem + L::off_in0);
+  TIn* const sm_in1 = reinterpret_cast<TIn*>(smem + L::off_in1);
+  float* const sm_scratch = reinterpret_cast<float*>(smem + L::off_scratch);
+  const float* const sm_window = reinterpret_cast<const float*>(smem + L::off_window);
+  const float2* const sm_tw1 = reinterpret_cast<const float2*>(smem + L::off_tw1);
+  const float2* const sm_tw2 = reinterpret_cast<const float2*>(smem + L::off_tw2);
+  const int* const sm_k0 = reinterpret_cast<const int*>(smem + L::off_k0);
+  float2* const sm_norm = reinterpret_cast<float2*>(smem + L::off_norm);
+  double* const sm_acc = reinterpret_cast<double*>(smem + L::off_acc);
+  int* const sm_masks = reinterpret_cast<int*>(smem + L::off_masks);
+  uint64_t* const sm_bar = reinterpret_cast<uint64_t*>(smem + L::off_bar);
+  Tile* const sm_tiles = reinterpret_cast<Tile*>(smem + L::off_tiles);
+  float* const sm_melw = reinterpret_cast<float*>(smem + L::off_melw);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int t = lane & 15;       // lane inside the frame's half-warp
-  const int half = lane >> 4;    // which of the warp's two frames
+  const int t = lane & 15;       // lane inside the half-warp
+  const int half = lane >> 4;    // which frame pair of the warp
   const int n_out = P.n_out;
-  const bool want_stats = (P.mode == 1) || (P.mode == 3);
+  const int mode = P.mode;
+  const bool want_stats = (mode == 1) || (mode == 3);
+
+  int taps[kBands], tap_off[kBands + 1];
+  tap_off[0] = 0;
+#pragma unroll
+  for (int b = 0; b < kBands; ++b) {
+    taps[b] = kStdMel ? std_taps(b) : P.band_taps[b];
+    tap_off[b + 1] = tap_off[b] + taps[b];
+  }
+  float* const sm_dct = sm_melw + tap_off[kBands] * 16;
+  float* const sm_lifter = sm_dct + (kMfcc ? P.n_mels * P.n_ceps : 0);
+
+  // this CTA's contiguous tile range (neighbouring tiles share their halo in L2 and their utterance's statistics)
+  const long long nt = P.n_tiles;
+  const int tile_begin = static_cast<int>((nt * blockIdx.x) / gridDim.x);
+  const int tile_end = static_cast<int>((nt * (blockIdx.x + 1)) / gridDim.x);
 
   // ---- one-time table staging ----------------------------------------------------------------
-  for (int i = tid; i < 512; i += kThreads) sm_window[i] = P.window[i];
-  for (int i = tid; i < 256; i += kThreads) sm_tw1[i] = P.tw1[i];
-  for (int i = tid; i < 128; i += kThreads) sm_tw2[i] = P.tw2[i];
-  for (int i = tid; i < kMaxMels; i += kThreads) sm_k0[i] = P.mel_k0[i];
-  for (int i = tid; i < kBands * P.mel_maxt * 16; i += kThreads) sm_melw[i] = P.mel_w[i];
-  if (kMfcc) {
-    for (int i = tid; i < P.n_mels * P.n_ceps; i += kThreads) sm_dct[i] = P.dct[i];
-    for (int i = tid; i < P.n_ceps; i += kThreads) sm_lifter[i] = P.lifter[i];
-  }
-  for (int i = tid; i < 4 * kMaxMels; i += kThreads) sm_stats[i] = 0.f;
-  for (int i = tid; i < 2 * kMaxMels + 2; i += kThreads) sm_gstats[i] = 0.0;
-  if (P.mode == 2 && tid < n_out) {
-    // finalise the all-reduced sums: mean, 1/(std + 1e-9) (unbiased)
-    const double n = P.stats_in[2 * n_out];
-    const double mean = P.stats_in[tid] / n;
-    double var = (P.stats_in[n_out + tid] - P.stats_in[tid] * mean) / (n - 1.0);
-    var = var > 0.0 ? var : 0.0;
-    sm_norm[tid] = static_cast<float>(mean);
-    sm_norm[kMaxMels + tid] = static_cast<float>(1.0 / (sqrt(var) + 1e-9));
-  }
-  if (tid == 0) {
-    mbar_init(&sm_bar[0], 1);
-    mbar_init(&sm_bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
+    {   // descriptors of the first kTileCache tiles of the range (4 x 8-byte words each)
+      const int n = min(tile_end - tile_begin, kTileCache);
+      const long long* src = reinterpret_cast<const long long*>(P.tiles + tile_begin);
+      long long* dst = reinterpret_cast<long long*>(sm_tiles);
+      for (int i = tid; i < n * 4; i += kThreads) dst[i] = src[i];
+    }
+    float* w = const_cast<float*>(sm_window);
+    for (int i = tid; i < 416; i += kThreads) w[i] = P.window[i];
+    float2* a = const_cast<float2*>(sm_tw1);
+    for (int i = tid; i < 256; i += kThreads) a[i] = P.tw1[i];
+    float2* c = const_cast<float2*>(sm_tw2);
+    for (int i = tid; i < 128; i += kThreads) c[i] = P.tw2[i];
+    int* k = const_cast<int*>(sm_k0);
+    for (int i = tid; i < kMaxMels; i += kThreads) k[i] = P.mel_k0[i];
+    for (int i = tid; i < tap_off[kBands] * 16; i += kThreads) sm_melw[i] = P.mel_w[i];
+    if (kMfcc) {
+      for (int i = tid; i < P.n_mels * P.n_ceps; i += kThreads) sm_dct[i] = P.dct[i];
+      for (int i = tid; i < P.n_ceps; i += kThreads) sm_lifter[i] = P.lifter[i];
+    }
+    for (int i = tid; i < 2 * kMaxMels + 2; i += kThreads) sm_acc[i] = 0.0;
+    if (mode == 2 && tid < n_out) {
+      // finalise the all-reduced sums: mean, 1/(std + 1e-9) (unbiased)
+      const double n = P.stats_in[2 * n_out];
+      const double mean = P.stats_in[tid] / n;
+      double var = (P.stats_in[n_out + tid] - P.stats_in[tid] * mean) / (n - 1.0);
+      var = var > 0.0 ? var : 0.0;
+      sm_norm[tid] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / (sqrt(var) + 1e-9)));
+    }
+    if (tid == 0) {
+      mbar_init(&sm_bar[0], 1);
+      mbar_init(&sm_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
   }
   __syncthreads();
 
-  // ---- tile staging ---------------------------------------------------------------------------
   auto stage_tile = [&](int tile_idx, int buf) {
-    if (tile_idx >= P.n_tiles) return;
-    const Tile tl = P.tiles[tile_idx];
+    if (tile_idx >= tile_end) return;
+    const Tile tl = sm_tiles[(tile_idx - tile_begin) % kTileCache];
     if (tl.nframes == 0) return;
     const int nsamp = kFrameShift * tl.nframes + (kFrameLen - kFrameShift);
     const TIn* src = reinterpret_cast<const TIn*>(P.wav) + tl.wav_off;
+    TIn* dst = buf ? sm_in1 : sm_in0;
     if (tl.aux) {
       if (tid == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t bytes = nsamp * (uint32_t)sizeof(TIn);
         mbar_expect_tx(&sm_bar[buf], bytes);
-        tma_bulk_g2s(sm_in[buf], src, bytes, &sm_bar[buf]);
+        tma_bulk_g2s(dst, src, bytes, &sm_bar[buf]);
       }
     } else {
-      for (int i = tid; i < nsamp; i += kThreads) sm_in[buf][i] = src[i];
+      for (int i = tid; i < nsamp; i += kThreads) dst[i] = src[i];
     }
   };
 
-  uint32_t phase[2] = {0u, 0u};
-  float* my_scratch = sm_scratch + (warp * 2 + half) * kScratchFloats;
-  float2* my_T = reinterpret_cast<float2*>(my_scratch);
-  const int src_lane = (lane & 16) | ((16 - t) & 15);
+  uint32_t phase0 = 0u, phase1 = 0u;
+  float* const my_scratch = sm_scratch + (warp * 2 + half) * kScratchFloats;
+  f2* const T_re = reinterpret_cast<f2*>(my_scratch);
+  f2* const T_im = reinterpret_cast<f2*>(my_scratch + kPlaneFloats);
+  f2* const my_P = reinterpret_cast<f2*>(my_scratch);
+  const int partner = (lane & 16) | ((16 - t) & 15);
+  const int up_lane = (lane & 16) | ((t - 1) & 15);
 
-  stage_tile(blockIdx.x, 0);
+  int k0[kBands];
+#pragma unroll
+  for (int b = 0; b < kBands; ++b) k0[b] = sm_k0[t + 16 * b];
+
+  int cur_utt = -1;
+  unsigned dim_masked = 0u;   // bit b: output dim t+16b is inside a frequency mask of the current utterance
+
+  stage_tile(tile_begin, 0);
 
   int it = 0;
-  for (int tile_idx = blockIdx.x; tile_idx < P.n_tiles; tile_idx += gridDim.x, ++it) {
+  for (int tile_idx = tile_begin; tile_idx < tile_end; ++tile_idx, ++it) {
     const int buf = it & 1;
-    const Tile tl = P.tiles[tile_idx];
+    const Tile tl = sm_tiles[it % kTileCache];
     // prefetch the next tile into the other buffer (its previous reader finished before the
     // __syncthreads that closed the previous iteration)
-    stage_tile(tile_idx + gridDim.x, buf ^ 1);
+    if ((it + 1) % kTileCache == 0 && tile_idx + 1 < tile_end) {
+      // descriptor cache exhausted (ranges longer than kTileCache tiles): refill.  Everyone has its copy of `tl`.
+      __syncthreads();
+      const int n = min(tile_end - (tile_idx + 1), kTileCache);
+      const long long* src = reinterpret_cast<const long long*>(P.tiles + tile_idx + 1);
+      long long* dst = reinterpret_cast<long long*>(sm_tiles);
+      for (int i = tid; i < n * 4; i += kThreads) dst[i] = src[i];
+      __syncthreads();
+    }
+    stage_tile(tile_idx + 1, buf ^ 1);
 
     if (tl.nframes == 0) {
       // zero-fill tile: pad_sequence's zeros (ref: lid/raw_datasets.py:347-350)
@@ -302,272 +386,381 @@ __global__ void __launch_bounds__(kThreads, 2) fbank_kernel(const __grid_constan
       continue;
     }
 
-    if (tid < P.n_masks * 4) sm_masks[tid] = P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + tid];
+    const bool new_utt = tl.utt != cur_utt;      // CTA-uniform
+    if (new_utt && tid < P.n_masks * 4) sm_masks[tid] = P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + tid];
     if (tl.aux) {
-      mbar_wait(&sm_bar[buf], phase[buf]);
-      phase[buf] ^= 1u;
+      if (buf) { mbar_wait(&sm_bar[1], phase1); phase1 ^= 1u; }
+      else     { mbar_wait(&sm_bar[0], phase0); phase0 ^= 1u; }
     }
-    __syncthreads();   // masks + (fallback path) generic stores visible
-    const TIn* in = sm_in[buf];
-    float* stats = sm_stats + buf * 2 * kMaxMels;
+    if ((new_utt && P.n_masks > 0) || !tl.aux) __syncthreads();   // new mask table / element-load staging visible
+    const TIn* in = buf ? sm_in1 : sm_in0;
 
-    float s1[kBands], s2[kBands];
+    if (new_utt) {
+      cur_utt = tl.utt;
+      dim_masked = 0u;
+      for (int q = 0; q < P.n_masks; ++q) {
+        const int f0 = sm_masks[4 * q + 2], f1 = sm_masks[4 * q + 3];
 #pragma unroll
-    for (int b = 0; b < kBands; ++b) s1[b] = s2[b] = 0.f;
+        for (int b = 0; b < kBands; ++b) dim_masked |= (t + 16 * b >= f0 && t + 16 * b < f1) ? (1u << b) : 0u;
+      }
+    }
 
-    for (int r0 = 0; r0 < tl.nframes; r0 += kFramesPerRound) {
-      const int fl = r0 + warp * 2 + half;        // frame inside the tile
-      if (r0 + warp * 2 >= tl.nframes) break;     // warp-uniform
-      const bool active = fl < tl.nframes;
-      const TIn* fr = in + kFrameShift * (active ? fl : r0 + warp * 2);
+    f2 val[kBands];
+    const int flA = warp * 4 + half * 2;          // frame A inside the tile; B = A + 1
+    const bool actA = flA < tl.nframes, actB = flA + 1 < tl.nframes;
+    {
+      // Frame B starts 160 samples = 5 x 32 after frame A, so lane t's element j of B is its element j+5 of A:
+      // 18 loads cover both frames.  A pair whose frame B lies beyond the utterance (odd tail) still reads valid
+      // shared memory; an entirely dead pair recomputes frame 0.  Neither is stored nor counted.
+      const TIn* fr = in + kFrameShift * (actA ? flA : 0);
 
       // ---- load, DC removal, pre-emphasis, window (ta: compliance/kaldi.py:183-204) ---------------
-      float2 v[16];
-      float pv[13];
-      float sum = 0.f;
+      f2 R[16], I[16];     // R[j] = (re_A, re_B), I[j] = (im_A, im_B) of z[t + 16 j]
+      {
+        float2 x[18];
 #pragma unroll
-      for (int j = 0; j < 13; ++j) {
-        const int n = t + 16 * j;
-        if (j < 12 || t < 8) {
-          v[j] = InTraits<TIn>::ld2(fr + 2 * n, P.in_scale);
-          pv[j] = InTraits<TIn>::ld1(fr + (n == 0 ? 0 : 2 * n - 1), P.in_scale);
-          sum += v[j].x;
-          sum += v[j].y;
-        } else {
-          v[j] = make_float2(0.f, 0.f);
-          pv[j] = 0.f;
+        for (int j = 0; j < 18; ++j) {
+          const int n = t + 16 * j;
+          x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
         }
-      }
+        f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int o = 8; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mean = P.remove_dc ? __fdiv_rn(sum, static_cast<float>(kFrameLen)) : 0.f;
-      const float c = P.preemph;
+        for (int j = 0; j < 13; ++j) {
+          if (j < 12 || t < 8) {
+            sA = add2(sA, x[j]);
+            sB = add2(sB, x[j + 5]);
+            R[j] = make_float2(x[j].x, x[j + 5].x);     // even samples of A, B
+            I[j] = make_float2(x[j].y, x[j + 5].y);     // odd samples
+          } else {
+            R[j] = I[j] = make_float2(0.f, 0.f);
+          }
+        }
+        f2 sum = make_float2(sA.x + sA.y, sB.x + sB.y);
 #pragma unroll
-      for (int j = 0; j < 13; ++j) {
-        const int n = t + 16 * j;
-        const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
-        const float te = __fsub_rn(v[j].x, mean);
-        const float to = __fsub_rn(v[j].y, mean);
-        const float tp = __fsub_rn(pv[j], mean);
-        // x[j] - c * x[j-1]: product and difference rounded separately, as the reference's two tensor ops
-        const float se = __fsub_rn(te, __fmul_rn(c, tp));
-        const float so = __fsub_rn(to, __fmul_rn(c, te));
-        v[j] = make_float2(__fmul_rn(se, w.x), __fmul_rn(so, w.y));
+        for (int o = 8; o >= 1; o >>= 1) {
+          sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+          sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+        }
+        f2 nmean = make_float2(0.f, 0.f);
+        if (P.remove_dc)
+          nmean = make_float2(-__fdiv_rn(sum.x, static_cast<float>(kFrameLen)),
+                              -__fdiv_rn(sum.y, static_cast<float>(kFrameLen)));
+        const float c = P.preemph;
+        f2 to_prev = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+          const int n = t + 16 * j;
+          const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
+          const f2 te = add2(R[j], nmean);      // x[2n]   - mean
+          const f2 to = add2(I[j], nmean);      // x[2n+1] - mean
+          // x[2n-1] - mean lives in lane t-1 (same j); lane 0 takes lane 15's value of step j-1, and the very
+          // first sample of the frame replicates itself (ta: compliance/kaldi.py:193-198)
+          const f2 send = (t == 15) ? to_prev : to;
+          f2 tp;
+          tp.x = __shfl_sync(0xffffffffu, send.x, up_lane);
+          tp.y = __shfl_sync(0xffffffffu, send.y, up_lane);
+          if (j == 0 && t == 0) tp = te;
+          to_prev = to;
+          // x[j] - c * x[j-1]: product and difference rounded separately, as the reference's two tensor ops
+          // (c == 1.0 in the reference's call: the product is then exact and costs one FMUL2)
+          const f2 se = sub2(te, mul2(tp, bc(c)));
+          const f2 so = sub2(to, mul2(te, bc(c)));
+          R[j] = mul2(se, bc(w.x));
+          I[j] = mul2(so, bc(w.y));
+        }
+        if (t >= 8) R[12] = I[12] = make_float2(0.f, 0.f);
+        R[13] = R[14] = R[15] = I[13] = I[14] = I[15] = make_float2(0.f, 0.f);
       }
-      if (t >= 8) v[12] = make_float2(0.f, 0.f);
-      v[13] = v[14] = v[15] = make_float2(0.f, 0.f);
 
       // ---- stage 1: 16-point DFT over j, twiddle W256^(K1*t), transpose through shared ------------
-      fft16<true>(v);
-      __syncwarp();   // previous round's readers of my_T are done
+      fft16<true>(R, I);
+      __syncwarp();   // previous tile's readers of this scratch are done
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int K1 = rev4(p);
-        float2 y = v[p];
-        if (K1 != 0) y = cmul(y, sm_tw1[K1 * 16 + t]);
-        my_T[K1 * kRowStride + t] = y;
+        if (K1 != 0) {
+          const float2 w = sm_tw1[K1 * 16 + t];
+          cmul2(R[p], I[p], w.x, w.y);
+        }
+        T_re[K1 * kRowStride + t] = R[p];
+        T_im[K1 * kRowStride + t] = I[p];
       }
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 two = *reinterpret_cast<const float4*>(my_T + t * kRowStride + 2 * q);
-        v[2 * q] = make_float2(two.x, two.y);
-        v[2 * q + 1] = make_float2(two.z, two.w);
+        const float4 a = *reinterpret_cast<const float4*>(T_re + t * kRowStride + 2 * q);
+        const float4 b = *reinterpret_cast<const float4*>(T_im + t * kRowStride + 2 * q);
+        R[2 * q] = make_float2(a.x, a.y);
+        R[2 * q + 1] = make_float2(a.z, a.w);
+        I[2 * q] = make_float2(b.x, b.y);
+        I[2 * q + 1] = make_float2(b.z, b.w);
       }
-      // ---- stage 2: v[p] = Z[t + 16*rev4(p)] --------------------------------------------------------
-      fft16<false>(v);
+      // ---- stage 2: position p holds Z[t + 16*rev4(p)] ----------------------------------------------
+      fft16<false>(R, I);
+      __syncwarp();   // all lanes finished reading the transpose planes before the power bins overwrite them
 
       // ---- real-FFT split + power; lane t pairs with lane 16-t ------------------------------------
-      float2 pb[8];
+      if (t == 0) my_P[128] = mul2(fma2(R[2], R[2], mul2(I[2], I[2])), bc(4.f));   // 4|Z[128]|^2, Z[128] at rev4(8)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float2 s = v[rev4(15 - i)];
-        pb[i].x = __shfl_sync(0xffffffffu, s.x, src_lane);
-        pb[i].y = __shfl_sync(0xffffffffu, s.y, src_lane);
-      }
-      if (t == 0) {
-        // lane 0 pairs k=16i with 256-16i = its own Z[16-i]; k=0 pairs with itself (DC / Nyquist)
-#pragma unroll
-        for (int i = 7; i >= 1; --i) pb[i] = pb[i - 1];
-        pb[0] = v[0];
-      }
-      __syncwarp();   // all lanes finished reading my_T before the power bins overwrite it
-      float* my_P = my_scratch;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 a = v[rev4(i)];
-        const float2 b = pb[i];
-        const float2 e2 = make_float2(a.x + b.x, a.y - b.y);          // 2E = a + conj(b)
-        const float2 o2 = make_float2(a.y + b.y, b.x - a.x);          // 2O = -i (a - conj(b))
-        const float2 tw = cmul(o2, sm_tw2[i * 16 + t]);               // W512^k * 2O
-        const float2 xa = e2 + tw;                                    // 2 X[k]
-        const float2 xb = e2 - tw;                                    // 2 conj(X[256-k])
+        // partner's Z[(16-t) + 16 (15-i)]; lane 0 pairs k=16i with 256-16i = its own Z[16 (16-i)], k=0 with itself
+        const int ps = rev4(15 - i);
+        f2 br, bi;
+        br.x = __shfl_sync(0xffffffffu, R[ps].x, partner);
+        br.y = __shfl_sync(0xffffffffu, R[ps].y, partner);
+        bi.x = __shfl_sync(0xffffffffu, I[ps].x, partner);
+        bi.y = __shfl_sync(0xffffffffu, I[ps].y, partner);
+        if (t == 0) {
+          const int own = (i == 0) ? 0 : rev4(16 - i);
+          br = R[own];
+          bi = I[own];
+        }
+        const f2 ar = R[rev4(i)], ai = I[rev4(i)];
+        const f2 e2r = add2(ar, br), e2i = sub2(ai, bi);          // 2E = a + conj(b)
+        f2 o2r = add2(ai, bi), o2i = sub2(br, ar);                // 2O = -i (a - conj(b))
+        const float2 w = sm_tw2[i * 16 + t];
+        cmul2(o2r, o2i, w.x, w.y);                                // W512^k * 2O
+        const f2 xar = add2(e2r, o2r), xai = add2(e2i, o2i);      // 2 X[k]
+        const f2 xbr = sub2(e2r, o2r), xbi = sub2(e2i, o2i);      // 2 conj(X[256-k])
         const int k = t + 16 * i;
-        my_P[k] = 0.25f * fmaf(xa.x, xa.x, xa.y * xa.y);
-        my_P[256 - k] = 0.25f * fmaf(xb.x, xb.x, xb.y * xb.y);
+        my_P[k] = fma2(xar, xar, mul2(xai, xai));                 // 4 |X[k]|^2   (the 1/4 lives in the mel weights)
+        my_P[256 - k] = fma2(xbr, xbr, mul2(xbi, xbi));
       }
-      if (t == 0) my_P[128] = fmaf(v[2].x, v[2].x, v[2].y * v[2].y);   // Z[128] = v[rev4(8)]
       __syncwarp();
 
       // ---- sparse triangular mel + log (ta: compliance/kaldi.py:621-633) ---------------------------
-      float val[kBands];
 #pragma unroll
       for (int b = 0; b < kBands; ++b) {
-        const int m = t + 16 * b;
-        float acc = 0.f;
-        const int k0 = sm_k0[m];
-        const float* wp = sm_melw + (b * P.mel_maxt) * 16 + t;
-        const int nt = P.band_taps[b];
-        for (int i = 0; i < nt; ++i) {
-          const int k = min(k0 + i, kBins - 1);
-          acc = fmaf(my_P[k], wp[i * 16], acc);
+        f2 acc = make_float2(0.f, 0.f);
+        const f2* pp = my_P + k0[b];
+        const float* wp = sm_melw + tap_off[b] * 16 + t;
+        if (kStdMel) {
+#pragma unroll
+          for (int i = 0; i < std_taps(b); ++i) acc = fma2(pp[i], bc(wp[i * 16]), acc);
+        } else {
+#pragma unroll 2
+          for (int i = 0; i < taps[b]; ++i) acc = fma2(pp[i], bc(wp[i * 16]), acc);
         }
-        val[b] = logf(fmaxf(acc, P.log_floor));
+        // lg2.approx (abs. error ~1e-7 in the log) except at the floor, where the reference's log(eps) is returned exactly
+        val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : __logf(acc.x),
+                             acc.y <= P.log_floor ? P.log_of_floor : __logf(acc.y));
       }
 
       // ---- MFCC: DCT-II + lifter (ta: compliance/kaldi.py:648-666,786-796) --------------------------
       if (kMfcc) {
-        float* my_L = my_scratch + kLogmelOff;
+        f2* my_L = reinterpret_cast<f2*>(my_scratch + kLogmelOff);
 #pragma unroll
         for (int b = 0; b < kBands; ++b)
           if (t + 16 * b < P.n_mels) my_L[t + 16 * b] = val[b];
         __syncwarp();
+        f2 acc[kBands];
 #pragma unroll
-        for (int b = 0; b < kBands; ++b) {
-          const int cidx = t + 16 * b;
-          float acc = 0.f;
-          if (cidx < P.n_ceps) {
-            for (int m = 0; m < P.n_mels; ++m) acc = fmaf(my_L[m], sm_dct[m * P.n_ceps + cidx], acc);
-            acc = __fmul_rn(acc, sm_lifter[cidx]);
-          }
-          val[b] = acc;
+        for (int b = 0; b < kBands; ++b) acc[b] = make_float2(0.f, 0.f);
+        const int nc = P.n_ceps;
+        for (int m = 0; m < P.n_mels; ++m) {
+          const f2 l = my_L[m];
+          const float* drow = sm_dct + m * nc + t;
+#pragma unroll
+          for (int b = 0; b < kBands; ++b)
+            if (16 * b < nc) acc[b] = fma2(l, bc((t + 16 * b < nc) ? drow[16 * b] : 0.f), acc[b]);
         }
+#pragma unroll
+        for (int b = 0; b < kBands; ++b) val[b] = mul2(acc[b], bc((t + 16 * b < nc) ? sm_lifter[t + 16 * b] : 0.f));
       }
 
-      // ---- epilogue: stats, global CMVN, SpecAugment zero-fill, store -------------------------------
-      if (active) {
-        const int tf = tl.t0 + fl;   // frame index inside the utterance
-        bool row_masked = false;
-        if (P.mode != 3) {
-          for (int q = 0; q < P.n_masks; ++q) row_masked |= (tf >= sm_masks[4 * q] && tf < sm_masks[4 * q + 1]);
+      // ---- epilogue: global CMVN, SpecAugment zero-fill, store ---------------------------------------
+      {
+        const int tfA = tl.t0 + flA;   // frame index inside the utterance
+        bool rowA = false, rowB = false;
+        unsigned dm = 0u;
+        if (mode == 0 || mode == 2) {
+          dm = dim_masked;
+          for (int q = 0; q < P.n_masks; ++q) {
+            const int m0 = sm_masks[4 * q], m1 = sm_masks[4 * q + 1];
+            rowA |= (tfA >= m0 && tfA < m1);
+            rowB |= (tfA + 1 >= m0 && tfA + 1 < m1);
+          }
         }
-        float* orow = P.out + (tl.out_row + fl) * P.out_ld;
+        float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
 #pragma unroll
         for (int b = 0; b < kBands; ++b) {
           const int d = t + 16 * b;
           if (d < n_out) {
-            float x = val[b];
-            if (want_stats) {
-              s1[b] += x;
-              s2[b] = fmaf(x, x, s2[b]);
+            f2 x = val[b];
+            if (mode == 2) {
+              const float2 nm = sm_norm[d];
+              x = mul2(sub2(x, bc(nm.x)), bc(nm.y));
             }
-            if (P.mode == 2) x = (x - sm_norm[d]) * sm_norm[kMaxMels + d];
-            if (P.mode != 1 && P.mode != 3) {
-              bool z = row_masked;
-              for (int q = 0; q < P.n_masks; ++q) z |= (d >= sm_masks[4 * q + 2] && d < sm_masks[4 * q + 3]);
-              if (z) x = 0.f;
-            }
-            orow[d] = x;
+            const bool dz = (dm >> b) & 1u;
+            if (actA) orow[16 * b] = (dz || rowA) ? 0.f : x.x;
+            if (actB) orow[P.out_ld + 16 * b] = (dz || rowB) ? 0.f : x.y;
           }
         }
       }
     }
 
+    // ---- statistics: every half-warp parks its (A,B) feature pairs in its scratch; after the barrier 80 threads
+    //      add them up in fp64 (x*x is exact in fp64), so sum and sum-of-squares carry no fp32 round-off ---------
     if (want_stats) {
+      f2* my_V = reinterpret_cast<f2*>(my_scratch + kValsOff);
 #pragma unroll
-      for (int b = 0; b < kBands; ++b) {
-        s1[b] += __shfl_xor_sync(0xffffffffu, s1[b], 16);
-        s2[b] += __shfl_xor_sync(0xffffffffu, s2[b], 16);
-        const int d = t + 16 * b;
-        if (half == 0 && d < n_out) {
-          atomicAdd(&stats[d], s1[b]);
-          atomicAdd(&stats[kMaxMels + d], s2[b]);
-        }
-      }
+      for (int b = 0; b < kBands; ++b)
+        if (t + 16 * b < n_out) my_V[t + 16 * b] = val[b];
     }
-    __syncthreads();   // everyone is done with sm_in[buf], sm_masks and has published its stats
-    if (want_stats && tid < 2 * kMaxMels) {
-      const int which = tid / kMaxMels, d = tid - which * kMaxMels;
-      if (d < n_out) {
-        const float s = stats[tid];
-        stats[tid] = 0.f;
-        if (P.mode == 1) {
-          atomicAdd(&P.utt_stats[(static_cast<long long>(tl.utt) * 2 + which) * n_out + d], static_cast<double>(s));
-        } else {
-          sm_gstats[which * n_out + d] += static_cast<double>(s);
-        }
+    __syncthreads();   // everyone is done with this input buffer and sm_masks, and has published its features
+    if (want_stats) {
+      bool flush = (mode == 1);
+      if (flush && tile_idx + 1 < tile_end) {
+        const Tile nx = sm_tiles[(it + 1) % kTileCache];
+        flush = (nx.utt != tl.utt) || (nx.nframes == 0);
       }
+      if (tid < n_out) {
+        double a1 = sm_acc[tid], a2 = sm_acc[kMaxMels + tid];
+#pragma unroll
+        for (int hw = 0; hw < 2 * kWarps; ++hw) {
+          const f2 v = *reinterpret_cast<const f2*>(sm_scratch + hw * kScratchFloats + kValsOff + 2 * tid);
+          if (2 * hw < tl.nframes) {
+            const double x = static_cast<double>(v.x);
+            a1 += x;
+            a2 = fma(x, x, a2);
+          }
+          if (2 * hw + 1 < tl.nframes) {
+            const double x = static_cast<double>(v.y);
+            a1 += x;
+            a2 = fma(x, x, a2);
+          }
+        }
+        if (flush) {
+          double* dst = P.utt_stats + static_cast<long long>(tl.utt) * 2 * n_out;
+          atomicAdd(dst + tid, a1);
+          atomicAdd(dst + n_out + tid, a2);
+          a1 = a2 = 0.0;
+        }
+        sm_acc[tid] = a1;
+        sm_acc[kMaxMels + tid] = a2;
+      }
+      if (mode == 3 && tid == kThreads - 1) sm_acc[2 * kMaxMels] += static_cast<double>(tl.nframes);
     }
-    if (P.mode == 3 && tid == 2 * kMaxMels) sm_gstats[2 * n_out] += static_cast<double>(tl.nframes);
   }
 
-  if (P.mode == 3) {
+  if (mode == 3) {
     __syncthreads();
-    for (int i = tid; i < 2 * n_out + 1; i += kThreads) {
-      const int slot = (i == 2 * n_out) ? i : i;   // same indexing on both sides
-      double vsum = sm_gstats[slot];
-      if (vsum != 0.0) atomicAdd(&P.stats_out[i], vsum);
+    for (int e = tid; e < 2 * kMaxMels; e += kThreads) {
+      const int which = e / kMaxMels, d = e - which * kMaxMels;
+      if (d < n_out && sm_acc[e] != 0.0) atomicAdd(&P.stats_out[which * n_out + d], sm_acc[e]);
     }
+    if (tid == 0 && sm_acc[2 * kMaxMels] != 0.0) atomicAdd(&P.stats_out[2 * n_out], sm_acc[2 * kMaxMels]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// CMVN apply + masks (second pass of per-utterance / global CMVN).  One CTA per tile.
+// CMVN apply + masks (second pass of per-utterance / global CMVN; standalone SpecAugment application).
+// grid = (utterances, row chunks of kApplyRows): every CTA finalises its utterance's mean / inv-std once and
+// streams 64 rows with 128-bit accesses, several loads in flight per thread.
 // ------------------------------------------------------------------------------------------------
+constexpr int kApplyRows = 64;
+
 struct ApplyParams {
   float* feats;
   long long ld;
-  const Tile* tiles;
-  int n_tiles;
   int n_out;
   const int* masks;
   int n_masks;
-  const double* utt_stats;     // [B][2][n_out] or NULL
-  const long long* utt_frames; // [B]
-  const double* glob_stats;    // [2*n_out+1] or NULL
-  int normalize;               // 0 -> masks only (standalone SpecAugment application)
+  const double* utt_stats;       // [B][2][n_out] or NULL
+  const long long* utt_frames;   // [B]
+  const long long* utt_out_row;  // [B]
+  const double* glob_stats;      // [2*n_out+1] or NULL
+  int normalize;                 // 0 -> masks only
 };
 
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__ ApplyParams P) {
   __shared__ float s_mean[kMaxMels], s_inv[kMaxMels];
   __shared__ int s_masks[kMaxMasks * 4];
   const int tid = threadIdx.x;
-  for (int tile_idx = blockIdx.x; tile_idx < P.n_tiles; tile_idx += gridDim.x) {
-    const Tile tl = P.tiles[tile_idx];
-    if (tl.nframes == 0) continue;
-    __syncthreads();
-    if (!P.normalize) {
-      if (tid < P.n_out) {
-        s_mean[tid] = 0.f;
-        s_inv[tid] = 1.f;
-      }
-    } else if (tid < P.n_out) {
-      double n, s, ss;
+  const int utt = blockIdx.x;
+  const long long T = P.utt_frames[utt];
+  const long long r0 = static_cast<long long>(blockIdx.y) * kApplyRows;
+  if (r0 >= T) return;
+  const int rows = static_cast<int>(T - r0 < kApplyRows ? T - r0 : kApplyRows);
+  if (tid < P.n_out) {
+    float mean = 0.f, inv = 1.f;
+    if (P.normalize) {
+      double n, sm, ss;
       if (P.utt_stats) {
-        n = static_cast<double>(P.utt_frames[tl.utt]);
-        s = P.utt_stats[(static_cast<long long>(tl.utt) * 2 + 0) * P.n_out + tid];
-        ss = P.utt_stats[(static_cast<long long>(tl.utt) * 2 + 1) * P.n_out + tid];
+        n = static_cast<double>(T);
+        sm = P.utt_stats[(static_cast<long long>(utt) * 2 + 0) * P.n_out + tid];
+        ss = P.utt_stats[(static_cast<long long>(utt) * 2 + 1) * P.n_out + tid];
       } else {
         n = P.glob_stats[2 * P.n_out];
-        s = P.glob_stats[tid];
+        sm = P.glob_stats[tid];
         ss = P.glob_stats[P.n_out + tid];
       }
-      const double mean = s / n;
-      double var = (ss - s * mean) / (n - 1.0);   // n == 1 -> NaN, as torch.std of one sample
+      const double mu = sm / n;
+      double var = (ss - sm * mu) / (n - 1.0);   // n == 1 -> NaN, as torch.std of one sample
       var = var > 0.0 ? var : (var == var ? 0.0 : var);
-      s_mean[tid] = static_cast<float>(mean);
-      s_inv[tid] = static_cast<float>(1.0 / (sqrt(var) + 1e-9));
+      mean = static_cast<float>(mu);
+      inv = static_cast<float>(1.0 / (sqrt(var) + 1e-9));
     }
-    if (tid < P.n_masks * 4) s_masks[tid] = P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + tid];
-    __syncthreads();
-    const int total = tl.nframes * P.n_out;
-    for (int i = tid; i < total; i += blockDim.x) {
+    s_mean[tid] = mean;
+    s_inv[tid] = inv;
+  }
+  if (tid < P.n_masks * 4) s_masks[tid] = P.masks[static_cast<long long>(utt) * P.n_masks * 4 + tid];
+  __syncthreads();
+
+  float* base = P.feats + (P.utt_out_row[utt] + r0) * P.ld;
+  const bool vec = (P.n_out % 4 == 0) && (P.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.feats) & 15) == 0);
+  if (vec) {
+    const int nvec = P.n_out >> 2;
+    const int total = rows * nvec;
+    constexpr int kU = 5;                       // 64 rows x 20 float4 = 1280 = 5 x 256: one batch of loads for n_out = 80
+    for (int i0 = tid; i0 < total; i0 += kU * 256) {
+      float4 x[kU];
+      int rr[kU], dd[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * 256;
+        rr[u] = i / nvec;
+        dd[u] = (i - rr[u] * nvec) * 4;
+        if (i < total) x[u] = *reinterpret_cast<const float4*>(base + static_cast<long long>(rr[u]) * P.ld + dd[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * 256;
+        if (i >= total) continue;
+        const int d = dd[u];
+        float4 v = x[u];
+        if (P.normalize) {
+          v.x = (v.x - s_mean[d + 0]) * s_inv[d + 0];
+          v.y = (v.y - s_mean[d + 1]) * s_inv[d + 1];
+          v.z = (v.z - s_mean[d + 2]) * s_inv[d + 2];
+          v.w = (v.w - s_mean[d + 3]) * s_inv[d + 3];
+        }
+        const int tf = static_cast<int>(r0) + rr[u];
+        bool zr = false, z0 = false, z1 = false, z2 = false, z3 = false;
+        for (int q = 0; q < P.n_masks; ++q) {
+          const int m0 = s_masks[4 * q], m1 = s_masks[4 * q + 1], f0 = s_masks[4 * q + 2], f1 = s_masks[4 * q + 3];
+          zr |= (tf >= m0 && tf < m1);
+          z0 |= (d + 0 >= f0 && d + 0 < f1);
+          z1 |= (d + 1 >= f0 && d + 1 < f1);
+          z2 |= (d + 2 >= f0 && d + 2 < f1);
+          z3 |= (d + 3 >= f0 && d + 3 < f1);
+        }
+        v.x = (zr || z0) ? 0.f : v.x;
+        v.y = (zr || z1) ? 0.f : v.y;
+        v.z = (zr || z2) ? 0.f : v.z;
+        v.w = (zr || z3) ? 0.f : v.w;
+        *reinterpret_cast<float4*>(base + static_cast<long long>(rr[u]) * P.ld + d) = v;
+      }
+    }
+  } else {
+    const int total = rows * P.n_out;
+    for (int i = tid; i < total; i += 256) {
       const int r = i / P.n_out;
       const int d = i - r * P.n_out;
-      float* p = P.feats + (tl.out_row + r) * P.ld + d;
+      float* p = base + static_cast<long long>(r) * P.ld + d;
       float x = *p;
       if (P.normalize) x = (x - s_mean[d]) * s_inv[d];
-      const int tf = tl.t0 + r;
+      const int tf = static_cast<int>(r0) + r;
       bool z = false;
       for (int q = 0; q < P.n_masks; ++q)
         z |= (tf >= s_masks[4 * q] && tf < s_masks[4 * q + 1]) || (d >= s_masks[4 * q + 2] && d < s_masks[4 * q + 3]);
