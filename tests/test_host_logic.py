@@ -1,0 +1,187 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/lidfe.h declares,
+argument validation, frame arithmetic, table construction, mask drawing, sharding.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import speech_lid_b200 as lid
+from speech_lid_b200 import _lib, tables
+from oracle import frontend_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lidfe.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(lidfe_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 18
+    lib = lid.load_library()
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, "liblidfe.so does not export %s" % missing
+    assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
+    assert lib.lidfe_abi_version() == 1
+
+
+def _cfg(**kw):
+    base = dict(sample_rate=16000, frame_len=400, frame_shift=160, fft_len=512, n_mels=80, n_ceps=0, preemph=1.0,
+                remove_dc=1, log_floor=1.1920929e-07, in_dtype=0, in_scale=1.0)
+    base.update(kw)
+    return _lib.LidfeConfig(**base)
+
+
+def test_num_frames_matches_kaldi_snip_edges():
+    lib = lid.load_library()
+    cfg = _cfg()
+    for n in list(range(0, 1300)) + [16000, 48000, 64000, 128000, 320000, 2 ** 31 + 5]:
+        assert lib.lidfe_num_frames(n, C.byref(cfg)) == O.kaldi_num_frames(n), n
+    assert lib.lidfe_num_frames(1000, None) == 0
+
+
+def test_error_codes_and_messages():
+    lib = lid.load_library()
+    assert lib.lidfe_strerror(0) == b"ok"
+    for rc in range(-7, 0):
+        assert lib.lidfe_strerror(rc).startswith(b"lidfe:")
+    with pytest.raises(AssertionError):        # too-short utterance mirrors torchaudio's assertion
+        _lib.check(_lib.E_SHORT)
+    with pytest.raises(lid.LidfeError) as e:
+        _lib.check(_lib.E_CONFIG)
+    assert e.value.rc == _lib.E_CONFIG
+    _lib.check(0)
+
+
+def test_create_validates_arguments_before_touching_the_device():
+    lib = lid.load_library()
+    h = C.c_void_p()
+    win = tables.povey_window(400).contiguous()
+    banks = tables.mel_banks(80, 512, 16000.0).contiguous()
+    assert lib.lidfe_create(None, C.byref(_cfg()), win.data_ptr(), banks.data_ptr(), None, None) == _lib.E_NULL
+    assert lib.lidfe_create(C.byref(h), C.byref(_cfg()), None, banks.data_ptr(), None, None) == _lib.E_NULL
+    for bad in (dict(sample_rate=8000), dict(frame_len=200), dict(frame_shift=80), dict(fft_len=256),
+                dict(n_mels=128), dict(n_mels=2), dict(n_ceps=81), dict(preemph=1.5), dict(in_dtype=7)):
+        assert lib.lidfe_create(C.byref(h), C.byref(_cfg(**bad)), win.data_ptr(), banks.data_ptr(), None, None) \
+            == _lib.E_CONFIG, bad
+    assert lib.lidfe_create(C.byref(h), C.byref(_cfg(n_ceps=40)), win.data_ptr(), banks.data_ptr(), None, None) \
+        == _lib.E_NULL          # MFCC without a DCT table
+    assert lib.lidfe_destroy(None) == _lib.E_NULL and lib.lidfe_plan_destroy(None) == _lib.E_NULL
+    assert lib.lidfe_featurize(None, None, None, None, 80, None, 0, 0, None, None, None) == _lib.E_NULL
+    if not torch.cuda.is_available():
+        # a valid configuration needs the device: the call must fail loudly (cudaError), never fall back
+        rc = lib.lidfe_create(C.byref(h), C.byref(_cfg()), win.data_ptr(), banks.data_ptr(), None, None)
+        assert rc > 0 and not h.value
+        with pytest.raises(RuntimeError):
+            lid.FrontEnd()
+
+
+def test_tables_bit_identical_to_oracle():
+    assert torch.equal(tables.povey_window(400), O.povey_window(400))
+    for n in (80, 40, 23):
+        assert torch.equal(tables.mel_banks(n, 512, 16000.0), O.kaldi_mel_banks(n, 512, 16000.0))
+    assert torch.equal(tables.dct_matrix(40, 80), O.kaldi_dct_matrix(40, 80))
+    assert torch.equal(tables.dct_matrix(13, 23), O.kaldi_dct_matrix(13, 23))
+    assert torch.equal(tables.lifter(40, 22.0), O.kaldi_lifter(40, 22.0).float())
+    K = pytest.importorskip("torchaudio.compliance.kaldi")
+    ref = torch.nn.functional.pad(K.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)[0], (0, 1))
+    assert torch.equal(tables.mel_banks(80, 512, 16000.0), ref)
+    assert torch.equal(tables.povey_window(400),
+                       K._feature_window_function("povey", 400, 0.42, torch.device("cpu"), torch.float32))
+
+
+def test_mel_plan_is_sparse_exact_and_bank_conflict_free():
+    lib = lid.load_library()
+    for n in (80, 64, 40, 23):
+        banks = tables.mel_banks(n, 512, 16000.0).contiguous()
+        k0, cnt, st = (C.c_int * 80)(), (C.c_int * 80)(), (C.c_int * 80)()
+        bt = (C.c_int * 5)()
+        assert lib.lidfe_mel_plan(n, banks.data_ptr(), k0, cnt, st, bt) == 0
+        taps = list(bt)
+        nz = banks > 0
+        for m in range(n):
+            idx = nz[m].nonzero().flatten()
+            assert k0[m] == int(idx[0]) and cnt[m] == int(idx[-1] - idx[0] + 1) == len(idx)   # contiguous support
+            band = m // 16
+            assert st[m] <= k0[m] and st[m] + taps[band] >= k0[m] + cnt[m]
+        for band in range(5):
+            ms = list(range(16 * band, min(n, 16 * band + 16)))
+            for i in range(taps[band]):
+                by_bank = {}
+                for m in ms:
+                    by_bank.setdefault((st[m] + i) % 16, set()).add(st[m] + i)
+                assert all(len(v) == 1 for v in by_bank.values()), "bank conflict in band %d" % band
+        if n == 80:
+            assert int(nz.sum()) == 501 and taps == [3, 5, 6, 10, 17]      # the fully-unrolled kernel variant
+    assert lib.lidfe_mel_plan(80, None, k0, cnt, st, bt) == _lib.E_NULL
+    assert lib.lidfe_mel_plan(200, banks.data_ptr(), k0, cnt, st, bt) == _lib.E_CONFIG
+    empty = torch.zeros(80, 257)
+    assert lib.lidfe_mel_plan(80, empty.data_ptr(), k0, cnt, st, bt) == _lib.E_MELBANK
+
+
+def test_draw_masks_consumes_rng_like_the_reference(golden_dir):
+    torch.manual_seed(123)
+    table = lid.draw_masks([798], 80, 0.05, 27, 2)
+    assert table.dtype == torch.int32 and table.shape == (1, 2, 4)
+    assert table[0].tolist() == [[406, 417, 50, 56], [688, 690, 7, 10]]
+    # batch order, ragged, including T < 20 (no time mask, no RNG draw)
+    frames = [798, 18, 298, 5]
+    torch.manual_seed(7)
+    a = lid.draw_masks(frames, 80, 0.05, 27, 2)
+    torch.manual_seed(7)
+    b = [O.draw_mask_bounds(T, 80, 0.05, 27, 2) for T in frames]
+    assert a.tolist() == [[list(m) for m in u] for u in b]
+    assert a[1, :, :2].abs().sum() == 0 and a[3, :, :2].abs().sum() == 0
+    # against the reference's own output
+    z = np.load(os.path.join(golden_dir, "specaug.npz"))
+    for name in ("t798_default", "t298_yaml", "t18_no_tmask"):
+        spec = torch.from_numpy(z["spec_" + name])
+        t_mask, f_mask, times, seed = z["kw_" + name]
+        torch.manual_seed(int(seed))
+        m = lid.draw_masks([spec.shape[2]], 80, float(t_mask), int(f_mask), int(times))
+        out = O.apply_mask_bounds(spec, [tuple(int(v) for v in row) for row in m[0]])
+        assert torch.equal(out, torch.from_numpy(z["out_" + name])), name
+    g = torch.Generator().manual_seed(1)
+    assert lid.draw_masks([100], 80, 0.05, 27, 0, generator=g).shape == (1, 0, 4)
+
+
+def test_lpt_partition():
+    g = torch.Generator().manual_seed(3)
+    lengths = torch.randint(16000, 320001, (1000,), generator=g).tolist()
+    for world in (1, 2, 4, 8):
+        shards = lid.lpt_partition(lengths, world)
+        assert sorted(i for s in shards for i in s) == list(range(1000))
+        loads = [sum(lengths[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(lengths)
+        assert shards == lid.lpt_partition(lengths, world)          # deterministic: every rank computes the same split
+    assert lid.lpt_partition([5, 5], 4) == [[0], [1], [], []]
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "speech-lid_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "frontend_oracle" not in src, f
+
+
+def test_audio_processor_surface_matches_reference_signatures():
+    import inspect
+    from speech_lid_b200 import audio_processor as ap
+    sig = inspect.signature(ap.wav2mel)
+    assert list(sig.parameters) == ["x", "use_kaildi", "win_length", "hop_length", "n_mels", "n_fft", "pad", "sr"]
+    assert [p.default for p in sig.parameters.values()][1:] == [False, 0.025, 0.01, 80, 512, 0, 16000]
+    sig = inspect.signature(ap.spectrogram_augment)
+    assert list(sig.parameters) == ["spec", "sr", "n_mels", "hop_length", "t_mask", "f_mask", "mask_times", "t_stretch"]
+    assert [p.default for p in sig.parameters.values()][1:] == [16000, 80, 0.01, 0.05, 27, 0, False]
+    assert list(inspect.signature(ap.wav_augment).parameters) == ["wav", "sr", "speed_shift", "pitch_shift", "reverb"]
+    assert list(inspect.signature(ap.normalize_wav).parameters) == ["wav"]
+    assert list(inspect.signature(ap.read_audio).parameters) == ["audio_path", "normalize"]
+    spec = torch.zeros(1, 80, 50)
+    assert ap.spectrogram_augment(spec, mask_times=0) is spec           # no masks -> returns its input, like the reference
+    with pytest.raises(NotImplementedError):
+        ap.spectrogram_augment(spec, mask_times=1, t_stretch=True)
