@@ -462,7 +462,13 @@ static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, 
   A.utt_out_row = p->d_out_rows;
   A.glob_stats = glob_stats;
   A.normalize = (utt_stats || glob_stats) ? 1 : 0;
-  const long long chunks = (p->max_frames + kApplyRows - 1) / kApplyRows;
+  int rows_per_cta = kApplyRowsDefault;
+  if (const char* env = getenv("LIDFE_APPLY_ROWS")) {
+    const int v = atoi(env);
+    if (v >= 8 && v <= 65536) rows_per_cta = v;
+  }
+  A.rows_per_cta = rows_per_cta;
+  const long long chunks = (p->max_frames + rows_per_cta - 1) / rows_per_cta;
   if (chunks > 65535) return LIDFE_E_ARG;
   dim3 grid(static_cast<unsigned>(p->B), static_cast<unsigned>(chunks));
   cmvn_apply_kernel<<<grid, 256, 0, st>>>(A);

@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
 // grid = (utterances, row chunks of kApplyRows): every CTA finalises its utterance's mean / inv-std once and
 // streams 64 rows with 128-bit accesses, several loads in flight per thread.
 // ------------------------------------------------------------------------------------------------
-constexpr int kApplyRows = 256;
+constexpr int kApplyRowsDefault = 128;   // rows of one utterance per CTA (tunable: LIDFE_APPLY_ROWS)
 
 struct ApplyParams {
   float* feats;
@@ -674,6 +674,7 @@ struct ApplyParams {
   const long long* utt_out_row;  // [B]
   const double* glob_stats;      // [2*n_out+1] or NULL
   int normalize;                 // 0 -> masks only
+  int rows_per_cta;
 };
 
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__ ApplyParams P) {
@@ -682,9 +683,33 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   const int tid = threadIdx.x;
   const int utt = blockIdx.x;
   const long long T = P.utt_frames[utt];
-  const long long r0 = static_cast<long long>(blockIdx.y) * kApplyRows;
+  const long long r0 = static_cast<long long>(blockIdx.y) * P.rows_per_cta;
   if (r0 >= T) return;
-  const int rows = static_cast<int>(T - r0 < kApplyRows ? T - r0 : kApplyRows);
+  const int rows = static_cast<int>(T - r0 < P.rows_per_cta ? T - r0 : P.rows_per_cta);
+  float* base = P.feats + (P.utt_out_row[utt] + r0) * P.ld;
+  const bool vec = (P.n_out % 4 == 0) && (P.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.feats) & 15) == 0);
+
+  // flat float4 index i = tid + 256 q -> (row, col) advanced incrementally: no division in the loop.
+  // The first batch of loads is issued before the statistics are finalised, so its latency overlaps the fp64 prologue.
+  constexpr int kU = 5;                     // 64 rows x 20 float4 = 5 x 256 per batch
+  const int nvec = vec ? (P.n_out >> 2) : 1;
+  const int dr = 256 / nvec, dc = 256 - dr * nvec;
+  int r = tid / nvec, c = tid - r * nvec;
+  float4 x[kU];
+  int rr[kU], cc[kU];
+  auto load_batch = [&]() {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      rr[u] = r;
+      cc[u] = c;
+      if (r < rows) x[u] = *reinterpret_cast<const float4*>(base + static_cast<long long>(r) * P.ld + 4 * c);
+      r += dr;
+      c += dc;
+      if (c >= nvec) { c -= nvec; r += 1; }
+    }
+  };
+  if (vec) load_batch();
+
   if (tid < P.n_out) {
     float mean = 0.f, inv = 1.f;
     if (P.normalize) {
@@ -709,27 +734,10 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   if (tid < P.n_masks * 4) s_masks[tid] = P.masks[static_cast<long long>(utt) * P.n_masks * 4 + tid];
   __syncthreads();
 
-  float* base = P.feats + (P.utt_out_row[utt] + r0) * P.ld;
-  const bool vec = (P.n_out % 4 == 0) && (P.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.feats) & 15) == 0);
   if (vec) {
-    // flat float4 index i = tid + 256 q -> (row, col) advanced incrementally: no division in the loop
-    const int nvec = P.n_out >> 2;
-    const int dr = 256 / nvec, dc = 256 - dr * nvec;
-    int r = tid / nvec, c = tid - r * nvec;
-    constexpr int kU = 5;
     const int n_batches = (rows * nvec + 256 * kU - 1) / (256 * kU);
     for (int bt = 0; bt < n_batches; ++bt) {
-      float4 x[kU];
-      int rr[kU], cc[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        rr[u] = r;
-        cc[u] = c;
-        if (r < rows) x[u] = *reinterpret_cast<const float4*>(base + static_cast<long long>(r) * P.ld + 4 * c);
-        r += dr;
-        c += dc;
-        if (c >= nvec) { c -= nvec; r += 1; }
-      }
+      if (bt > 0) load_batch();
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         if (rr[u] >= rows) continue;
@@ -762,16 +770,16 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   } else {
     const int total = rows * P.n_out;
     for (int i = tid; i < total; i += 256) {
-      const int r = i / P.n_out;
-      const int d = i - r * P.n_out;
-      float* p = base + static_cast<long long>(r) * P.ld + d;
-      float x = *p;
-      if (P.normalize) x = (x - s_norm[d].x) * s_norm[d].y;
-      const int tf = static_cast<int>(r0) + r;
+      const int rw = i / P.n_out;
+      const int d = i - rw * P.n_out;
+      float* p = base + static_cast<long long>(rw) * P.ld + d;
+      float xv = *p;
+      if (P.normalize) xv = (xv - s_norm[d].x) * s_norm[d].y;
+      const int tf = static_cast<int>(r0) + rw;
       bool z = false;
       for (int q = 0; q < P.n_masks; ++q)
         z |= (tf >= s_masks[4 * q] && tf < s_masks[4 * q + 1]) || (d >= s_masks[4 * q + 2] && d < s_masks[4 * q + 3]);
-      *p = z ? 0.f : x;
+      *p = z ? 0.f : xv;
     }
   }
 }
