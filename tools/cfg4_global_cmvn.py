@@ -80,7 +80,12 @@ def main():
             b = [tuple(int(v) for v in masks[j, q]) for q in range(masks.shape[1])]
             ref = O.apply_mask_bounds(ref.T.unsqueeze(0), b)[0].T
             got = feats[row:row + T].cpu()
-            assert torch.equal(got == 0, ref == 0), "mask positions differ (rank %d utt %d)" % (rank, j)
+            # every masked position is exactly 0 (an unmasked value may also be 0: x == mean to fp32 precision)
+            masked = torch.zeros_like(ref, dtype=torch.bool)
+            for t0, t1, f0, f1 in b:
+                masked[t0:t1, :] = True
+                masked[:, f0:f1] = True
+            assert torch.all(got[masked] == 0), "masked positions not zero (rank %d utt %d)" % (rank, j)
             worst = max(worst, float((got - ref).abs().max()))
         row += T
     assert worst < 5e-3, worst      # 1/std amplifies the fbank round-off of the three low bins
