@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LIDFE_ABI_VERSION 1
+#define LIDFE_ABI_VERSION 2
 
 /* error codes (negative) */
 #define LIDFE_OK 0
@@ -49,6 +49,15 @@ extern "C" {
 #define LIDFE_CMVN_PER_UTT 1       /* per utterance, per output dim: (x - mean_t) / (std_t + 1e-9), unbiased */
 #define LIDFE_CMVN_APPLY_GLOBAL 2  /* normalise in the fbank epilogue with caller-supplied global sums */
 #define LIDFE_CMVN_ACCUM_GLOBAL 3  /* write raw features, add [sum, sumsq, count] to stats_out_dev */
+#define LIDFE_POST_TOPDB 4         /* AmplitudeToDB(top_db): clamp every value of an utterance at (its max - cfg.top_db) */
+
+/* framing */
+#define LIDFE_FRAMING_KALDI 0      /* snip_edges=True: frame f = x[160 f, 160 f + 400), 1 + (N-400)/160 frames */
+#define LIDFE_FRAMING_CENTER 1     /* torch.stft(center=True, reflect): frame f centred at 160 f over the (constant-
+                                      padded) signal, 1 + (N + 2 pad)/160 frames; window centred in the 512-point FFT */
+/* log flavours */
+#define LIDFE_LOG_NATURAL 0        /* log(max(x, log_floor))           (kaldi fbank) */
+#define LIDFE_LOG_DB10 1           /* 10*log10(max(x, log_floor))      (AmplitudeToDB, power) */
 
 typedef struct lidfe_ctx* lidfe_handle;
 typedef struct lidfe_plan_s* lidfe_plan;
@@ -56,6 +65,10 @@ typedef struct lidfe_plan_s* lidfe_plan;
 /*
  * Front-end configuration.  Mirrors the argument set the reference passes to
  * torchaudio.compliance.kaldi.fbank (ref: lid/audio_processor.py:41-69; ta: compliance/kaldi.py:514-541).
+ * The same struct configures the reference's default branch, MelSpectrogram + AmplitudeToDB(top_db=80)
+ * (ref: lid/audio_processor.py:72-105): framing CENTER, preemph 0, remove_dc 0, periodic Hann window, HTK mel bank,
+ * log_kind DB10, log_floor 1e-10, top_db 80 -- the |FFT|^2 of a frame does not depend on where the 400-sample window
+ * sits inside the 512-point buffer, so the kernel is shared.
  * Supported geometry this round: sample_rate 16000, frame_len 400, frame_shift 160, fft_len 512,
  * 4 <= n_mels <= 80, n_ceps 0 (fbank) or 1..n_mels (MFCC).  Anything else -> LIDFE_E_CONFIG (the survey
  * asks for a loud error rather than silent mis-framing at other rates).
@@ -72,6 +85,11 @@ typedef struct {
   float log_floor;   /* 1.1920929e-07 (FLT_EPSILON)                              */
   int in_dtype;      /* LIDFE_IN_F32 | LIDFE_IN_I16                              */
   float in_scale;    /* multiplier applied to int16 samples (ignored for f32)    */
+  /* -- MelSpectrogram + AmplitudeToDB branch (ref: lid/audio_processor.py:72-105); all zero for the kaldi branch -- */
+  int framing;       /* LIDFE_FRAMING_KALDI | LIDFE_FRAMING_CENTER               */
+  int pad;           /* MelSpectrogram(pad=...): zeros added on both sides (CENTER framing only) */
+  int log_kind;      /* LIDFE_LOG_NATURAL | LIDFE_LOG_DB10                       */
+  float top_db;      /* LIDFE_POST_TOPDB: 80.0 in the reference                  */
 } lidfe_config;
 
 /* -- lifetime ------------------------------------------------------------------------------------- */
@@ -90,8 +108,9 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
                  const float* melbank_host, const float* dct_host, const float* lifter_host);
 int lidfe_destroy(lidfe_handle h);
 
-/* Number of frames kaldi's snip_edges=True framing yields (ta: compliance/kaldi.py:63-67):
- * 1 + (n - frame_len) / frame_shift, or 0 when n < frame_len.  Host helper, integer-exact. */
+/* Number of frames.  KALDI framing (ta: compliance/kaldi.py:63-67): 1 + (n - frame_len) / frame_shift, or 0 when
+ * n < frame_len.  CENTER framing (torch.stft): 1 + (n + 2 pad) / frame_shift, or 0 when n + 2 pad <= fft_len / 2
+ * (reflect padding needs more samples than it mirrors; torch raises there).  Host helper, integer-exact. */
 long long lidfe_num_frames(long long n_samples, const lidfe_config* cfg);
 
 /* Output feature dimension: n_ceps if n_ceps > 0 else n_mels. */

@@ -163,6 +163,53 @@ def wav2mel_kaldi(x: torch.Tensor, win_length: float = 0.025, hop_length: float 
 
 
 # --------------------------------------------------------------------------------------
+# A9  the reference's DEFAULT branch: MelSpectrogram + AmplitudeToDB(top_db=80)
+#                                                       ref: lid/audio_processor.py:72-105
+#     ta: transforms/_transforms.py (Spectrogram, MelScale, AmplitudeToDB), functional/functional.py:54-146,
+#         :356-403 (amplitude_to_DB), :425-588 (_hz_to_mel, _mel_to_hz, melscale_fbanks)
+# --------------------------------------------------------------------------------------
+def htk_mel_fbanks(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """(n_freqs, n_mels) triangular filters on the HTK scale 2595*log10(1+f/700), norm=None.
+    ta: functional/functional.py:492-588"""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + (f_min / 700.0))
+    m_max = 2595.0 * math.log10(1.0 + (f_max / 700.0))
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+def num_frames_centered(num_samples: int, hop: int = 160, pad: int = 0) -> int:
+    """torch.stft(center=True): 1 + (N + 2*pad) // hop"""
+    return 1 + (num_samples + 2 * pad) // hop
+
+
+def melspec_db(x: torch.Tensor, win_length: float = 0.025, hop_length: float = 0.01, n_mels: int = 80,
+               n_fft: int = 512, pad: int = 0, sr: int = 16000, top_db: Optional[float] = 80.0) -> torch.Tensor:
+    """``wav2mel(x, use_kaildi=False)``: (1,N) -> (1, n_mels, 1 + (N+2*pad)//hop).  Note the reference does not forward
+    ``sr`` to MelSpectrogram's mel scale (always 16 kHz): kept."""
+    win = int(sr * win_length)
+    hop = int(sr * hop_length)
+    if pad > 0:
+        x = torch.nn.functional.pad(x, (pad, pad), "constant")
+    window = torch.hann_window(win)
+    spec = torch.stft(input=x, n_fft=n_fft, hop_length=hop, win_length=win, window=window, center=True,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    spec = spec.abs().pow(2.0)                                                   # (1, n_fft/2+1, T)
+    fb = htk_mel_fbanks(n_fft // 2 + 1, 0.0, float(16000 // 2), n_mels, 16000)
+    mel = torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)             # (1, n_mels, T)
+    db = 10.0 * torch.log10(torch.clamp(mel, min=1e-10))
+    db -= 10.0 * math.log10(max(1e-10, 1.0))
+    if top_db is not None:
+        db = torch.max(db, (db.amax(dim=(-3, -2, -1)) - top_db).view(-1, 1, 1))
+    return db
+
+
+# --------------------------------------------------------------------------------------
 # A5  MFCC (not in the reference; pinned to torchaudio.compliance.kaldi.mfcc with A4's framing)
 #                                                       ta: compliance/kaldi.py:669-813
 # --------------------------------------------------------------------------------------

@@ -14,7 +14,10 @@ LIB_PATH = os.path.join(_HERE, "liblidfe.so")
 # include/lidfe.h
 E_NULL, E_CONFIG, E_SHORT, E_OFFSETS, E_ARG, E_MELBANK, E_NOMEM = -1, -2, -3, -4, -5, -6, -7
 IN_F32, IN_I16 = 0, 1
-CMVN_NONE, CMVN_PER_UTT, CMVN_APPLY_GLOBAL, CMVN_ACCUM_GLOBAL = 0, 1, 2, 3
+CMVN_NONE, CMVN_PER_UTT, CMVN_APPLY_GLOBAL, CMVN_ACCUM_GLOBAL, POST_TOPDB = 0, 1, 2, 3, 4
+FRAMING_KALDI, FRAMING_CENTER = 0, 1
+LOG_NATURAL, LOG_DB10 = 0, 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "lidfe_create", "lidfe_destroy", "lidfe_num_frames", "lidfe_out_dim", "lidfe_plan_create",
@@ -28,7 +31,8 @@ class LidfeConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_int), ("frame_len", C.c_int), ("frame_shift", C.c_int),
                 ("fft_len", C.c_int), ("n_mels", C.c_int), ("n_ceps", C.c_int), ("preemph", C.c_float),
                 ("remove_dc", C.c_int), ("log_floor", C.c_float), ("in_dtype", C.c_int),
-                ("in_scale", C.c_float)]
+                ("in_scale", C.c_float), ("framing", C.c_int), ("pad", C.c_int), ("log_kind", C.c_int),
+                ("top_db", C.c_float)]
 
 
 class LidfeError(RuntimeError):

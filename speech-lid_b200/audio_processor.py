@@ -23,12 +23,13 @@ from .specaug import draw_masks
 _frontends: Dict[Tuple, FrontEnd] = {}
 
 
-def _frontend(n_mels: int, sr: int, win_length: float, hop_length: float, device) -> FrontEnd:
-    key = (int(n_mels), int(sr), float(win_length), float(hop_length), str(device))
+def _frontend(n_mels: int, sr: int, win_length: float, hop_length: float, device, kind: str = "kaldi",
+              pad: int = 0) -> FrontEnd:
+    key = (int(n_mels), int(sr), float(win_length), float(hop_length), str(device), kind, int(pad))
     fe = _frontends.get(key)
     if fe is None:
         fe = FrontEnd(n_mels=n_mels, sr=sr, win_length=win_length, hop_length=hop_length, preemph=1.0,
-                      device=device)
+                      device=device, kind=kind, pad=pad)
         _frontends[key] = fe
     return fe
 
@@ -39,17 +40,23 @@ def _device_of(x: torch.Tensor):
 
 def wav2mel(x, use_kaildi: bool = False, win_length: float = 0.025, hop_length: float = 0.01,
             n_mels: int = 80, n_fft: int = 512, pad: int = 0, sr: int = 16000):
-    """x (1, T) -> (1, n_mels, T').  ``use_kaildi=True`` is the Kaldi-fbank branch
-    (``n_fft`` and ``pad`` are ignored by it, as in the reference, ref: lid/audio_processor.py:27-29)."""
-    if not use_kaildi:
-        raise NotImplementedError(
-            "speech_lid_b200: the MelSpectrogram+AmplitudeToDB branch (use_kaildi=False, "
-            "ref: lid/audio_processor.py:72-105) is the next row of the scope table and is not built yet; "
-            "call wav2mel(..., use_kaildi=True)")
+    """x (1, T) -> (1, n_mels, T').  ``use_kaildi=True`` is the Kaldi-fbank branch (``n_fft`` and ``pad`` are ignored by
+    it, as in the reference, ref: lid/audio_processor.py:27-29); the default is MelSpectrogram + AmplitudeToDB(top_db=80)
+    (ref: lid/audio_processor.py:72-105)."""
     if x.dim() != 2:
         raise ValueError("wav2mel expects a (channel, time) tensor")
-    fe = _frontend(n_mels, sr, win_length, hop_length, _device_of(x))
-    plan = fe.make_plan([x.shape[-1]], padded=False)          # raises AssertionError when T < 400
+    if use_kaildi:
+        fe = _frontend(n_mels, sr, win_length, hop_length, _device_of(x))
+    else:
+        # default branch: MelSpectrogram(n_fft, win, hop, pad, center, reflect, power 2) + AmplitudeToDB(top_db=80)
+        if n_fft != 512:
+            raise NotImplementedError("speech_lid_b200: only n_fft=512 is built (the value every config uses)")
+        if x.shape[0] != 1:
+            raise ValueError("the MelSpectrogram branch is built for mono (1, T) input")
+        fe = _frontend(n_mels, sr, win_length, hop_length, _device_of(x), kind="melspec_db", pad=pad)
+        if fe.num_frames(x.shape[-1]) <= 0:      # torch.stft: reflect padding needs more samples than it mirrors
+            raise RuntimeError("Argument #4: Padding size should be less than the corresponding input dimension")
+    plan = fe.make_plan([x.shape[-1]], padded=False)          # kaldi branch: AssertionError when T < 400
     packed = fe.pack([x], plan)
     feats = fe.featurize_packed(packed, plan)                  # (T', n_mels)
     out = feats.transpose(0, 1).unsqueeze(0)                   # ref: lid/audio_processor.py:63-65

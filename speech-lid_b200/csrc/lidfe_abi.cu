@@ -51,6 +51,7 @@ struct lidfe_plan_s {
   long long* d_offsets;   // [B]
   long long* d_lengths;   // [B]
   double* d_utt_stats;    // [B][2][n_out]
+  unsigned* d_utt_max;    // [B] (LIDFE_POST_TOPDB)
 };
 
 static std::atomic<long long> g_launches{0};
@@ -195,6 +196,11 @@ const char* lidfe_strerror(int rc) {
 
 long long lidfe_num_frames(long long n_samples, const lidfe_config* cfg) {
   if (!cfg || cfg->frame_len <= 0 || cfg->frame_shift <= 0) return 0;
+  if (cfg->framing == LIDFE_FRAMING_CENTER) {
+    const long long L = n_samples + 2LL * cfg->pad;
+    if (n_samples < 0 || L <= cfg->fft_len / 2) return 0;      // torch.stft: reflect padding must be < input length
+    return 1 + L / cfg->frame_shift;
+  }
   if (n_samples < cfg->frame_len) return 0;
   return 1 + (n_samples - cfg->frame_len) / cfg->frame_shift;
 }
@@ -234,7 +240,10 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   if (cfg->sample_rate != 16000 || cfg->frame_len != kFrameLen || cfg->frame_shift != kFrameShift ||
       cfg->fft_len != kFftLen || cfg->n_mels < 4 || cfg->n_mels > kMaxMels || cfg->n_ceps < 0 ||
       cfg->n_ceps > cfg->n_mels || (cfg->in_dtype != LIDFE_IN_F32 && cfg->in_dtype != LIDFE_IN_I16) ||
-      !(cfg->preemph >= 0.f && cfg->preemph <= 1.f))
+      !(cfg->preemph >= 0.f && cfg->preemph <= 1.f) ||
+      (cfg->framing != LIDFE_FRAMING_KALDI && cfg->framing != LIDFE_FRAMING_CENTER) || cfg->pad < 0 ||
+      cfg->pad > 4096 || (cfg->framing == LIDFE_FRAMING_KALDI && cfg->pad != 0) ||
+      (cfg->log_kind != LIDFE_LOG_NATURAL && cfg->log_kind != LIDFE_LOG_DB10) || !(cfg->log_floor > 0.f))
     return LIDFE_E_CONFIG;
   if (cfg->n_ceps > 0 && !dct_host) return LIDFE_E_NULL;
 
@@ -376,14 +385,22 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
     if (T > 0x7fffffffLL) return LIDFE_E_ARG;
     frames[i] = T;
     total += T;
-    const bool aligned = ((static_cast<unsigned long long>(wav_offsets_host[i]) * in_elt) % 16ull) == 0ull;
+    const bool center = h->cfg.framing == LIDFE_FRAMING_CENTER;
+    const long long N = wav_lengths_host[i], cpad = h->cfg.pad;
     for (long long f = 0; f < T; f += kTileFrames) {
       Tile tl;
-      tl.wav_off = wav_offsets_host[i] + f * kFrameShift;
       tl.out_row = out_rows_host[i] + f;
       tl.nframes = static_cast<int>((T - f) < kTileFrames ? (T - f) : kTileFrames);
       tl.utt = i;
       tl.t0 = static_cast<int>(f);
+      // first sample of the tile relative to the utterance's first sample.  CENTER framing: frame f covers
+      // p[160 f - 200, 160 f + 200) of the constant-padded signal p (the Hann window sits at 56..455 of the 512-point
+      // buffer and |FFT|^2 does not see that shift); tiles that touch the padding / reflection are staged element-wise.
+      const long long rel = center ? f * kFrameShift - kFrameLen / 2 - cpad : f * kFrameShift;
+      const long long nsamp = static_cast<long long>(kFrameShift) * tl.nframes + (kFrameLen - kFrameShift);
+      const bool interior = rel >= 0 && rel + nsamp <= N;
+      tl.wav_off = wav_offsets_host[i] + rel;
+      const bool aligned = interior && ((static_cast<unsigned long long>(tl.wav_off) * in_elt) % 16ull) == 0ull;
       tl.aux = aligned ? 1 : 0;
       tiles.push_back(tl);
     }
@@ -418,6 +435,7 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   p->d_offsets = nullptr;
   p->d_lengths = nullptr;
   p->d_utt_stats = nullptr;
+  p->d_utt_max = nullptr;
   cudaError_t e = upload(&p->d_tiles, tiles.data(), tiles.size());
   if (e == cudaSuccess) e = upload(&p->d_frames, frames.data(), frames.size());
   if (e == cudaSuccess) e = upload(&p->d_out_rows, out_rows_host, static_cast<size_t>(B));
@@ -425,6 +443,7 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   if (e == cudaSuccess) e = upload(&p->d_lengths, wav_lengths_host, static_cast<size_t>(B));
   if (e == cudaSuccess)
     e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_stats), static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_max), static_cast<size_t>(B) * sizeof(unsigned));
   if (e != cudaSuccess) {
     cudaGetLastError();
     lidfe_plan_destroy(p);
@@ -442,6 +461,7 @@ int lidfe_plan_destroy(lidfe_plan p) {
   cudaFree(p->d_offsets);
   cudaFree(p->d_lengths);
   cudaFree(p->d_utt_stats);
+  cudaFree(p->d_utt_max);
   delete p;
   return LIDFE_OK;
 }
@@ -450,7 +470,7 @@ long long lidfe_plan_num_tiles(lidfe_plan p) { return p ? p->n_tiles : 0; }
 long long lidfe_plan_frames(lidfe_plan p, int i) { return (p && i >= 0 && i < p->B) ? p->frames[i] : 0; }
 
 static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, const int* masks, int n_masks,
-                        const double* utt_stats, const double* glob_stats, cudaStream_t st) {
+                        const double* utt_stats, const double* glob_stats, cudaStream_t st, int normalize) {
   ApplyParams A;
   A.feats = feats;
   A.ld = ld;
@@ -461,7 +481,9 @@ static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, 
   A.utt_frames = p->d_frames;
   A.utt_out_row = p->d_out_rows;
   A.glob_stats = glob_stats;
-  A.normalize = (utt_stats || glob_stats) ? 1 : 0;
+  A.normalize = normalize;
+  A.utt_max = p->d_utt_max;
+  A.top_db = h->cfg.top_db;
   int rows_per_cta = kApplyRowsDefault;
   if (const char* env = getenv("LIDFE_APPLY_ROWS")) {
     const int v = atoi(env);
@@ -482,7 +504,7 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
                     double* stats_out_dev, void* stream) {
   if (!h || !p || !wav_dev || !out_dev) return LIDFE_E_NULL;
   if (p->ctx != h) return LIDFE_E_ARG;
-  if (out_ld < h->n_out || cmvn_mode < 0 || cmvn_mode > 3 || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
+  if (out_ld < h->n_out || cmvn_mode < 0 || cmvn_mode > 4 || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
   if (cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL && !stats_in_dev) return LIDFE_E_NULL;
   if (cmvn_mode == LIDFE_CMVN_ACCUM_GLOBAL && !stats_out_dev) return LIDFE_E_NULL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -507,7 +529,18 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   P.n_out = h->n_out;
   P.preemph = h->cfg.preemph;
   P.log_floor = h->cfg.log_floor;
-  P.log_of_floor = logf(h->cfg.log_floor);
+  if (h->cfg.log_kind == LIDFE_LOG_DB10) {
+    P.log_of_floor = 10.0f * log10f(h->cfg.log_floor);       // 10 * log10(amin), fp32 like the reference
+    P.log_scale = 3.01029995663981195f;                       // 10 * log10(2)
+  } else {
+    P.log_of_floor = logf(h->cfg.log_floor);
+    P.log_scale = 0.693147180559945309f;                      // ln 2
+  }
+  P.center = (h->cfg.framing == LIDFE_FRAMING_CENTER) ? 1 : 0;
+  P.pad = h->cfg.pad;
+  P.utt_offsets = p->d_offsets;
+  P.utt_lengths = p->d_lengths;
+  P.utt_max = p->d_utt_max;
   P.in_scale = h->cfg.in_scale;
   P.remove_dc = h->cfg.remove_dc;
   P.masks = masks_dev;
@@ -519,6 +552,8 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
 
   if (cmvn_mode == LIDFE_CMVN_PER_UTT)
     CU_TRY(cudaMemsetAsync(p->d_utt_stats, 0, static_cast<size_t>(p->B) * 2 * h->n_out * sizeof(double), st));
+  if (cmvn_mode == LIDFE_POST_TOPDB)
+    CU_TRY(cudaMemsetAsync(p->d_utt_max, 0, static_cast<size_t>(p->B) * sizeof(unsigned), st));
 
   long long grid = p->n_tiles < h->grid_cap ? p->n_tiles : h->grid_cap;
   if (grid < 1) grid = 1;
@@ -534,7 +569,9 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   }
 
   if (cmvn_mode == LIDFE_CMVN_PER_UTT)
-    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, p->d_utt_stats, nullptr, st);
+    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, p->d_utt_stats, nullptr, st, 1);
+  if (cmvn_mode == LIDFE_POST_TOPDB)
+    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, nullptr, st, 2);
   return LIDFE_OK;
 }
 
@@ -542,7 +579,7 @@ int lidfe_cmvn_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
                      const double* stats_dev, void* stream) {
   if (!h || !p || !feats_dev || !stats_dev) return LIDFE_E_NULL;
   if (p->ctx != h || ld < h->n_out || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
-  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, stats_dev, static_cast<cudaStream_t>(stream));
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, stats_dev, static_cast<cudaStream_t>(stream), 1);
 }
 
 int lidfe_profile_begin(lidfe_handle h, int max_launches) {
@@ -579,7 +616,7 @@ int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
                      void* stream) {
   if (!h || !p || !feats_dev || !masks_dev) return LIDFE_E_NULL;
   if (p->ctx != h || ld < h->n_out || n_masks < 1 || n_masks > kMaxMasks) return LIDFE_E_ARG;
-  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, nullptr, static_cast<cudaStream_t>(stream), 0);
 }
 
 int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,

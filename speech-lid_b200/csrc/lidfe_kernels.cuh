@@ -68,7 +68,12 @@ struct FbankParams {
   const float* lifter;      // [n_ceps] (ones when no liftering)
   int band_taps[kBands];    // taps per band
   int n_mels, n_ceps, n_out;
-  float preemph, log_floor, log_of_floor, in_scale;   // log_of_floor = logf(log_floor), rounded on the host
+  float preemph, log_floor, log_of_floor, in_scale;   // log_of_floor = the reference's log of the floor, rounded on the host
+  float log_scale;          // lg2(x) * log_scale: ln 2 (natural log) or 10 log10(2) (dB)
+  int center, pad;          // LIDFE_FRAMING_CENTER: frames centred at 160 f over the constant-padded, reflect-extended signal
+  const long long* utt_offsets;  // [B] first sample of each utterance (edge tiles of CENTER framing)
+  const long long* utt_lengths;  // [B]
+  unsigned* utt_max;        // [B] order-preserving encoding of the utterance's max feature (LIDFE_POST_TOPDB)
   int remove_dc;
   // epilogue
   const int* masks;         // [B][n_masks][4]
@@ -110,6 +115,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// order-preserving float -> uint map (atomicMax on floats of either sign); 0 is below every finite value
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
 // ---- packed f32x2 arithmetic: .x = frame A, .y = frame B (SASS: FADD2 / FMUL2 / FFMA2) ---------------
@@ -232,7 +246,7 @@ struct SmemLayout {
   static constexpr int off_k0 = off_tw2 + 128 * 8;                                 // [80] int
   static constexpr int off_norm = off_k0 + kMaxMels * 4;                           // [80] float2 (mean, inv_std)
   static constexpr int off_acc = off_norm + kMaxMels * 8;                          // fp64: [kWarps][2][80] per-warp sums + frame count
-  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 2) * 8;               // [kMaxMasks][4] int
+  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;               // [kMaxMasks][4] int
   static constexpr int off_bar = off_masks + kMaxMasks * 16;                       // 2 mbarriers
   static constexpr int off_tiles = off_bar + 16;                                   // [kTileCache] Tile descriptors
   static constexpr int off_melw = off_tiles + kTileCache * 32;                                    // sum(band_taps)*16 floats, then dct, lifter
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
       for (int i = tid; i < P.n_ceps; i += kThreads) sm_lifter[i] = P.lifter[i];
     }
     for (int i = tid; i < kWarps * 2 * kMaxMels + 2; i += kThreads) sm_acc[i] = 0.0;
+    if (tid < kWarps) reinterpret_cast<float*>(sm_acc + kWarps * 2 * kMaxMels + 2)[tid] = -INFINITY;
     if (mode == 2 && tid < n_out) {
       // finalise the all-reduced sums: mean, 1/(std + 1e-9) (unbiased)
       const double n = P.stats_in[2 * n_out];
@@ -335,8 +350,21 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         mbar_expect_tx(&sm_bar[buf], bytes);
         tma_bulk_g2s(dst, src, bytes, &sm_bar[buf]);
       }
-    } else {
+    } else if (!P.center) {
       for (int i = tid; i < nsamp; i += kThreads) dst[i] = src[i];
+    } else {
+      // edge tile of the centred framing: index u of the constant-padded signal p (length L = N + 2 pad), mirrored
+      // once at either end like torch.stft(center=True, pad_mode="reflect"); zeros inside the constant padding
+      const long long N = P.utt_lengths[tl.utt];
+      const TIn* x = reinterpret_cast<const TIn*>(P.wav) + P.utt_offsets[tl.utt];
+      const long long L = N + 2 * P.pad;
+      const long long u0 = static_cast<long long>(kFrameShift) * tl.t0 - (kFrameLen / 2);
+      for (int i = tid; i < nsamp; i += kThreads) {
+        long long u = u0 + i;
+        u = u < 0 ? -u : (u >= L ? 2 * (L - 1) - u : u);
+        const long long r = u - P.pad;
+        dst[i] = (r >= 0 && r < N) ? x[r] : static_cast<TIn>(0);
+      }
     }
   };
 
@@ -542,8 +570,8 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
           for (int i = 0; i < taps[b]; ++i) acc = fma2(pp[i], bc(wp[i * 16]), acc);
         }
         // lg2.approx (abs. error ~1e-7 in the log) except at the floor, where the reference's log(eps) is returned exactly
-        val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : __logf(acc.x),
-                             acc.y <= P.log_floor ? P.log_of_floor : __logf(acc.y));
+        val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : __log2f(acc.x) * P.log_scale,
+                             acc.y <= P.log_floor ? P.log_of_floor : __log2f(acc.y) * P.log_scale);
       }
 
       // ---- MFCC: DCT-II + lifter (ta: compliance/kaldi.py:648-666,786-796) --------------------------
@@ -624,7 +652,38 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         wacc[kMaxMels + d] = a2;
       }
     }
+    float* const sm_wmax = reinterpret_cast<float*>(sm_acc + kWarps * 2 * kMaxMels + 2);
+    if (mode == 4) {   // AmplitudeToDB(top_db): running max of this warp's live features (ta: functional/functional.py:391-403)
+      float m = -INFINITY;
+#pragma unroll
+      for (int b = 0; b < kBands; ++b)
+        if (t + 16 * b < n_out) {
+          if (actA) m = fmaxf(m, val[b].x);
+          if (actB) m = fmaxf(m, val[b].y);
+        }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) sm_wmax[warp] = fmaxf(sm_wmax[warp], m);
+    }
     __syncthreads();   // everyone is done with this input buffer and sm_masks
+    if (mode == 4) {
+      bool flush = (tile_idx + 1 == tile_end);
+      if (!flush) {
+        const Tile nx = sm_tiles[(it + 1) % kTileCache];
+        flush = (nx.nframes == 0) || (nx.utt != tl.utt);
+      }
+      if (flush) {
+        if (tid == 0) {
+          float m = sm_wmax[0];
+#pragma unroll
+          for (int w = 1; w < kWarps; ++w) m = fmaxf(m, sm_wmax[w]);
+          atomicMax(&P.utt_max[tl.utt], f2ord(m));
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) sm_wmax[w] = -INFINITY;
+        }
+        __syncthreads();
+      }
+    }
     if (want_stats) {
       bool flush = (tile_idx + 1 == tile_end);
       if (!flush) {    // zero-fill tiles skip this block, so sums are also handed over before one
@@ -673,8 +732,10 @@ struct ApplyParams {
   const long long* utt_frames;   // [B]
   const long long* utt_out_row;  // [B]
   const double* glob_stats;      // [2*n_out+1] or NULL
-  int normalize;                 // 0 -> masks only
+  int normalize;                 // 0 -> masks only, 1 -> (x - mean) * inv_std, 2 -> max(x, utt_max - top_db)
   int rows_per_cta;
+  const unsigned* utt_max;       // [B] (normalize == 2)
+  float top_db;
 };
 
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__ ApplyParams P) {
@@ -710,9 +771,10 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   };
   if (vec) load_batch();
 
+  const float db_floor = (P.normalize == 2) ? ord2f(P.utt_max[utt]) - P.top_db : 0.f;
   if (tid < P.n_out) {
     float mean = 0.f, inv = 1.f;
-    if (P.normalize) {
+    if (P.normalize == 1) {
       double n, sm, ss;
       if (P.utt_stats) {
         n = static_cast<double>(T);
@@ -743,12 +805,17 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
         if (rr[u] >= rows) continue;
         const int d = 4 * cc[u];
         float4 v = x[u];
-        if (P.normalize) {
+        if (P.normalize == 1) {
           const float2 n0 = s_norm[d], n1 = s_norm[d + 1], n2 = s_norm[d + 2], n3 = s_norm[d + 3];
           v.x = (v.x - n0.x) * n0.y;
           v.y = (v.y - n1.x) * n1.y;
           v.z = (v.z - n2.x) * n2.y;
           v.w = (v.w - n3.x) * n3.y;
+        } else if (P.normalize == 2) {
+          v.x = fmaxf(v.x, db_floor);
+          v.y = fmaxf(v.y, db_floor);
+          v.z = fmaxf(v.z, db_floor);
+          v.w = fmaxf(v.w, db_floor);
         }
         const int tf = static_cast<int>(r0) + rr[u];
         bool zr = false, z0 = false, z1 = false, z2 = false, z3 = false;
@@ -774,7 +841,8 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
       const int d = i - rw * P.n_out;
       float* p = base + static_cast<long long>(rw) * P.ld + d;
       float xv = *p;
-      if (P.normalize) xv = (xv - s_norm[d].x) * s_norm[d].y;
+      if (P.normalize == 1) xv = (xv - s_norm[d].x) * s_norm[d].y;
+      else if (P.normalize == 2) xv = fmaxf(xv, db_floor);
       const int tf = static_cast<int>(r0) + rw;
       bool z = false;
       for (int q = 0; q < P.n_masks; ++q)

@@ -17,7 +17,7 @@ import torch
 from . import _lib, tables
 
 CMVN_MODES = {"none": _lib.CMVN_NONE, "utt": _lib.CMVN_PER_UTT, "global_apply": _lib.CMVN_APPLY_GLOBAL,
-              "global_accum": _lib.CMVN_ACCUM_GLOBAL}
+              "global_accum": _lib.CMVN_ACCUM_GLOBAL, "topdb": _lib.POST_TOPDB}
 LOG_FLOOR = float(torch.finfo(torch.float32).eps)   # ta: compliance/kaldi.py:22
 
 
@@ -81,7 +81,17 @@ class FrontEnd:
     def __init__(self, n_mels: int = 80, n_ceps: int = 0, sr: int = 16000, win_length: float = 0.025,
                  hop_length: float = 0.01, preemph: float = 1.0, cepstral_lifter: float = 22.0,
                  remove_dc: bool = True, in_dtype: torch.dtype = torch.float32, in_scale: float = 1.0,
-                 device: Union[str, torch.device, None] = None):
+                 device: Union[str, torch.device, None] = None, kind: str = "kaldi", pad: int = 0,
+                 top_db: float = 80.0):
+        """``kind="kaldi"``: the ``use_kaildi=True`` branch (ref: lid/audio_processor.py:41-69).
+        ``kind="melspec_db"``: the reference's default branch, MelSpectrogram(n_fft=512, win 400, hop 160, pad,
+        center, reflect, power 2, HTK mel 0-8 kHz) + AmplitudeToDB(top_db=80) (ref: lid/audio_processor.py:72-105);
+        ``preemph`` / ``remove_dc`` / ``n_ceps`` do not apply to it."""
+        if kind not in ("kaldi", "melspec_db"):
+            raise ValueError("kind must be 'kaldi' or 'melspec_db'")
+        self.kind = kind
+        if kind == "melspec_db":
+            preemph, remove_dc, n_ceps = 0.0, False, 0
         self.lib = _lib.load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("speech_lid_b200.FrontEnd needs a CUDA device (sm_100a); there is no CPU path")
@@ -90,14 +100,23 @@ class FrontEnd:
             raise ValueError("in_dtype must be torch.float32 or torch.int16")
         # seconds -> milliseconds -> samples exactly as the reference + torchaudio do
         # (ref: lid/audio_processor.py:50-51; ta: compliance/kaldi.py:138-140)
-        frame_len = int(sr * int(1000 * win_length) * 0.001)
-        frame_shift = int(sr * int(1000 * hop_length) * 0.001)
+        if kind == "melspec_db":       # samples straight from seconds (ref: lid/audio_processor.py:89-90)
+            frame_len = int(sr * win_length)
+            frame_shift = int(sr * hop_length)
+        else:
+            frame_len = int(sr * int(1000 * win_length) * 0.001)
+            frame_shift = int(sr * int(1000 * hop_length) * 0.001)
         fft_len = 1 if frame_len == 0 else 2 ** (frame_len - 1).bit_length()
         self.cfg = _lib.LidfeConfig(sample_rate=int(sr), frame_len=frame_len, frame_shift=frame_shift,
                                     fft_len=fft_len, n_mels=int(n_mels), n_ceps=int(n_ceps),
                                     preemph=float(preemph), remove_dc=int(bool(remove_dc)),
-                                    log_floor=LOG_FLOOR, in_dtype=_lib.IN_I16 if in_dtype == torch.int16 else _lib.IN_F32,
-                                    in_scale=float(in_scale))
+                                    log_floor=LOG_FLOOR if kind == "kaldi" else 1e-10,
+                                    in_dtype=_lib.IN_I16 if in_dtype == torch.int16 else _lib.IN_F32,
+                                    in_scale=float(in_scale),
+                                    framing=_lib.FRAMING_KALDI if kind == "kaldi" else _lib.FRAMING_CENTER,
+                                    pad=int(pad) if kind == "melspec_db" else 0,
+                                    log_kind=_lib.LOG_NATURAL if kind == "kaldi" else _lib.LOG_DB10,
+                                    top_db=float(top_db))
         self.in_dtype = in_dtype
         self.n_mels, self.n_ceps = int(n_mels), int(n_ceps)
         self.n_out = self.n_ceps if self.n_ceps > 0 else self.n_mels
@@ -105,8 +124,12 @@ class FrontEnd:
         self.align = 8 if in_dtype == torch.int16 else 4     # samples per 16 bytes (TMA bulk copy granularity)
         if frame_len != 400 or frame_shift != 160 or int(sr) != 16000:
             _lib.check(_lib.E_CONFIG)
-        window = tables.povey_window(frame_len).contiguous()
-        banks = tables.mel_banks(self.n_mels, fft_len, float(sr)).contiguous()
+        if kind == "kaldi":
+            window = tables.povey_window(frame_len).contiguous()
+            banks = tables.mel_banks(self.n_mels, fft_len, float(sr)).contiguous()
+        else:
+            window = tables.hann_window(frame_len).contiguous()
+            banks = tables.htk_mel_banks(self.n_mels, fft_len).contiguous()
         dct = tables.dct_matrix(self.n_ceps, self.n_mels).contiguous() if self.n_ceps > 0 else None
         lift = tables.lifter(self.n_ceps, cepstral_lifter).contiguous() if self.n_ceps > 0 else None
         self._tables = (window, banks, dct, lift)
@@ -141,7 +164,8 @@ class FrontEnd:
 
     # ------------------------------------------------------------------ frame arithmetic
     def num_frames(self, n_samples: int) -> int:
-        """1 + (N - 400) // 160 (0 if N < 400)          ta: compliance/kaldi.py:63-67"""
+        """kaldi: 1 + (N - 400) // 160 (0 if N < 400), ta: compliance/kaldi.py:63-67;
+        melspec_db: 1 + (N + 2 pad) // 160 (torch.stft, center=True)"""
         return int(self.lib.lidfe_num_frames(int(n_samples), C.byref(self.cfg)))
 
     # ------------------------------------------------------------------ planning / packing
@@ -212,6 +236,13 @@ class FrontEnd:
                          stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """Launch the fused kernel(s) on device-resident packed samples.  Returns ``out``:
         (B, T_max, n_out) if the plan is padded, (sum T_i, n_out) otherwise."""
+        if self.kind == "melspec_db":
+            # the reference's default branch always ends in AmplitudeToDB(top_db=80); it has no CMVN
+            if cmvn not in ("none", "topdb"):
+                raise ValueError("kind='melspec_db' supports no CMVN (ref: lid/audio_processor.py:72-105)")
+            cmvn = "topdb"
+        elif cmvn == "topdb":
+            raise ValueError("cmvn='topdb' belongs to kind='melspec_db'")
         if packed.dtype != self.in_dtype or not packed.is_cuda or not packed.is_contiguous():
             raise ValueError("packed must be a contiguous CUDA tensor of dtype %s" % self.in_dtype)
         if packed.numel() < plan.total_samples:
@@ -288,7 +319,7 @@ class FrontEnd:
         (PCIe is full duplex).  Returns ``host_out`` after synchronising."""
         if not plan.padded:
             raise ValueError("featurize_host needs a padded plan")
-        if cmvn not in ("none", "utt"):
+        if cmvn not in ("none", "utt", "topdb"):
             raise ValueError("featurize_host supports cmvn 'none' or 'utt' (global CMVN needs the all-reduce in between)")
         B = plan.batch
         chunks = max(1, min(chunks, B))

@@ -68,3 +68,29 @@ def lifter(n_ceps: int, cepstral_lifter: float) -> torch.Tensor:
         return torch.ones(n_ceps, dtype=torch.float32)
     i = torch.arange(n_ceps)
     return (1.0 + 0.5 * cepstral_lifter * torch.sin(math.pi * i / cepstral_lifter)).to(torch.float32)
+
+
+def hann_window(win_length: int) -> torch.Tensor:
+    """Periodic Hann window, the default of torchaudio's Spectrogram (ta: transforms/_transforms.py Spectrogram)."""
+    return torch.hann_window(win_length)
+
+
+def htk_mel_banks(n_mels: int, fft_len: int, sample_rate: int = 16000, f_min: float = 0.0,
+                  f_max: float = None) -> torch.Tensor:
+    """(n_mels, fft_len/2 + 1) triangular filters on the HTK scale 2595*log10(1 + f/700), norm=None: the transpose of
+    ``melscale_fbanks`` as ``MelScale`` builds it (ta: functional/functional.py:492-588).  The reference never forwards
+    its ``sr`` argument to MelSpectrogram (ref: lid/audio_processor.py:91-101), so the scale is always 16 kHz."""
+    n_freqs = fft_len // 2 + 1
+    if f_max is None:
+        f_max = float(sample_rate // 2)
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + (f_min / 700.0))
+    m_max = 2595.0 * math.log10(1.0 + (f_max / 700.0))
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    falling = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    rising = slopes[:, 2:] / f_diff[1:]
+    fb = torch.max(torch.zeros(1), torch.min(falling, rising))     # (n_freqs, n_mels)
+    return fb.t().contiguous()

@@ -49,6 +49,16 @@ def main():
         fb["out_" + name] = ap.wav2mel(x, use_kaildi=True).numpy()      # (1, 80, T)
     np.savez_compressed(os.path.join(HERE, "fbank_kaldi.npz"), **fb)
 
+    # ---- default branch (A9): MelSpectrogram + AmplitudeToDB(top_db=80), pad 0 and 16 (the yaml value) ------------
+    ms = {}
+    for name, x, pad in (("noise_1s", O.synth_noise(16000, 41), 0), ("speech_1s_pad16", O.synth_speechlike(16000, 42), 16),
+                         ("n700", O.synth_noise(700, 43), 0), ("n4000_pad16", O.synth_noise(4000, 44), 16),
+                         ("quiet_tail", torch.cat([O.synth_noise(8000, 45), 1e-4 * O.synth_noise(8000, 46)], 1), 0)):
+        ms["in_" + name] = x.numpy()
+        ms["pad_" + name] = np.array([pad])
+        ms["out_" + name] = ap.wav2mel(x, use_kaildi=False, pad=pad).numpy()            # (1, 80, T)
+    np.savez_compressed(os.path.join(HERE, "melspec_db.npz"), **ms)
+
     # ---- MFCC (A5): torchaudio kaldi.mfcc with the reference's framing args ------------------------
     mf = {}
     for name, x in (("noise_1s", O.synth_noise(16000, 11)), ("speech_1s", O.synth_speechlike(16000, 12)),

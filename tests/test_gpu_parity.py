@@ -63,7 +63,7 @@ def _check_fbank(got, want, what, all_bins=False):
 
 def test_extension_is_loaded(lid):
     lib = lid.load_library()
-    assert lib.lidfe_abi_version() == 1
+    assert lib.lidfe_abi_version() == 2
     with open("/proc/self/maps") as f:
         assert "liblidfe.so" in f.read()
 
@@ -317,3 +317,51 @@ def test_full_size_properties(fe, lid):
     # per-utterance CMVN at full size: zero mean / unit (unbiased) std per utterance and bin
     y = fe.featurize_packed(wav.reshape(-1), plan, cmvn="utt")
     assert y.mean(1).abs().max() < 1e-4 and (y.std(1) - 1).abs().max() < 1e-4
+
+
+def test_melspec_db_default_branch(lid, golden_dir):
+    """Row A9 -- the reference's DEFAULT wav2mel branch: MelSpectrogram + AmplitudeToDB(top_db=80), pad 0 / 16, against
+    outputs of the reference itself (tests/golden/melspec_db.npz) and the oracle on a ragged batch."""
+    from speech_lid_b200 import audio_processor as ap
+    z = np.load(os.path.join(golden_dir, "melspec_db.npz"))
+    fes = {}
+    for name in [k[3:] for k in z.files if k.startswith("in_")]:
+        x = torch.from_numpy(z["in_" + name])
+        pad = int(z["pad_" + name][0])
+        want = torch.from_numpy(z["out_" + name])                       # (1, 80, T)
+        fe = fes.setdefault(pad, lid.FrontEnd(kind="melspec_db", pad=pad))
+        feats, percents = fe.featurize([x])
+        got = feats[0].cpu()
+        assert got.shape == (want.shape[2], 80) and want.shape[2] == O.num_frames_centered(x.shape[-1], pad=pad)
+        assert _norm_rel(got, want[0].T) <= NORM_REL, "%s: %g" % (name, _norm_rel(got, want[0].T))
+        assert torch.allclose(got, want[0].T, rtol=1e-4, atol=2e-4), (name, float((got - want[0].T).abs().max()))
+        # the top_db clamp floor is the utterance max - 80
+        assert abs(float(got.min()) - max(float(want.min()), float(want.max()) - 80.0)) < 1e-3
+        # drop-in call, default branch
+        got2 = ap.wav2mel(x, pad=pad)
+        assert got2.shape == want.shape and _norm_rel(got2, want) <= NORM_REL
+    # ragged batch incl. utterances shorter than one tile and edge-only utterances (every tile reflects)
+    lens = [16000, 300, 2560, 40000, 257, 12345]
+    wavs = [O.synth_noise(n, 950 + i) for i, n in enumerate(lens)]
+    wavs[3] = torch.cat([wavs[3][:, :20000], 1e-5 * wavs[3][:, 20000:]], 1)       # makes the clamp bite
+    fe = fes[0]
+    feats, percents = fe.featurize(wavs)
+    feats = feats.cpu()
+    for i, w in enumerate(wavs):
+        want = O.melspec_db(w)[0].T
+        T = want.shape[0]
+        assert _norm_rel(feats[i, :T], want) <= NORM_REL, i
+        assert torch.all(feats[i, T:] == 0)
+    assert abs(float(feats[3, :O.num_frames_centered(40000)].min()) - (float(O.melspec_db(wavs[3]).max()) - 80.0)) < 1e-3
+    # SpecAugment on top (masks after the clamp, as the reference composes them)
+    frames = [O.num_frames_centered(n) for n in lens]
+    torch.manual_seed(3)
+    masks = lid.draw_masks(frames, 80, 0.05, 27, 2)
+    torch.manual_seed(3)
+    ref = [O.spectrogram_augment(O.melspec_db(w), 0.05, 27, 2)[0].T for w in wavs]
+    got, _ = fe.featurize(wavs, masks=masks)
+    for i, r in enumerate(ref):
+        g = got[i, :frames[i]].cpu()
+        assert torch.equal(g == 0, r == 0) and _norm_rel(g, r) <= NORM_REL
+    with pytest.raises(RuntimeError):
+        ap.wav2mel(torch.zeros(1, 200))                                            # reflect padding >= input length

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, "liblidfe.so does not export %s" % missing
     assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
-    assert lib.lidfe_abi_version() == 1
+    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 2
 
 
 def _cfg(**kw):
@@ -63,7 +63,8 @@ def test_create_validates_arguments_before_touching_the_device():
     assert lib.lidfe_create(None, C.byref(_cfg()), win.data_ptr(), banks.data_ptr(), None, None) == _lib.E_NULL
     assert lib.lidfe_create(C.byref(h), C.byref(_cfg()), None, banks.data_ptr(), None, None) == _lib.E_NULL
     for bad in (dict(sample_rate=8000), dict(frame_len=200), dict(frame_shift=80), dict(fft_len=256),
-                dict(n_mels=128), dict(n_mels=2), dict(n_ceps=81), dict(preemph=1.5), dict(in_dtype=7)):
+                dict(n_mels=128), dict(n_mels=2), dict(n_ceps=81), dict(preemph=1.5), dict(in_dtype=7),
+                dict(framing=3), dict(pad=16), dict(log_kind=2), dict(log_floor=0.0)):
         assert lib.lidfe_create(C.byref(h), C.byref(_cfg(**bad)), win.data_ptr(), banks.data_ptr(), None, None) \
             == _lib.E_CONFIG, bad
     assert lib.lidfe_create(C.byref(h), C.byref(_cfg(n_ceps=40)), win.data_ptr(), banks.data_ptr(), None, None) \
@@ -90,6 +91,25 @@ def test_tables_bit_identical_to_oracle():
     assert torch.equal(tables.mel_banks(80, 512, 16000.0), ref)
     assert torch.equal(tables.povey_window(400),
                        K._feature_window_function("povey", 400, 0.42, torch.device("cpu"), torch.float32))
+
+
+def test_melspec_tables_and_centered_frame_count():
+    assert torch.equal(tables.hann_window(400), torch.hann_window(400))
+    assert torch.equal(tables.htk_mel_banks(80, 512), O.htk_mel_fbanks(257, 0.0, 8000.0, 80, 16000).t())
+    F = pytest.importorskip("torchaudio.functional")
+    assert torch.equal(tables.htk_mel_banks(80, 512), F.melscale_fbanks(257, 0.0, 8000.0, 80, 16000).t())
+    lib = lid.load_library()
+    for pad in (0, 16):
+        cfg = _cfg(framing=_lib.FRAMING_CENTER, pad=pad, log_kind=_lib.LOG_DB10, preemph=0.0, remove_dc=0,
+                   log_floor=1e-10, top_db=80.0)
+        for n in (257, 300, 700, 4000, 16000, 128000):
+            assert lib.lidfe_num_frames(n, C.byref(cfg)) == O.num_frames_centered(n, pad=pad)
+        assert lib.lidfe_num_frames(256 - 2 * pad, C.byref(cfg)) == 0     # torch.stft refuses to reflect-pad this
+    # the HTK bank goes through the same sparsifier / tap placement
+    k0, cnt, st = (C.c_int * 80)(), (C.c_int * 80)(), (C.c_int * 80)()
+    bt = (C.c_int * 5)()
+    assert lib.lidfe_mel_plan(80, tables.htk_mel_banks(80, 512).data_ptr(), k0, cnt, st, bt) == 0
+    assert all(b > 0 for b in bt)
 
 
 def test_mel_plan_is_sparse_exact_and_bank_conflict_free():
@@ -185,3 +205,5 @@ def test_audio_processor_surface_matches_reference_signatures():
     assert ap.spectrogram_augment(spec, mask_times=0) is spec           # no masks -> returns its input, like the reference
     with pytest.raises(NotImplementedError):
         ap.spectrogram_augment(spec, mask_times=1, t_stretch=True)
+    with pytest.raises(NotImplementedError):
+        ap.wav2mel(torch.zeros(1, 16000), n_fft=400)
