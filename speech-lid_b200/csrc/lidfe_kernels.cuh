@@ -457,10 +457,6 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
           if (j < 12 || t < 8) {
             sA = add2(sA, x[j]);
             sB = add2(sB, x[j + 5]);
-            R[j] = make_float2(x[j].x, x[j + 5].x);     // even samples of A, B
-            I[j] = make_float2(x[j].y, x[j + 5].y);     // odd samples
-          } else {
-            R[j] = I[j] = make_float2(0.f, 0.f);
           }
         }
         f2 sum = make_float2(sA.x + sA.y, sB.x + sB.y);
@@ -469,18 +465,20 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
           sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
           sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
         }
-        f2 nmean = make_float2(0.f, 0.f);
-        if (P.remove_dc)
-          nmean = make_float2(-__fdiv_rn(sum.x, static_cast<float>(kFrameLen)),
-                              -__fdiv_rn(sum.y, static_cast<float>(kFrameLen)));
+        float mA = 0.f, mB = 0.f;
+        if (P.remove_dc) {
+          mA = __fdiv_rn(sum.x, static_cast<float>(kFrameLen));
+          mB = __fdiv_rn(sum.y, static_cast<float>(kFrameLen));
+        }
         const float c = P.preemph;
         f2 to_prev = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 13; ++j) {
           const int n = t + 16 * j;
           const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
-          const f2 te = add2(R[j], nmean);      // x[2n]   - mean
-          const f2 to = add2(I[j], nmean);      // x[2n+1] - mean
+          // (A,B) pairs are formed by the subtraction itself: scalar FADDs write straight into the pair halves
+          const f2 te = make_float2(__fsub_rn(x[j].x, mA), __fsub_rn(x[j + 5].x, mB));   // x[2n]   - mean
+          const f2 to = make_float2(__fsub_rn(x[j].y, mA), __fsub_rn(x[j + 5].y, mB));   // x[2n+1] - mean
           // x[2n-1] - mean lives in lane t-1 (same j); lane 0 takes lane 15's value of step j-1, and the very
           // first sample of the frame replicates itself (ta: compliance/kaldi.py:193-198)
           const f2 send = (t == 15) ? to_prev : to;

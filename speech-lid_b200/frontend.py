@@ -311,7 +311,7 @@ class FrontEnd:
         return out
 
     def featurize_host(self, host_in: torch.Tensor, plan: Plan, host_out: torch.Tensor,
-                       masks: Optional[torch.Tensor] = None, cmvn: str = "none", chunks: int = 4) -> torch.Tensor:
+                       masks: Optional[torch.Tensor] = None, cmvn: str = "none", chunks: int = 8) -> torch.Tensor:
         """Host-buffer entry (what a CPU-side caller of the reference's ``wav2mel`` sees): ``host_in`` is the packed
         waveform buffer laid out by ``plan`` in (ideally pinned) host memory, ``host_out`` receives the padded
         ``(B, T_max, n_out)`` batch.  The batch is cut into ``chunks`` groups of utterances, each on its own stream, so

@@ -365,3 +365,42 @@ def test_melspec_db_default_branch(lid, golden_dir):
         assert torch.equal(g == 0, r == 0) and _norm_rel(g, r) <= NORM_REL
     with pytest.raises(RuntimeError):
         ap.wav2mel(torch.zeros(1, 200))                                            # reflect padding >= input length
+
+
+def test_cfg3_mfcc_full_size_properties(lid):
+    """BASELINE config 3 at full size (512 x 4 s, 40 MFCC of 80 mel): shape, determinism, spot checks, linearity of
+    the DCT epilogue (MFCC == log-mel @ DCT * lifter computed from the fbank path's own output)."""
+    from speech_lid_b200 import tables
+    mf = lid.FrontEnd(n_mels=80, n_ceps=40)
+    fb = lid.FrontEnd(n_mels=80)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    wav = torch.randn(512, 64000, device="cuda", generator=g)
+    plan_m = mf.make_plan([64000] * 512, padded=True)
+    plan_f = fb.make_plan([64000] * 512, padded=True)
+    c = mf.featurize_packed(wav.reshape(-1), plan_m)
+    assert c.shape == (512, 398, 40) and torch.isfinite(c).all()
+    assert torch.equal(c, mf.featurize_packed(wav.reshape(-1), plan_m))
+    logmel = fb.featurize_packed(wav.reshape(-1), plan_f)
+    dct = tables.dct_matrix(40, 80).cuda().double()
+    lift = tables.lifter(40, 22.0).cuda().double()
+    want = (logmel.double() @ dct) * lift
+    assert float((c.double() - want).abs().max() / want.abs().max()) < 2e-6
+    for i in (0, 255, 511):
+        assert _norm_rel(c[i].cpu(), O.kaldi_mfcc(wav[i].cpu())) <= NORM_REL
+
+
+def test_host_buffer_entry_matches_device_entry(fe, lid):
+    """featurize_host (pinned host in / out, 8 pipelined utterance groups) == featurize_packed on the same data."""
+    lens = [20000 + 977 * i for i in range(37)]
+    wavs = [O.synth_noise(n, 1200 + i) for i, n in enumerate(lens)]
+    plan = fe.make_plan(lens, padded=True)
+    host_in = torch.zeros(plan.total_samples).pin_memory()
+    for w, o, n in zip(wavs, plan.offsets, lens):
+        host_in[o:o + n] = w[0]
+    torch.manual_seed(8)
+    masks = lid.draw_masks(plan.frames, 80, 0.05, 27, 2)
+    host_out = torch.empty(len(lens), plan.t_max, 80).pin_memory()
+    fe.featurize_host(host_in, plan, host_out, masks=masks, cmvn="utt")
+    dev = fe.featurize_packed(host_in.cuda(), plan, masks=masks, cmvn="utt").cpu()
+    assert torch.allclose(host_out, dev, rtol=0, atol=2e-6)      # per-utterance sums are added in a different order
+    assert torch.equal(host_out == 0, dev == 0)
