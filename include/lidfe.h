@@ -198,6 +198,11 @@ int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
 int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,
                       float dither, const float* noise_dev, float preemph, void* stream);
 
+/* Same stages fed with raw int16 PCM (what torchaudio.load decodes from a 16-bit wav before scaling by 1/32768,
+ * ref: lid/audio_processor.py:118-122): x = (float)pcm * in_scale first.  Lets the host ship 2 bytes per sample. */
+int lidfe_wave_stages_i16(lidfe_handle h, lidfe_plan p, const short* pcm_in_dev, float in_scale, float* wav_out_dev,
+                          int normalize, float dither, const float* noise_dev, float preemph, void* stream);
+
 /* -- measurement --------------------------------------------------------------------------------
  * Between lidfe_profile_begin and lidfe_profile_end every lidfe_featurize call brackets its fused fbank kernel with
  * a CUDA event pair on the launching stream (up to max_launches calls).  lidfe_profile_end synchronises on them and

@@ -619,14 +619,16 @@ int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
   return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, nullptr, static_cast<cudaStream_t>(stream), 0);
 }
 
-int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,
-                      float dither, const float* noise_dev, float preemph, void* stream) {
-  if (!h || !p || !wav_in_dev || !wav_out_dev) return LIDFE_E_NULL;
-  if (p->ctx != h || wav_in_dev == wav_out_dev) return LIDFE_E_ARG;
+static int launch_wave(lidfe_handle h, lidfe_plan p, const void* in, int in_i16, float in_scale, float* out, int normalize,
+                       float dither, const float* noise_dev, float preemph, void* stream) {
+  if (!h || !p || !in || !out) return LIDFE_E_NULL;
+  if (p->ctx != h || in == static_cast<const void*>(out)) return LIDFE_E_ARG;
   if (dither != 0.f && !noise_dev) return LIDFE_E_NULL;
   WaveParams W;
-  W.in = wav_in_dev;
-  W.out = wav_out_dev;
+  W.in = in;
+  W.in_i16 = in_i16;
+  W.in_scale = in_scale;
+  W.out = out;
   W.offsets = p->d_offsets;
   W.lengths = p->d_lengths;
   W.normalize = normalize;
@@ -637,6 +639,16 @@ int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, flo
   g_launches.fetch_add(1);
   CU_TRY(cudaGetLastError());
   return LIDFE_OK;
+}
+
+int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,
+                      float dither, const float* noise_dev, float preemph, void* stream) {
+  return launch_wave(h, p, wav_in_dev, 0, 1.f, wav_out_dev, normalize, dither, noise_dev, preemph, stream);
+}
+
+int lidfe_wave_stages_i16(lidfe_handle h, lidfe_plan p, const short* pcm_in_dev, float in_scale, float* wav_out_dev,
+                          int normalize, float dither, const float* noise_dev, float preemph, void* stream) {
+  return launch_wave(h, p, pcm_in_dev, 1, in_scale, wav_out_dev, normalize, dither, noise_dev, preemph, stream);
 }
 
 }  // extern "C"

@@ -854,7 +854,9 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
 // waveform-level stages (ref: lid/audio_processor.py:108-115,129-134).  One CTA per utterance.
 // ------------------------------------------------------------------------------------------------
 struct WaveParams {
-  const float* in;
+  const void* in;             // float32 or int16 samples
+  int in_i16;                 // 1 -> int16 PCM, converted as (float)s * in_scale before anything else
+  float in_scale;
   float* out;
   const long long* offsets;   // [B]
   const long long* lengths;   // [B]
@@ -869,7 +871,9 @@ __global__ void __launch_bounds__(512) wave_stages_kernel(const __grid_constant_
   __shared__ float s_mean, s_div;
   const int u = blockIdx.x;
   const long long off = P.offsets[u], n = P.lengths[u];
-  const float* x = P.in + off;
+  const float* xf = reinterpret_cast<const float*>(P.in) + off;
+  const short* xs = reinterpret_cast<const short*>(P.in) + off;
+  auto ld = [&](long long i) -> float { return P.in_i16 ? static_cast<float>(xs[i]) * P.in_scale : xf[i]; };
   const float* nz = P.noise ? P.noise + off : nullptr;
   float* y = P.out + off;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -877,7 +881,7 @@ __global__ void __launch_bounds__(512) wave_stages_kernel(const __grid_constant_
   if (P.normalize) {
     // two-pass mean / unbiased variance in fp64 (torch.std_mean accumulates in fp32 with a cascade)
     double s = 0.0;
-    for (long long i = tid; i < n; i += blockDim.x) s += x[i];
+    for (long long i = tid; i < n; i += blockDim.x) s += ld(i);
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) s_red[0][warp] = s;
     __syncthreads();
@@ -886,7 +890,7 @@ __global__ void __launch_bounds__(512) wave_stages_kernel(const __grid_constant_
     const double m = tot / static_cast<double>(n);
     double q = 0.0;
     for (long long i = tid; i < n; i += blockDim.x) {
-      const double dlt = x[i] - m;
+      const double dlt = ld(i) - m;
       q += dlt * dlt;
     }
     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -903,7 +907,7 @@ __global__ void __launch_bounds__(512) wave_stages_kernel(const __grid_constant_
     div = s_div;
   }
   auto stage1 = [&](long long i) -> float {
-    float v = x[i];
+    float v = ld(i);
     if (P.normalize) v = __fdiv_rn(__fsub_rn(v, mean), div);
     if (P.dither != 0.f) v = __fadd_rn(v, __fmul_rn(P.dither, nz[i]));
     return v;

@@ -297,17 +297,25 @@ class FrontEnd:
 
     def wave_stages(self, packed: torch.Tensor, plan: Plan, normalize: bool = False, dither: float = 0.0,
                     noise: Optional[torch.Tensor] = None, preemph: float = 0.0,
-                    stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+                    stream: Optional[torch.cuda.Stream] = None, out: Optional[torch.Tensor] = None,
+                    pcm_scale: float = 1.0 / 32768.0) -> torch.Tensor:
         """normalize_wav / dither / 0.97 pre-emphasis over every utterance of a packed float32 buffer
-        (ref: lid/audio_processor.py:108-115,129-134).  Returns a new packed buffer."""
-        if packed.dtype != torch.float32:
-            raise ValueError("wave_stages works on float32 samples")
-        out = torch.zeros_like(packed)
+        (ref: lid/audio_processor.py:108-115,129-134).  ``packed`` may be int16 PCM (scaled by ``pcm_scale`` first, as
+        torchaudio.load does).  Returns a new packed float32 buffer (or fills ``out``)."""
+        if packed.dtype not in (torch.float32, torch.int16):
+            raise ValueError("wave_stages works on float32 samples or int16 PCM")
+        if out is None:
+            out = torch.zeros(packed.numel(), dtype=torch.float32, device=packed.device)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.lidfe_wave_stages(self.handle, plan.handle, packed.data_ptr(), out.data_ptr(),
-                                                  int(normalize), float(dither), _ptr(noise), float(preemph),
-                                                  st.cuda_stream))
+            if packed.dtype == torch.int16:
+                _lib.check(self.lib.lidfe_wave_stages_i16(self.handle, plan.handle, packed.data_ptr(), float(pcm_scale),
+                                                          out.data_ptr(), int(normalize), float(dither), _ptr(noise),
+                                                          float(preemph), st.cuda_stream))
+            else:
+                _lib.check(self.lib.lidfe_wave_stages(self.handle, plan.handle, packed.data_ptr(), out.data_ptr(),
+                                                      int(normalize), float(dither), _ptr(noise), float(preemph),
+                                                      st.cuda_stream))
         return out
 
     def featurize_host(self, host_in: torch.Tensor, plan: Plan, host_out: torch.Tensor,
@@ -316,14 +324,19 @@ class FrontEnd:
         waveform buffer laid out by ``plan`` in (ideally pinned) host memory, ``host_out`` receives the padded
         ``(B, T_max, n_out)`` batch.  The batch is cut into ``chunks`` groups of utterances, each on its own stream, so
         the H2D copy of one group, the kernels of the previous one and the D2H copy of the one before overlap
-        (PCIe is full duplex).  Returns ``host_out`` after synchronising."""
+        (PCIe is full duplex).  Returns ``host_out`` after synchronising.
+
+        ``host_in`` may also hold raw int16 PCM (what a 16-bit wav file decodes to): each group is then shipped at
+        2 bytes per sample and ``read_audio``'s scaling + ``normalize_wav`` (ref: lid/audio_processor.py:108-122) run on
+        the device before framing."""
+        pcm = host_in.dtype == torch.int16 and self.in_dtype == torch.float32
         if not plan.padded:
             raise ValueError("featurize_host needs a padded plan")
         if cmvn not in ("none", "utt", "topdb"):
             raise ValueError("featurize_host supports cmvn 'none' or 'utt' (global CMVN needs the all-reduce in between)")
         B = plan.batch
         chunks = max(1, min(chunks, B))
-        key = (plan.handle, chunks)
+        key = (plan.handle, chunks, pcm)
         cache = self.__dict__.setdefault("_host_cache", {})
         st = cache.get(key)
         if st is None:
@@ -336,7 +349,8 @@ class FrontEnd:
                 sub = self.make_plan(plan.lengths[a:b], padded=True, offsets=[o - base for o in plan.offsets[a:b]],
                                      t_max=plan.t_max)
                 st.append(dict(a=a, b=b, base=base, end=end, plan=sub, stream=torch.cuda.Stream(self.device),
-                               dev_in=torch.empty(end - base, dtype=self.in_dtype, device=self.device),
+                               dev_in=torch.empty(end - base, dtype=host_in.dtype, device=self.device),
+                               dev_f32=torch.zeros(end - base, dtype=torch.float32, device=self.device) if pcm else None,
                                dev_out=torch.empty((b - a, plan.t_max, self.n_out), dtype=torch.float32, device=self.device),
                                dev_masks=None))
             cache.clear()          # one cached pipeline at a time
@@ -350,7 +364,10 @@ class FrontEnd:
                 m = None
                 if masks is not None and masks.shape[1] > 0:
                     m = masks[c["a"]:c["b"]].to(self.device, non_blocking=True)
-                self.featurize_packed(c["dev_in"], c["plan"], out=c["dev_out"], masks=m, cmvn=cmvn, stream=s)
+                src = c["dev_in"]
+                if pcm:
+                    src = self.wave_stages(c["dev_in"], c["plan"], normalize=True, stream=s, out=c["dev_f32"])
+                self.featurize_packed(src, c["plan"], out=c["dev_out"], masks=m, cmvn=cmvn, stream=s)
                 host_out[c["a"]:c["b"]].copy_(c["dev_out"], non_blocking=True)
         for c in st:
             c["stream"].synchronize()

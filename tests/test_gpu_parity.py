@@ -404,3 +404,19 @@ def test_host_buffer_entry_matches_device_entry(fe, lid):
     dev = fe.featurize_packed(host_in.cuda(), plan, masks=masks, cmvn="utt").cpu()
     assert torch.allclose(host_out, dev, rtol=0, atol=2e-6)      # per-utterance sums are added in a different order
     assert torch.equal(host_out == 0, dev == 0)
+
+
+def test_int16_pcm_host_pipeline(fe, lid):
+    """Row f2: host ships raw int16 PCM; scaling by 1/32768 + normalize_wav run on the device before framing."""
+    g = torch.Generator().manual_seed(11)
+    lens = [16000, 23456, 9000, 40000, 12000]
+    pcm = [(torch.randn(1, n, generator=g) * 2500 + 30).clamp(-32768, 32767).to(torch.int16) for n in lens]
+    plan = fe.make_plan(lens, padded=True)
+    host_in = torch.zeros(plan.total_samples, dtype=torch.int16).pin_memory()
+    for w, o, n in zip(pcm, plan.offsets, lens):
+        host_in[o:o + n] = w[0]
+    host_out = torch.empty(len(lens), plan.t_max, 80).pin_memory()
+    fe.featurize_host(host_in, plan, host_out, chunks=2)
+    for i, w in enumerate(pcm):
+        want = O.kaldi_fbank(O.normalize_wav(w.float() * (1.0 / 32768.0)))
+        _check_fbank(host_out[i, :want.shape[0]], want, "pcm utt %d" % i)
