@@ -56,7 +56,7 @@ def wav2mel(x, use_kaildi: bool = False, win_length: float = 0.025, hop_length: 
         fe = _frontend(n_mels, sr, win_length, hop_length, _device_of(x), kind="melspec_db", pad=pad)
         if fe.num_frames(x.shape[-1]) <= 0:      # torch.stft: reflect padding needs more samples than it mirrors
             raise RuntimeError("Argument #4: Padding size should be less than the corresponding input dimension")
-    plan = fe.make_plan([x.shape[-1]], padded=False)          # kaldi branch: AssertionError when T < 400
+    plan = fe.cached_plan([x.shape[-1]], padded=False)        # kaldi branch: AssertionError when T < 400
     packed = fe.pack([x], plan)
     feats = fe.featurize_packed(packed, plan)                  # (T', n_mels)
     out = feats.transpose(0, 1).unsqueeze(0)                   # ref: lid/audio_processor.py:63-65
@@ -82,7 +82,7 @@ def spectrogram_augment(spec, sr: int = 16000, n_mels: int = 80, hop_length: flo
     if F != fe.n_out or spec.dim() != 3 or spec.shape[0] != 1:
         raise ValueError("spectrogram_augment expects (1, n_mels<=80, T)")
     rows = spec.to(fe.device)[0].transpose(0, 1).contiguous()      # (T, F) rows as the kernels lay them out
-    plan = fe.make_plan([400 + 160 * (T - 1)], padded=False)       # a plan with exactly T frames
+    plan = fe.cached_plan([400 + 160 * (T - 1)], padded=False)     # a plan with exactly T frames
     fe.mask_apply(rows, plan, masks)
     out = rows.transpose(0, 1).unsqueeze(0)
     return out if spec.is_cuda else out.cpu()
@@ -100,7 +100,7 @@ def _wave(fe: FrontEnd, wav: torch.Tensor, normalize=False, dither=0.0, noise=No
     n = int(wav.shape[-1])
     if n < fe.frame_len:
         raise AssertionError("waveform shorter than one frame")
-    plan = fe.make_plan([n], padded=False)
+    plan = fe.cached_plan([n], padded=False)
     packed = fe.pack([wav.to(torch.float32)], plan)
     nz = None
     if noise is not None:

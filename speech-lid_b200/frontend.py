@@ -209,6 +209,20 @@ class FrontEnd:
         return Plan(handle=ph.value, lengths=lengths, offsets=offsets, frames=frames, out_rows=out_rows,
                     rows=rows, t_max=t_max, padded=padded, total_samples=total, _owner=self)
 
+    def cached_plan(self, lengths: Sequence[int], padded: bool = True) -> Plan:
+        """``make_plan`` behind a small LRU keyed by the batch's length signature: repeated shapes (fixed-length
+        batches, the single-utterance wrappers) skip the table upload.  A plan owns device workspace, so one plan is
+        meant to be in flight on one stream at a time."""
+        key = (tuple(int(n) for n in lengths), bool(padded))
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        plan = cache.pop(key, None)
+        if plan is None:
+            plan = self.make_plan(lengths, padded=padded)
+            while len(cache) >= 16:
+                cache.pop(next(iter(cache)))
+        cache[key] = plan
+        return plan
+
     def pack(self, wavs: Sequence[torch.Tensor], plan: Plan, pinned: Optional[torch.Tensor] = None,
              stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """Copy a list of (N_i,) / (1, N_i) waveforms (host or device) into one packed device buffer laid out
@@ -378,7 +392,7 @@ class FrontEnd:
         """The batched public entry: list of waveforms -> ``(feats, wav_percents)`` with the collate contract
         (ref: lid/raw_datasets.py:345-365).  ``feats`` stays on the device -- that is where the model consumes it."""
         lengths = [int(w.shape[-1]) for w in wavs]
-        plan = self.make_plan(lengths, padded=padded)
+        plan = self.cached_plan(lengths, padded=padded)
         packed = self.pack(wavs, plan)
         out = self.featurize_packed(packed, plan, masks=masks, cmvn=cmvn)
         return out, plan.wav_percents     # plan teardown (cudaFree) waits for the launched work
