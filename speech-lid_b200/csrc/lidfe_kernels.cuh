@@ -109,12 +109,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).  The samples are read once:
+// they go through L2 with an evict-first policy so that the feature rows written by this kernel stay resident for the
+// normalisation pass that follows.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 
 // order-preserving float -> uint map (atomicMax on floats of either sign); 0 is below every finite value
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t bytes = nsamp * (uint32_t)sizeof(TIn);
         mbar_expect_tx(&sm_bar[buf], bytes);
-        tma_bulk_g2s(dst, src, bytes, &sm_bar[buf]);
+        tma_bulk_g2s(dst, src, bytes, &sm_bar[buf], l2_evict_first_policy());
       }
     } else if (!P.center) {
       for (int i = tid; i < nsamp; i += kThreads) dst[i] = src[i];
@@ -718,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
 // grid = (utterances, row chunks of kApplyRows): every CTA finalises its utterance's mean / inv-std once and
 // streams 64 rows with 128-bit accesses, several loads in flight per thread.
 // ------------------------------------------------------------------------------------------------
-constexpr int kApplyRowsDefault = 128;   // rows of one utterance per CTA (tunable: LIDFE_APPLY_ROWS)
+constexpr int kApplyRowsDefault = 192;   // rows of one utterance per CTA (tunable: LIDFE_APPLY_ROWS)
 
 struct ApplyParams {
   float* feats;
@@ -748,26 +756,22 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   float* base = P.feats + (P.utt_out_row[utt] + r0) * P.ld;
   const bool vec = (P.n_out % 4 == 0) && (P.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.feats) & 15) == 0);
 
-  // flat float4 index i = tid + 256 q -> (row, col) advanced incrementally: no division in the loop.
-  // The first batch of loads is issued before the statistics are finalised, so its latency overlaps the fp64 prologue.
-  constexpr int kU = 5;                     // 64 rows x 20 float4 = 5 x 256 per batch
+  // Every thread owns ONE float4 column (4 output dims) and walks down the rows: its normalisation constants and its
+  // frequency-mask verdict live in registers, so the per-element work is a load, 8 flops, a row test and a store.
   const int nvec = vec ? (P.n_out >> 2) : 1;
-  const int dr = 256 / nvec, dc = 256 - dr * nvec;
-  int r = tid / nvec, c = tid - r * nvec;
+  const int rstep = 256 / nvec;                 // rows covered by one pass of the CTA
+  const int c = tid % nvec;
+  const int rlane = tid / nvec;
+  const bool live = vec && rlane < rstep;
+  constexpr int kU = 4;
   float4 x[kU];
-  int rr[kU], cc[kU];
-  auto load_batch = [&]() {
+  if (live) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      rr[u] = r;
-      cc[u] = c;
+      const int r = rlane + u * rstep;
       if (r < rows) x[u] = *reinterpret_cast<const float4*>(base + static_cast<long long>(r) * P.ld + 4 * c);
-      r += dr;
-      c += dc;
-      if (c >= nvec) { c -= nvec; r += 1; }
     }
-  };
-  if (vec) load_batch();
+  }
 
   const float db_floor = (P.normalize == 2) ? ord2f(P.utt_max[utt]) - P.top_db : 0.f;
   if (tid < P.n_out) {
@@ -795,16 +799,38 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   __syncthreads();
 
   if (vec) {
-    const int n_batches = (rows * nvec + 256 * kU - 1) / (256 * kU);
-    for (int bt = 0; bt < n_batches; ++bt) {
-      if (bt > 0) load_batch();
+    if (!live) return;
+    const int d = 4 * c;
+    const float2 n0 = s_norm[d], n1 = s_norm[d + 1], n2 = s_norm[d + 2], n3 = s_norm[d + 3];
+    bool z0 = false, z1 = false, z2 = false, z3 = false;
+    int t0[kMaxMasks], t1[kMaxMasks];
+#pragma unroll
+    for (int q = 0; q < kMaxMasks; ++q) {
+      t0[q] = t1[q] = 0;
+      if (q < P.n_masks) {
+        t0[q] = s_masks[4 * q];
+        t1[q] = s_masks[4 * q + 1];
+        const int f0 = s_masks[4 * q + 2], f1 = s_masks[4 * q + 3];
+        z0 |= (d + 0 >= f0 && d + 0 < f1);
+        z1 |= (d + 1 >= f0 && d + 1 < f1);
+        z2 |= (d + 2 >= f0 && d + 2 < f1);
+        z3 |= (d + 3 >= f0 && d + 3 < f1);
+      }
+    }
+    for (int rb = 0; rb < rows; rb += kU * rstep) {
+      if (rb > 0) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int r = rb + rlane + u * rstep;
+          if (r < rows) x[u] = *reinterpret_cast<const float4*>(base + static_cast<long long>(r) * P.ld + d);
+        }
+      }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        if (rr[u] >= rows) continue;
-        const int d = 4 * cc[u];
+        const int r = rb + rlane + u * rstep;
+        if (r >= rows) continue;
         float4 v = x[u];
         if (P.normalize == 1) {
-          const float2 n0 = s_norm[d], n1 = s_norm[d + 1], n2 = s_norm[d + 2], n3 = s_norm[d + 3];
           v.x = (v.x - n0.x) * n0.y;
           v.y = (v.y - n1.x) * n1.y;
           v.z = (v.z - n2.x) * n2.y;
@@ -815,21 +841,15 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
           v.z = fmaxf(v.z, db_floor);
           v.w = fmaxf(v.w, db_floor);
         }
-        const int tf = static_cast<int>(r0) + rr[u];
-        bool zr = false, z0 = false, z1 = false, z2 = false, z3 = false;
-        for (int q = 0; q < P.n_masks; ++q) {
-          const int m0 = s_masks[4 * q], m1 = s_masks[4 * q + 1], f0 = s_masks[4 * q + 2], f1 = s_masks[4 * q + 3];
-          zr |= (tf >= m0 && tf < m1);
-          z0 |= (d + 0 >= f0 && d + 0 < f1);
-          z1 |= (d + 1 >= f0 && d + 1 < f1);
-          z2 |= (d + 2 >= f0 && d + 2 < f1);
-          z3 |= (d + 3 >= f0 && d + 3 < f1);
-        }
+        const int tf = static_cast<int>(r0) + r;
+        bool zr = false;
+#pragma unroll
+        for (int q = 0; q < kMaxMasks; ++q) zr |= (tf >= t0[q] && tf < t1[q]);
         v.x = (zr || z0) ? 0.f : v.x;
         v.y = (zr || z1) ? 0.f : v.y;
         v.z = (zr || z2) ? 0.f : v.z;
         v.w = (zr || z3) ? 0.f : v.w;
-        *reinterpret_cast<float4*>(base + static_cast<long long>(rr[u]) * P.ld + d) = v;
+        *reinterpret_cast<float4*>(base + static_cast<long long>(r) * P.ld + d) = v;
       }
     }
   } else {
