@@ -24,13 +24,8 @@ struct lidfe_ctx {
   int band_taps[kBands];
   int std_mel;    // band_taps == kStdTaps -> fully unrolled mel loop
   // device tables
-  float* d_window;
-  float2* d_tw1;
-  float2* d_tw2;
-  float* d_melw;
-  int* d_k0;
-  float* d_dct;
-  float* d_lifter;
+  unsigned char* d_blob;   // window | tw1 | tw2 | mel_k0 | mel_w | dct | lifter, laid out like the kernel's shared memory
+  int blob_bytes;
   size_t smem_bytes;
   int grid_cap;   // resident CTAs of the fbank kernel on this device
   // optional per-launch timing of the fbank kernel (bench.py's roofline leg)
@@ -86,7 +81,7 @@ static fbank_fn pick_kernel(const lidfe_ctx* c) {
 static size_t smem_for(const lidfe_config& c, int total_taps) {
   const size_t base = (c.in_dtype == LIDFE_IN_I16) ? SmemLayout<short>::off_melw : SmemLayout<float>::off_melw;
   size_t extra = static_cast<size_t>(total_taps) * 16;
-  if (c.n_ceps > 0) extra += static_cast<size_t>(c.n_mels) * c.n_ceps + c.n_ceps;
+  if (c.n_ceps > 0) extra += ((static_cast<size_t>(c.n_mels) * c.n_ceps + 3) & ~static_cast<size_t>(3)) + ((c.n_ceps + 3) & ~3);
   return base + extra * sizeof(float);
 }
 
@@ -323,16 +318,27 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   if (cfg->n_ceps > 0 && lifter_host)
     for (int i = 0; i < cfg->n_ceps; ++i) lifter[i] = lifter_host[i];
 
+  // ---- one blob in the kernel's shared-memory table layout (every section a multiple of 16 bytes)
+  std::vector<unsigned char> blob;
+  auto append = [&blob](const void* src, size_t bytes) {
+    const size_t at = blob.size();
+    blob.resize(at + ((bytes + 15) & ~static_cast<size_t>(15)), 0);
+    memcpy(blob.data() + at, src, bytes);
+  };
+  append(window.data(), window.size() * sizeof(float));
+  append(tw1.data(), tw1.size() * sizeof(float2));
+  append(tw2.data(), tw2.size() * sizeof(float2));
+  append(k0.data(), static_cast<size_t>(kMaxMels) * sizeof(int));
+  if (total_taps > 0) append(melw.data(), static_cast<size_t>(total_taps) * 16 * sizeof(float));
+  if (cfg->n_ceps > 0) {
+    append(dct_host, static_cast<size_t>(cfg->n_mels) * cfg->n_ceps * sizeof(float));
+    append(lifter.data(), static_cast<size_t>(cfg->n_ceps) * sizeof(float));
+  }
+  c->blob_bytes = static_cast<int>(blob.size());
+
   cudaError_t e = cudaGetDevice(&c->device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
-  if (e == cudaSuccess) e = upload(&c->d_window, window.data(), window.size());
-  if (e == cudaSuccess) e = upload(&c->d_tw1, tw1.data(), tw1.size());
-  if (e == cudaSuccess) e = upload(&c->d_tw2, tw2.data(), tw2.size());
-  if (e == cudaSuccess) e = upload(&c->d_melw, melw.data(), melw.size());
-  if (e == cudaSuccess) e = upload(&c->d_k0, k0.data(), k0.size());
-  if (e == cudaSuccess && cfg->n_ceps > 0)
-    e = upload(&c->d_dct, dct_host, static_cast<size_t>(cfg->n_mels) * cfg->n_ceps);
-  if (e == cudaSuccess) e = upload(&c->d_lifter, lifter.data(), lifter.size());
+  if (e == cudaSuccess) e = upload(&c->d_blob, blob.data(), blob.size());
   if (e == cudaSuccess) {
     c->smem_bytes = smem_for(*cfg, total_taps);
     fbank_fn fn = pick_kernel(c);
@@ -357,13 +363,7 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
 
 int lidfe_destroy(lidfe_handle h) {
   if (!h) return LIDFE_E_NULL;
-  cudaFree(h->d_window);
-  cudaFree(h->d_tw1);
-  cudaFree(h->d_tw2);
-  cudaFree(h->d_melw);
-  cudaFree(h->d_k0);
-  cudaFree(h->d_dct);
-  cudaFree(h->d_lifter);
+  cudaFree(h->d_blob);
   delete h;
   return LIDFE_OK;
 }
@@ -516,13 +516,8 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   P.out_ld = out_ld;
   P.tiles = p->d_tiles;
   P.n_tiles = static_cast<int>(p->n_tiles);
-  P.window = h->d_window;
-  P.tw1 = h->d_tw1;
-  P.tw2 = h->d_tw2;
-  P.mel_w = h->d_melw;
-  P.mel_k0 = h->d_k0;
-  P.dct = h->d_dct;
-  P.lifter = h->d_lifter;
+  P.const_blob = h->d_blob;
+  P.const_bytes = h->blob_bytes;
   for (int b = 0; b < kBands; ++b) P.band_taps[b] = h->band_taps[b];
   P.n_mels = h->cfg.n_mels;
   P.n_ceps = h->cfg.n_ceps;

@@ -58,14 +58,12 @@ struct FbankParams {
   long long out_ld;
   const Tile* tiles;
   int n_tiles;
-  // constant tables (device)
-  const float* window;      // [416] zero padded
-  const float2* tw1;        // [16][16]  W256^(K1*t)
-  const float2* tw2;        // [8][16]   W512^(t+16i)
-  const float* mel_w;       // per band, [taps_b][16] (x 0.25: the power bins are left scaled by 4)
-  const int* mel_k0;        // [kBands*16]
-  const float* dct;         // [n_mels][n_ceps]
-  const float* lifter;      // [n_ceps] (ones when no liftering)
+  // constant tables: ONE device blob laid out exactly like the kernel's shared-memory table area, so a single TMA
+  // bulk copy stages it:  window[416] | tw1[16][16] float2 = W256^(K1*t) | tw2[8][16] float2 = W512^(t+16i) |
+  // mel_k0[80] int | mel_w per band [taps_b][16] (x 0.25: the power bins are left scaled by 4) |
+  // dct[n_mels][n_ceps] | lifter[n_ceps]   (each section padded to 16 bytes)
+  const void* const_blob;
+  int const_bytes;
   int band_taps[kBands];    // taps per band
   int n_mels, n_ceps, n_out;
   float preemph, log_floor, log_of_floor, in_scale;   // log_of_floor = the reference's log of the floor, rounded on the host
@@ -116,6 +114,12 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_plain(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
@@ -248,16 +252,17 @@ struct SmemLayout {
   static constexpr int off_in0 = 0;
   static constexpr int off_in1 = kInBytes;
   static constexpr int off_scratch = 2 * kInBytes;                                 // [2*kWarps][kScratchFloats] floats
-  static constexpr int off_window = off_scratch + 2 * kWarps * kScratchFloats * 4; // [416]
+  static constexpr int off_norm = off_scratch + 2 * kWarps * kScratchFloats * 4;   // [80] float2 (mean, inv_std)
+  static constexpr int off_acc = off_norm + kMaxMels * 8;                          // fp64: [kWarps][2][80] per-warp sums + frame count
+  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;      // [kMaxMasks][4] int
+  static constexpr int off_bar = off_masks + kMaxMasks * 16;                       // 3 mbarriers (2 input buffers, tables)
+  static constexpr int off_tiles = off_bar + 32;                                   // [kTileCache] Tile descriptors
+  // constant tables, one contiguous block = the device blob (see FbankParams::const_blob)
+  static constexpr int off_window = off_tiles + kTileCache * 32;                   // [416]
   static constexpr int off_tw1 = off_window + 416 * 4;                             // [16][16] float2
   static constexpr int off_tw2 = off_tw1 + 256 * 8;                                // [8][16] float2
   static constexpr int off_k0 = off_tw2 + 128 * 8;                                 // [80] int
-  static constexpr int off_norm = off_k0 + kMaxMels * 4;                           // [80] float2 (mean, inv_std)
-  static constexpr int off_acc = off_norm + kMaxMels * 8;                          // fp64: [kWarps][2][80] per-warp sums + frame count
-  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;               // [kMaxMasks][4] int
-  static constexpr int off_bar = off_masks + kMaxMasks * 16;                       // 2 mbarriers
-  static constexpr int off_tiles = off_bar + 16;                                   // [kTileCache] Tile descriptors
-  static constexpr int off_melw = off_tiles + kTileCache * 32;                                    // sum(band_taps)*16 floats, then dct, lifter
+  static constexpr int off_melw = off_k0 + kMaxMels * 4;                           // sum(band_taps)*16 floats, then dct, lifter
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -298,33 +303,28 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
     tap_off[b + 1] = tap_off[b] + taps[b];
   }
   float* const sm_dct = sm_melw + tap_off[kBands] * 16;
-  float* const sm_lifter = sm_dct + (kMfcc ? P.n_mels * P.n_ceps : 0);
+  float* const sm_lifter = sm_dct + (kMfcc ? ((P.n_mels * P.n_ceps + 3) & ~3) : 0);   // sections padded to 16 B
 
   // this CTA's contiguous tile range (neighbouring tiles share their halo in L2 and their utterance's statistics)
   const long long nt = P.n_tiles;
   const int tile_begin = static_cast<int>((nt * blockIdx.x) / gridDim.x);
   const int tile_end = static_cast<int>((nt * (blockIdx.x + 1)) / gridDim.x);
 
-  // ---- one-time table staging ----------------------------------------------------------------
+  // ---- one-time staging: all constant tables arrive with ONE TMA bulk copy while the CTA sets up the rest ------
+  if (tid == 0) {
+    mbar_init(&sm_bar[0], 1);
+    mbar_init(&sm_bar[1], 1);
+    mbar_init(&sm_bar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&sm_bar[2], static_cast<uint32_t>(P.const_bytes));
+    tma_bulk_g2s_plain(smem + L::off_window, P.const_blob, static_cast<uint32_t>(P.const_bytes), &sm_bar[2]);
+  }
   {
     {   // descriptors of the first kTileCache tiles of the range (4 x 8-byte words each)
       const int n = min(tile_end - tile_begin, kTileCache);
       const long long* src = reinterpret_cast<const long long*>(P.tiles + tile_begin);
       long long* dst = reinterpret_cast<long long*>(sm_tiles);
       for (int i = tid; i < n * 4; i += kThreads) dst[i] = src[i];
-    }
-    float* w = const_cast<float*>(sm_window);
-    for (int i = tid; i < 416; i += kThreads) w[i] = P.window[i];
-    float2* a = const_cast<float2*>(sm_tw1);
-    for (int i = tid; i < 256; i += kThreads) a[i] = P.tw1[i];
-    float2* c = const_cast<float2*>(sm_tw2);
-    for (int i = tid; i < 128; i += kThreads) c[i] = P.tw2[i];
-    int* k = const_cast<int*>(sm_k0);
-    for (int i = tid; i < kMaxMels; i += kThreads) k[i] = P.mel_k0[i];
-    for (int i = tid; i < tap_off[kBands] * 16; i += kThreads) sm_melw[i] = P.mel_w[i];
-    if (kMfcc) {
-      for (int i = tid; i < P.n_mels * P.n_ceps; i += kThreads) sm_dct[i] = P.dct[i];
-      for (int i = tid; i < P.n_ceps; i += kThreads) sm_lifter[i] = P.lifter[i];
     }
     for (int i = tid; i < kWarps * 2 * kMaxMels + 2; i += kThreads) sm_acc[i] = 0.0;
     if (tid < kWarps) reinterpret_cast<float*>(sm_acc + kWarps * 2 * kMaxMels + 2)[tid] = -INFINITY;
@@ -336,13 +336,8 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
       var = var > 0.0 ? var : 0.0;
       sm_norm[tid] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / (sqrt(var) + 1e-9)));
     }
-    if (tid == 0) {
-      mbar_init(&sm_bar[0], 1);
-      mbar_init(&sm_bar[1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
   }
-  __syncthreads();
+  __syncthreads();   // mbarriers initialised, descriptors cached
 
   auto stage_tile = [&](int tile_idx, int buf) {
     if (tile_idx >= tile_end) return;
@@ -384,14 +379,14 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
   const int partner = (lane & 16) | ((16 - t) & 15);
   const int up_lane = (lane & 16) | ((t - 1) & 15);
 
+  stage_tile(tile_begin, 0);           // first tile's samples are in flight while the tables land
+  mbar_wait(&sm_bar[2], 0u);
   int k0[kBands];
 #pragma unroll
   for (int b = 0; b < kBands; ++b) k0[b] = sm_k0[t + 16 * b];
 
   int cur_utt = -1;
   unsigned dim_masked = 0u;   // bit b: output dim t+16b is inside a frequency mask of the current utterance
-
-  stage_tile(tile_begin, 0);
 
   int it = 0;
   for (int tile_idx = tile_begin; tile_idx < tile_end; ++tile_idx, ++it) {
