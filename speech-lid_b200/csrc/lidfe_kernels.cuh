@@ -38,7 +38,7 @@ constexpr int kScratchFloats = 2 * kPlaneFloats;  // per half-warp: re plane + i
 constexpr int kLogmelOff = 640;                   // MFCC log-mel staging (80 pairs) behind the 257 power pairs
 constexpr int kValsOff = 960;                     // final feature pairs parked for the statistics pass (80 pairs)
 constexpr int kMaxMasks = 8;
-constexpr int kTileCache = 48;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
+constexpr int kTileCache = 32;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
 // taps per band of the 80-mel / 16 kHz / 512 Kaldi bank
 // (after the host shifts each filter's first tap so that the 16 lanes of a band read 16 distinct bank pairs)
 __host__ __device__ constexpr int std_taps(int b) { return b == 0 ? 3 : b == 1 ? 5 : b == 2 ? 6 : b == 3 ? 10 : 17; }
@@ -94,6 +94,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -254,9 +257,9 @@ struct SmemLayout {
   static constexpr int off_scratch = 2 * kInBytes;                                 // [2*kWarps][kScratchFloats] floats
   static constexpr int off_norm = off_scratch + 2 * kWarps * kScratchFloats * 4;   // [80] float2 (mean, inv_std)
   static constexpr int off_acc = off_norm + kMaxMels * 8;                          // fp64: [kWarps][2][80] per-warp sums + frame count
-  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;      // [kMaxMasks][4] int
-  static constexpr int off_bar = off_masks + kMaxMasks * 16;                       // 3 mbarriers (2 input buffers, tables)
-  static constexpr int off_tiles = off_bar + 32;                                   // [kTileCache] Tile descriptors
+  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;      // [2 staged + kWarps private][kMaxMasks][4] int
+  static constexpr int off_bar = off_masks + (2 + kWarps) * kMaxMasks * 16;        // mbarriers: full[2], tables, empty[2]
+  static constexpr int off_tiles = off_bar + 48;                                   // [kTileCache] Tile descriptors
   // constant tables, one contiguous block = the device blob (see FbankParams::const_blob)
   static constexpr int off_window = off_tiles + kTileCache * 32;                   // [416]
   static constexpr int off_tw1 = off_window + 416 * 4;                             // [16][16] float2
@@ -312,9 +315,11 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
 
   // ---- one-time staging: all constant tables arrive with ONE TMA bulk copy while the CTA sets up the rest ------
   if (tid == 0) {
-    mbar_init(&sm_bar[0], 1);
-    mbar_init(&sm_bar[1], 1);
-    mbar_init(&sm_bar[2], 1);
+    mbar_init(&sm_bar[0], 1);            // full[0]: samples of the tile in buffer 0 have landed
+    mbar_init(&sm_bar[1], 1);            // full[1]
+    mbar_init(&sm_bar[2], 1);            // constant tables have landed
+    mbar_init(&sm_bar[3], kWarps);       // empty[0]: every warp has consumed the samples in buffer 0
+    mbar_init(&sm_bar[4], kWarps);       // empty[1]
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&sm_bar[2], static_cast<uint32_t>(P.const_bytes));
     tma_bulk_g2s_plain(smem + L::off_window, P.const_blob, static_cast<uint32_t>(P.const_bytes), &sm_bar[2]);
@@ -339,35 +344,58 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
   }
   __syncthreads();   // mbarriers initialised, descriptors cached
 
+  // Producer side (warp 0): stage a tile's samples -- and its utterance's mask table -- into buffer `buf`.  There is no
+  // CTA-wide barrier per tile: a buffer is re-filled once every warp has arrived on its "empty" mbarrier (after its
+  // stage-0 reads), and consumers wait on the "full" mbarrier, so warps may drift up to two tiles apart.
+  int staged0 = 0, staged1 = 0, staged_utt = -1;
+  const bool stage_masks = (mode == 0 || mode == 2) && P.n_masks > 0;
   auto stage_tile = [&](int tile_idx, int buf) {
-    if (tile_idx >= tile_end) return;
+    if (warp != 0 || tile_idx >= tile_end) return;
     const Tile tl = sm_tiles[(tile_idx - tile_begin) % kTileCache];
     if (tl.nframes == 0) return;
+    const int k = buf ? staged1 : staged0;            // uses of this buffer so far
+    if (k > 0) {
+      if (lane == 0) mbar_wait(&sm_bar[3 + buf], static_cast<uint32_t>((k - 1) & 1));
+      __syncwarp();
+    }
+    if (buf) ++staged1; else ++staged0;
+    if (stage_masks) {
+      int* ms = sm_masks + buf * kMaxMasks * 4;
+      if (lane < P.n_masks * 4)
+        ms[lane] = (tl.utt == staged_utt) ? sm_masks[(buf ^ 1) * kMaxMasks * 4 + lane]
+                                          : P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + lane];
+      staged_utt = tl.utt;
+      __syncwarp();
+    }
     const int nsamp = kFrameShift * tl.nframes + (kFrameLen - kFrameShift);
     const TIn* src = reinterpret_cast<const TIn*>(P.wav) + tl.wav_off;
     TIn* dst = buf ? sm_in1 : sm_in0;
     if (tl.aux) {
-      if (tid == 0) {
+      if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t bytes = nsamp * (uint32_t)sizeof(TIn);
         mbar_expect_tx(&sm_bar[buf], bytes);
         tma_bulk_g2s(dst, src, bytes, &sm_bar[buf], l2_evict_first_policy());
       }
-    } else if (!P.center) {
-      for (int i = tid; i < nsamp; i += kThreads) dst[i] = src[i];
     } else {
-      // edge tile of the centred framing: index u of the constant-padded signal p (length L = N + 2 pad), mirrored
-      // once at either end like torch.stft(center=True, pad_mode="reflect"); zeros inside the constant padding
-      const long long N = P.utt_lengths[tl.utt];
-      const TIn* x = reinterpret_cast<const TIn*>(P.wav) + P.utt_offsets[tl.utt];
-      const long long L = N + 2 * P.pad;
-      const long long u0 = static_cast<long long>(kFrameShift) * tl.t0 - (kFrameLen / 2);
-      for (int i = tid; i < nsamp; i += kThreads) {
-        long long u = u0 + i;
-        u = u < 0 ? -u : (u >= L ? 2 * (L - 1) - u : u);
-        const long long r = u - P.pad;
-        dst[i] = (r >= 0 && r < N) ? x[r] : static_cast<TIn>(0);
+      if (!P.center) {
+        for (int i = lane; i < nsamp; i += 32) dst[i] = src[i];
+      } else {
+        // edge tile of the centred framing: index u of the constant-padded signal p (length L = N + 2 pad), mirrored
+        // once at either end like torch.stft(center=True, pad_mode="reflect"); zeros inside the constant padding
+        const long long N = P.utt_lengths[tl.utt];
+        const TIn* x = reinterpret_cast<const TIn*>(P.wav) + P.utt_offsets[tl.utt];
+        const long long L = N + 2 * P.pad;
+        const long long u0 = static_cast<long long>(kFrameShift) * tl.t0 - (kFrameLen / 2);
+        for (int i = lane; i < nsamp; i += 32) {
+          long long u = u0 + i;
+          u = u < 0 ? -u : (u >= L ? 2 * (L - 1) - u : u);
+          const long long r = u - P.pad;
+          dst[i] = (r >= 0 && r < N) ? x[r] : static_cast<TIn>(0);
+        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm_bar[buf]);       // element-wise staging: plain arrival completes the phase
     }
   };
 
@@ -413,26 +441,26 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         const int d = static_cast<int>(i - r * n_out);
         P.out[(tl.out_row + r) * P.out_ld + d] = 0.f;
       }
-      __syncthreads();
       continue;
     }
 
-    const bool new_utt = tl.utt != cur_utt;      // CTA-uniform
-    if (new_utt && tid < P.n_masks * 4) sm_masks[tid] = P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + tid];
-    if (tl.aux) {
-      if (buf) { mbar_wait(&sm_bar[1], phase1); phase1 ^= 1u; }
-      else     { mbar_wait(&sm_bar[0], phase0); phase0 ^= 1u; }
-    }
-    if ((new_utt && P.n_masks > 0) || !tl.aux) __syncthreads();   // new mask table / element-load staging visible
+    // consumer side: wait for this tile's samples (and mask table), take a private copy of the masks
+    if (buf) { mbar_wait(&sm_bar[1], phase1); phase1 ^= 1u; }
+    else     { mbar_wait(&sm_bar[0], phase0); phase0 ^= 1u; }
     const TIn* in = buf ? sm_in1 : sm_in0;
-
-    if (new_utt) {
-      cur_utt = tl.utt;
-      dim_masked = 0u;
-      for (int q = 0; q < P.n_masks; ++q) {
-        const int f0 = sm_masks[4 * q + 2], f1 = sm_masks[4 * q + 3];
+    int* const wm = sm_masks + (2 + warp) * kMaxMasks * 4;
+    if (stage_masks) {
+      __syncwarp();                                  // previous tile's readers of this warp's copy are done
+      if (lane < P.n_masks * 4) wm[lane] = sm_masks[buf * kMaxMasks * 4 + lane];
+      __syncwarp();
+      if (tl.utt != cur_utt) {
+        cur_utt = tl.utt;
+        dim_masked = 0u;
+        for (int q = 0; q < P.n_masks; ++q) {
+          const int f0 = wm[4 * q + 2], f1 = wm[4 * q + 3];
 #pragma unroll
-        for (int b = 0; b < kBands; ++b) dim_masked |= (t + 16 * b >= f0 && t + 16 * b < f1) ? (1u << b) : 0u;
+          for (int b = 0; b < kBands; ++b) dim_masked |= (t + 16 * b >= f0 && t + 16 * b < f1) ? (1u << b) : 0u;
+        }
       }
     }
 
@@ -503,7 +531,8 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
 
       // ---- stage 1: 16-point DFT over j, twiddle W256^(K1*t), transpose through shared ------------
       fft16<true>(R, I);
-      __syncwarp();   // previous tile's readers of this scratch are done
+      __syncwarp();   // previous tile's readers of this scratch are done; every lane has consumed its samples
+      if (lane == 0) mbar_arrive(&sm_bar[3 + buf]);   // release the input buffer (and the staged mask table)
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int K1 = rev4(p);
@@ -605,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         if (mode == 0 || mode == 2) {
           dm = dim_masked;
           for (int q = 0; q < P.n_masks; ++q) {
-            const int m0 = sm_masks[4 * q], m1 = sm_masks[4 * q + 1];
+            const int m0 = wm[4 * q], m1 = wm[4 * q + 1];
             rowA |= (tfA >= m0 && tfA < m1);
             rowB |= (tfA + 1 >= m0 && tfA + 1 < m1);
           }
@@ -666,7 +695,8 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
       for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       if (lane == 0) sm_wmax[warp] = fmaxf(sm_wmax[warp], m);
     }
-    __syncthreads();   // everyone is done with this input buffer and sm_masks
+    // No per-tile CTA barrier.  Cross-warp state is only touched when sums / maxima are handed over (utterance change,
+    // zero-fill ahead, end of the CTA's range): a CTA-uniform, rare event bracketed by two barriers.
     if (mode == 4) {
       bool flush = (tile_idx + 1 == tile_end);
       if (!flush) {
@@ -674,6 +704,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         flush = (nx.nframes == 0) || (nx.utt != tl.utt);
       }
       if (flush) {
+        __syncthreads();   // every warp's running maximum covers this tile
         if (tid == 0) {
           float m = sm_wmax[0];
 #pragma unroll
@@ -692,7 +723,8 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         flush = (nx.nframes == 0) || (mode == 1 && nx.utt != tl.utt);
       }
       if (mode == 3 && tid == kThreads - 1) sm_acc[kWarps * 2 * kMaxMels] += static_cast<double>(tl.nframes);
-      if (flush) {     // CTA-uniform, rare: combine the warps' accumulators (the barrier above ordered their updates)
+      if (flush) {     // combine the warps' accumulators
+        __syncthreads();   // every warp has added this tile
         for (int e = tid; e < 2 * kMaxMels; e += kThreads) {
           const int which = e / kMaxMels, d = e - which * kMaxMels;
           double a = 0.0;
