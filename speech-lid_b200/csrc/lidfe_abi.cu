@@ -420,6 +420,7 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
     }
   }
   // int16 bulk copies also need the tile's own offset 16B aligned: 160 samples * 2 B = 320 B -> ok.
+  if (tiles.size() > 0x7fffffffull) return LIDFE_E_ARG;
   lidfe_plan_s* p = new (std::nothrow) lidfe_plan_s();
   if (!p) return LIDFE_E_NOMEM;
   p->ctx = h;
