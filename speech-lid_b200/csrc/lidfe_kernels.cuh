@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
   double* const sm_acc = reinterpret_cast<double*>(smem + L::off_acc);
   int* const sm_masks = reinterpret_cast<int*>(smem + L::off_masks);
   uint64_t* const sm_bar = reinterpret_cast<uint64_t*>(smem + L::off_bar);
+  int* const sm_claim = reinterpret_cast<int*>(smem + L::off_bar + 40);   // highest tile sequence number whose staging is taken
   Tile* const sm_tiles = reinterpret_cast<Tile*>(smem + L::off_tiles);
   float* const sm_melw = reinterpret_cast<float*>(smem + L::off_melw);
 
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
     mbar_init(&sm_bar[2], 1);            // constant tables have landed
     mbar_init(&sm_bar[3], kWarps);       // empty[0]: every warp has consumed the samples in buffer 0
     mbar_init(&sm_bar[4], kWarps);       // empty[1]
+    *sm_claim = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&sm_bar[2], static_cast<uint32_t>(P.const_bytes));
     tma_bulk_g2s_plain(smem + L::off_window, P.const_blob, static_cast<uint32_t>(P.const_bytes), &sm_bar[2]);
@@ -347,24 +349,32 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
   // Producer side (warp 0): stage a tile's samples -- and its utterance's mask table -- into buffer `buf`.  There is no
   // CTA-wide barrier per tile: a buffer is re-filled once every warp has arrived on its "empty" mbarrier (after its
   // stage-0 reads), and consumers wait on the "full" mbarrier, so warps may drift up to two tiles apart.
+  // The producer of a tile is whichever warp reaches the staging point first (smem atomicMax election), so a slow
+  // warp never delays the prefetch.  The bookkeeping (uses per buffer, utterance of the staged masks) is a
+  // function of the tile sequence alone and is tracked identically by every warp.
   int staged0 = 0, staged1 = 0, staged_utt = -1;
   const bool stage_masks = (mode == 0 || mode == 2) && P.n_masks > 0;
-  auto stage_tile = [&](int tile_idx, int buf) {
-    if (warp != 0 || tile_idx >= tile_end) return;
+  auto stage_tile = [&](int tile_idx, int buf, int seq) {
+    if (tile_idx >= tile_end) return;
     const Tile tl = sm_tiles[(tile_idx - tile_begin) % kTileCache];
     if (tl.nframes == 0) return;
     const int k = buf ? staged1 : staged0;            // uses of this buffer so far
+    if (buf) ++staged1; else ++staged0;
+    const int prev_utt = staged_utt;
+    staged_utt = tl.utt;
+    int mine = 0;
+    if (lane == 0) mine = atomicMax(sm_claim, seq) < seq;
+    mine = __shfl_sync(0xffffffffu, mine, 0);
+    if (!mine) return;
     if (k > 0) {
       if (lane == 0) mbar_wait(&sm_bar[3 + buf], static_cast<uint32_t>((k - 1) & 1));
       __syncwarp();
     }
-    if (buf) ++staged1; else ++staged0;
     if (stage_masks) {
       int* ms = sm_masks + buf * kMaxMasks * 4;
       if (lane < P.n_masks * 4)
-        ms[lane] = (tl.utt == staged_utt) ? sm_masks[(buf ^ 1) * kMaxMasks * 4 + lane]
-                                          : P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + lane];
-      staged_utt = tl.utt;
+        ms[lane] = (tl.utt == prev_utt) ? sm_masks[(buf ^ 1) * kMaxMasks * 4 + lane]
+                                        : P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + lane];
       __syncwarp();
     }
     const int nsamp = kFrameShift * tl.nframes + (kFrameLen - kFrameShift);
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
   const int partner = (lane & 16) | ((16 - t) & 15);
   const int up_lane = (lane & 16) | ((t - 1) & 15);
 
-  stage_tile(tile_begin, 0);           // first tile's samples are in flight while the tables land
+  stage_tile(tile_begin, 0, 1);        // first tile's samples are in flight while the tables land (sequence number 1)
   mbar_wait(&sm_bar[2], 0u);
   int k0[kBands];
 #pragma unroll
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
       for (int i = tid; i < n * 4; i += kThreads) dst[i] = src[i];
       __syncthreads();
     }
-    stage_tile(tile_idx + 1, buf ^ 1);
+    stage_tile(tile_idx + 1, buf ^ 1, it + 2);
 
     if (tl.nframes == 0) {
       // zero-fill tile: pad_sequence's zeros (ref: lid/raw_datasets.py:347-350)
