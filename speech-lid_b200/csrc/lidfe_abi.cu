@@ -45,7 +45,8 @@ struct lidfe_plan_s {
   long long max_frames;
   long long* d_offsets;   // [B]
   long long* d_lengths;   // [B]
-  double* d_utt_stats;    // [B][2][n_out]
+  double* d_utt_stats;    // [2 launches][B][2][n_out]: ping-pong, the apply kernel of launch i clears the buffer of launch i+1
+  int stats_flip;         // which half the next per-utterance-CMVN launch accumulates into (host-side toggle)
   unsigned* d_utt_max;    // [B] (LIDFE_POST_TOPDB)
 };
 
@@ -436,6 +437,7 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   p->d_offsets = nullptr;
   p->d_lengths = nullptr;
   p->d_utt_stats = nullptr;
+  p->stats_flip = 0;
   p->d_utt_max = nullptr;
   cudaError_t e = upload(&p->d_tiles, tiles.data(), tiles.size());
   if (e == cudaSuccess) e = upload(&p->d_frames, frames.data(), frames.size());
@@ -443,7 +445,8 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   if (e == cudaSuccess) e = upload(&p->d_offsets, wav_offsets_host, static_cast<size_t>(B));
   if (e == cudaSuccess) e = upload(&p->d_lengths, wav_lengths_host, static_cast<size_t>(B));
   if (e == cudaSuccess)
-    e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_stats), static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
+    e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_stats), 2 * static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(p->d_utt_stats, 0, 2 * static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_max), static_cast<size_t>(B) * sizeof(unsigned));
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -471,7 +474,8 @@ long long lidfe_plan_num_tiles(lidfe_plan p) { return p ? p->n_tiles : 0; }
 long long lidfe_plan_frames(lidfe_plan p, int i) { return (p && i >= 0 && i < p->B) ? p->frames[i] : 0; }
 
 static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, const int* masks, int n_masks,
-                        const double* utt_stats, const double* glob_stats, cudaStream_t st, int normalize) {
+                        const double* utt_stats, const double* glob_stats, cudaStream_t st, int normalize,
+                        double* clear_stats) {
   ApplyParams A;
   A.feats = feats;
   A.ld = ld;
@@ -483,6 +487,7 @@ static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, 
   A.utt_out_row = p->d_out_rows;
   A.glob_stats = glob_stats;
   A.normalize = normalize;
+  A.clear_stats = clear_stats;
   A.utt_max = p->d_utt_max;
   A.top_db = h->cfg.top_db;
   int rows_per_cta = kApplyRowsDefault;
@@ -546,8 +551,15 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   P.stats_out = stats_out_dev;
   P.utt_stats = p->d_utt_stats;
 
-  if (cmvn_mode == LIDFE_CMVN_PER_UTT)
-    CU_TRY(cudaMemsetAsync(p->d_utt_stats, 0, static_cast<size_t>(p->B) * 2 * h->n_out * sizeof(double), st));
+  // per-utterance CMVN: no memset -- the statistics workspace is double buffered and the apply kernel of one launch
+  // clears the half the next launch accumulates into (a plan is in flight on one stream at a time)
+  const size_t stats_half = static_cast<size_t>(p->B) * 2 * h->n_out;
+  double* stats_cur = p->d_utt_stats + (p->stats_flip ? stats_half : 0);
+  double* stats_nxt = p->d_utt_stats + (p->stats_flip ? 0 : stats_half);
+  if (cmvn_mode == LIDFE_CMVN_PER_UTT) {
+    P.utt_stats = stats_cur;
+    p->stats_flip ^= 1;
+  }
   if (cmvn_mode == LIDFE_POST_TOPDB)
     CU_TRY(cudaMemsetAsync(p->d_utt_max, 0, static_cast<size_t>(p->B) * sizeof(unsigned), st));
 
@@ -565,9 +577,9 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   }
 
   if (cmvn_mode == LIDFE_CMVN_PER_UTT)
-    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, p->d_utt_stats, nullptr, st, 1);
+    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, stats_cur, nullptr, st, 1, stats_nxt);
   if (cmvn_mode == LIDFE_POST_TOPDB)
-    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, nullptr, st, 2);
+    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, nullptr, st, 2, nullptr);
   return LIDFE_OK;
 }
 
@@ -575,7 +587,7 @@ int lidfe_cmvn_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
                      const double* stats_dev, void* stream) {
   if (!h || !p || !feats_dev || !stats_dev) return LIDFE_E_NULL;
   if (p->ctx != h || ld < h->n_out || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
-  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, stats_dev, static_cast<cudaStream_t>(stream), 1);
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, stats_dev, static_cast<cudaStream_t>(stream), 1, nullptr);
 }
 
 int lidfe_profile_begin(lidfe_handle h, int max_launches) {
@@ -612,7 +624,7 @@ int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
                      void* stream) {
   if (!h || !p || !feats_dev || !masks_dev) return LIDFE_E_NULL;
   if (p->ctx != h || ld < h->n_out || n_masks < 1 || n_masks > kMaxMasks) return LIDFE_E_ARG;
-  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, nullptr, static_cast<cudaStream_t>(stream), 0);
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, nullptr, static_cast<cudaStream_t>(stream), 0, nullptr);
 }
 
 static int launch_wave(lidfe_handle h, lidfe_plan p, const void* in, int in_i16, float in_scale, float* out, int normalize,

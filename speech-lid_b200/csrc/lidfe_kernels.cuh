@@ -779,6 +779,7 @@ struct ApplyParams {
   int rows_per_cta;
   const unsigned* utt_max;       // [B] (normalize == 2)
   float top_db;
+  double* clear_stats;           // [B][2][n_out] or NULL: the other half of the ping-pong workspace, zeroed here
 };
 
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__ ApplyParams P) {
@@ -811,6 +812,8 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   }
 
   const float db_floor = (P.normalize == 2) ? ord2f(P.utt_max[utt]) - P.top_db : 0.f;
+  if (P.clear_stats && blockIdx.y == 0 && tid < 2 * P.n_out)
+    P.clear_stats[static_cast<long long>(utt) * 2 * P.n_out + tid] = 0.0;   // next launch's accumulators
   if (tid < P.n_out) {
     float mean = 0.f, inv = 1.f;
     if (P.normalize == 1) {
