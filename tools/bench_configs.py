@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Device-resident throughput of the other BASELINE configs / branches on one GPU (CUDA events, rotating buffers):
+cfg1 (32 x 3 s fbank), cfg2 without CMVN, cfg3 (512 x 4 s MFCC-40 of 80), the default MelSpectrogram+dB branch on the
+cfg2 shape, int16 input.  One JSON line each; informational (bench.py carries the headline)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import speech_lid_b200 as lid
+
+
+def run(name, fe, B, N, steps=100, warmup=10, dtype=torch.float32, **kw):
+    dev = fe.device
+    plan = fe.make_plan([N] * B, padded=True)
+    g = torch.Generator(device=dev).manual_seed(1)
+    nbuf = max(3, int(400e6 // (B * N * 4)) if B * N * 4 < 130e6 else 3)
+    ins = []
+    for _ in range(nbuf):
+        w = torch.randn(B * N, device=dev, generator=g)
+        ins.append((w * 3000).clamp(-32768, 32767).to(torch.int16) if dtype == torch.int16 else w)
+    outs = [torch.empty(B, plan.t_max, fe.n_out, device=dev) for _ in range(nbuf)]
+    for i in range(warmup):
+        fe.featurize_packed(ins[i % nbuf], plan, out=outs[i % nbuf], **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fe.featurize_packed(ins[i % nbuf], plan, out=outs[i % nbuf], **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    audio_s = B * N / 16000.0
+    print(json.dumps({"config": name, "utterances": B, "samples": N, "frames": plan.total_frames, "ms_per_step": round(ms, 5),
+                      "audio_s_per_s": round(audio_s / (ms * 1e-3), 1), "rotating_sets": nbuf}), flush=True)
+
+
+def main():
+    torch.cuda.set_device(0)
+    fb = lid.FrontEnd(n_mels=80)
+    run("cfg1: 80-dim kaldi fbank, 32 x 3 s", fb, 32, 48000)
+    run("cfg2 shape, kaldi fbank only (no CMVN, no masks), 256 x 8 s", fb, 256, 128000)
+    masks = lid.draw_masks([798] * 256, 80, 0.05, 27, 2)
+    run("cfg2 shape, kaldi fbank + SpecAugment in the epilogue (no CMVN), 256 x 8 s", fb, 256, 128000, masks=masks)
+    run("cfg2: kaldi fbank + SpecAugment + per-utterance CMVN, 256 x 8 s", fb, 256, 128000, masks=masks, cmvn="utt")
+    mf = lid.FrontEnd(n_mels=80, n_ceps=40)
+    run("cfg3: 40 MFCC of 80 mel (DCT epilogue), 512 x 4 s", mf, 512, 64000)
+    ms = lid.FrontEnd(kind="melspec_db", pad=16)
+    run("default branch: MelSpectrogram + AmplitudeToDB(top_db=80), pad 16, 256 x 8 s", ms, 256, 128000)
+    i16 = lid.FrontEnd(n_mels=80, in_dtype=torch.int16, in_scale=1.0 / 32768.0)
+    run("kaldi fbank from int16 samples (2 B/sample read), 256 x 8 s", i16, 256, 128000, dtype=torch.int16)
+
+
+if __name__ == "__main__":
+    main()
