@@ -625,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
 #pragma unroll
         for (int b = 0; b < kBands; ++b) acc[b] = make_float2(0.f, 0.f);
         const int nc = P.n_ceps;
+#pragma unroll 4
         for (int m = 0; m < P.n_mels; ++m) {
           const f2 l = my_L[m];
           const float* drow = sm_dct + m * nc + t;

@@ -42,7 +42,7 @@ def main():
     fb = lid.FrontEnd(n_mels=80)
     run("cfg1: 80-dim kaldi fbank, 32 x 3 s", fb, 32, 48000)
     run("cfg2 shape, kaldi fbank only (no CMVN, no masks), 256 x 8 s", fb, 256, 128000)
-    masks = lid.draw_masks([798] * 256, 80, 0.05, 27, 2)
+    masks = lid.draw_masks([798] * 256, 80, 0.05, 27, 2).cuda()      # resident, like the waveforms
     run("cfg2 shape, kaldi fbank + SpecAugment in the epilogue (no CMVN), 256 x 8 s", fb, 256, 128000, masks=masks)
     run("cfg2: kaldi fbank + SpecAugment + per-utterance CMVN, 256 x 8 s", fb, 256, 128000, masks=masks, cmvn="utt")
     mf = lid.FrontEnd(n_mels=80, n_ceps=40)
