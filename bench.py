@@ -212,7 +212,8 @@ def run_gpu_arm(args):
     barrier()
 
     sampler = ClockSampler(torch.cuda._get_nvml_device_index(dev) if hasattr(torch.cuda, "_get_nvml_device_index") else local_rank)
-    fe.profile_begin(args.steps)
+    prof_stride = 4 if args.steps >= 16 else 1     # sample the kernel timing: an event record between kernels costs ~us
+    fe.profile_begin(args.steps, stride=prof_stride)
     launches0 = lib.lidfe_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
@@ -314,6 +315,7 @@ def run_gpu_arm(args):
     roofline = {"bound": "hbm", "kernel": "fbank_kernel<float,false>", "achieved": round(achieved, 1),
                 "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
                 "traffic": traffic, "kernel_ms": round(k_ms, 5), "kernel_share_of_step": round(k_ms / ms_step, 3),
+                "kernel_timing": "CUDA event pair around every %d-th launch of the timed region (%d samples)" % (prof_stride, len(kernel_ms)),
                 "alg_bytes_per_launch": alg_bytes,
                 "fp32": {"achieved_tflops": round(fp32_achieved, 2), "peak_tflops_at_sampled_clock": round(fp32_peak_at_clock, 1),
                          "peak_tflops_at_max_clock": round(fp32_peak_boost, 1),

@@ -208,6 +208,8 @@ int lidfe_wave_stages_i16(lidfe_handle h, lidfe_plan p, const short* pcm_in_dev,
  * a CUDA event pair on the launching stream (up to max_launches calls).  lidfe_profile_end synchronises on them and
  * returns the per-launch durations in milliseconds (bench.py's roofline leg).  Not thread-safe per handle. */
 int lidfe_profile_begin(lidfe_handle h, int max_launches);
+/* bracket only every stride-th call (default 1): an event record between two kernels costs a few microseconds */
+int lidfe_profile_set_stride(lidfe_handle h, int stride);
 int lidfe_profile_end(lidfe_handle h, float* ms_host, int capacity, int* n_out);
 
 /* -- misc ----------------------------------------------------------------------------------------- */

@@ -23,7 +23,7 @@ EXPORTS = (
     "lidfe_create", "lidfe_destroy", "lidfe_num_frames", "lidfe_out_dim", "lidfe_plan_create",
     "lidfe_plan_destroy", "lidfe_plan_total_frames", "lidfe_plan_num_tiles", "lidfe_plan_frames",
     "lidfe_featurize", "lidfe_cmvn_apply", "lidfe_wave_stages", "lidfe_wave_stages_i16", "lidfe_mask_apply", "lidfe_strerror",
-    "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_mel_plan",
+    "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_profile_set_stride", "lidfe_mel_plan",
 )
 
 
@@ -82,6 +82,8 @@ def load_library() -> C.CDLL:
     lib.lidfe_mask_apply.restype = i32
     lib.lidfe_wave_stages.argtypes = [vp, vp, vp, vp, i32, f32, vp, f32, vp]
     lib.lidfe_wave_stages.restype = i32
+    lib.lidfe_profile_set_stride.argtypes = [vp, i32]
+    lib.lidfe_profile_set_stride.restype = i32
     lib.lidfe_profile_begin.argtypes = [vp, i32]
     lib.lidfe_profile_begin.restype = i32
     lib.lidfe_profile_end.argtypes = [vp, C.POINTER(C.c_float), i32, C.POINTER(C.c_int)]

@@ -26,11 +26,17 @@ struct lidfe_ctx {
   // device tables
   unsigned char* d_blob;   // window | tw1 | tw2 | mel_k0 | mel_w | dct | lifter, laid out like the kernel's shared memory
   int blob_bytes;
+  int blob_bytes_fbank;    // prefix without dct / lifter (the fbank-only kernel variant of the two-kernel MFCC path)
+  int dct_off, lifter_off; // byte offsets of those sections inside the blob
+  size_t smem_bytes_fbank;
+  size_t smem_bytes_dct;
   size_t smem_bytes;
   int grid_cap;   // resident CTAs of the fbank kernel on this device
   // optional per-launch timing of the fbank kernel (bench.py's roofline leg)
   std::vector<cudaEvent_t>* prof_events;
   int prof_used;
+  int prof_stride;   // bracket every prof_stride-th featurize call (event records between kernels cost a few us)
+  int prof_calls;
 };
 
 struct lidfe_plan_s {
@@ -48,6 +54,8 @@ struct lidfe_plan_s {
   double* d_utt_stats;    // [2 launches][B][2][n_out]: ping-pong, the apply kernel of launch i clears the buffer of launch i+1
   int stats_flip;         // which half the next per-utterance-CMVN launch accumulates into (host-side toggle)
   unsigned* d_utt_max;    // [B] (LIDFE_POST_TOPDB)
+  float* d_logmel;        // [rows][n_mels] log-mel workspace of the two-kernel MFCC path (allocated on first use)
+  long long max_row;      // rows of the output matrix this plan touches
 };
 
 static std::atomic<long long> g_launches{0};
@@ -331,8 +339,11 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   append(tw2.data(), tw2.size() * sizeof(float2));
   append(k0.data(), static_cast<size_t>(kMaxMels) * sizeof(int));
   if (total_taps > 0) append(melw.data(), static_cast<size_t>(total_taps) * 16 * sizeof(float));
+  c->blob_bytes_fbank = static_cast<int>(blob.size());
   if (cfg->n_ceps > 0) {
+    c->dct_off = static_cast<int>(blob.size());
     append(dct_host, static_cast<size_t>(cfg->n_mels) * cfg->n_ceps * sizeof(float));
+    c->lifter_off = static_cast<int>(blob.size());
     append(lifter.data(), static_cast<size_t>(cfg->n_ceps) * sizeof(float));
   }
   c->blob_bytes = static_cast<int>(blob.size());
@@ -342,8 +353,22 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   if (e == cudaSuccess) e = upload(&c->d_blob, blob.data(), blob.size());
   if (e == cudaSuccess) {
     c->smem_bytes = smem_for(*cfg, total_taps);
+    if (cfg->n_ceps > 0 && cfg->n_ceps <= kDctMaxCeps) {
+      // two-kernel MFCC path: fbank-only variant into a log-mel workspace, then mfcc_dct_kernel
+      lidfe_config fb = *cfg;
+      fb.n_ceps = 0;
+      c->smem_bytes_fbank = smem_for(fb, total_taps);
+      fbank_fn f2 = (cfg->in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, c->std_mel != 0)
+                                                      : pick_kernel_t<float>(false, c->std_mel != 0);
+      e = cudaFuncSetAttribute(f2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes_fbank));
+      c->smem_bytes_dct = (static_cast<size_t>(kDctRows) * (cfg->n_mels + 1) + static_cast<size_t>(cfg->n_mels) * kDctMaxCeps +
+                           kDctMaxCeps + 2 * kDctMaxCeps) * sizeof(float);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mfcc_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes_dct));
+    }
     fbank_fn fn = pick_kernel(c);
-    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes));
     if (e == cudaSuccess) {
       int per_sm = 0;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, c->smem_bytes);
@@ -439,6 +464,12 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   p->d_utt_stats = nullptr;
   p->stats_flip = 0;
   p->d_utt_max = nullptr;
+  p->d_logmel = nullptr;
+  p->max_row = 0;
+  for (int i = 0; i < B; ++i) {
+    const long long end = out_rows_host[i] + ((pad_rows_host && pad_rows_host[i] > frames[i]) ? pad_rows_host[i] : frames[i]);
+    if (end > p->max_row) p->max_row = end;
+  }
   cudaError_t e = upload(&p->d_tiles, tiles.data(), tiles.size());
   if (e == cudaSuccess) e = upload(&p->d_frames, frames.data(), frames.size());
   if (e == cudaSuccess) e = upload(&p->d_out_rows, out_rows_host, static_cast<size_t>(B));
@@ -466,6 +497,7 @@ int lidfe_plan_destroy(lidfe_plan p) {
   cudaFree(p->d_lengths);
   cudaFree(p->d_utt_stats);
   cudaFree(p->d_utt_max);
+  cudaFree(p->d_logmel);
   delete p;
   return LIDFE_OK;
 }
@@ -563,10 +595,62 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   if (cmvn_mode == LIDFE_POST_TOPDB)
     CU_TRY(cudaMemsetAsync(p->d_utt_max, 0, static_cast<size_t>(p->B) * sizeof(unsigned), st));
 
+  const bool mfcc2 = h->cfg.n_ceps > 0 && h->cfg.n_ceps <= kDctMaxCeps &&
+                     (cmvn_mode == LIDFE_CMVN_NONE || cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL);
+  if (mfcc2) {
+    // MFCC without statistics: fbank-only kernel into the log-mel workspace, then the register-tiled DCT kernel
+    if (!p->d_logmel)
+      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&p->d_logmel), static_cast<size_t>(p->max_row) * h->cfg.n_mels * sizeof(float)));
+    FbankParams F = P;
+    F.out = p->d_logmel;
+    F.out_ld = h->cfg.n_mels;
+    F.n_ceps = 0;
+    F.n_out = h->cfg.n_mels;
+    F.masks = nullptr;
+    F.n_masks = 0;
+    F.mode = LIDFE_CMVN_NONE;
+    F.const_bytes = h->blob_bytes_fbank;
+    fbank_fn f2 = (h->cfg.in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, h->std_mel != 0)
+                                                     : pick_kernel_t<float>(false, h->std_mel != 0);
+    long long g2 = p->n_tiles < static_cast<long long>(h->num_sms) * 3 ? p->n_tiles : static_cast<long long>(h->num_sms) * 3;
+    if (g2 < 1) g2 = 1;
+    const bool prof2 = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
+    if (prof2) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
+    f2<<<static_cast<unsigned>(g2), kThreads, h->smem_bytes_fbank, st>>>(F);
+    g_launches.fetch_add(1);
+    CU_TRY(cudaGetLastError());
+    if (prof2) {
+      CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used + 1], st));
+      h->prof_used += 2;
+    }
+    DctParams D;
+    D.logmel = p->d_logmel;
+    D.out = out_dev;
+    D.out_ld = out_ld;
+    D.tiles = p->d_tiles;
+    D.n_tiles = static_cast<int>(p->n_tiles);
+    D.n_mels = h->cfg.n_mels;
+    D.n_ceps = h->cfg.n_ceps;
+    D.dct = reinterpret_cast<const float*>(h->d_blob + h->dct_off);
+    D.lifter = reinterpret_cast<const float*>(h->d_blob + h->lifter_off);
+    D.masks = masks_dev;
+    D.n_masks = masks_dev ? n_masks : 0;
+    D.mode = cmvn_mode;
+    D.stats_in = stats_in_dev;
+    long long groups = (p->n_tiles + 7) / 8;
+    long long gd = groups < static_cast<long long>(h->num_sms) * 4 ? groups : static_cast<long long>(h->num_sms) * 4;
+    if (gd < 1) gd = 1;
+    mfcc_dct_kernel<<<static_cast<unsigned>(gd), kDctRows, h->smem_bytes_dct, st>>>(D);
+    g_launches.fetch_add(1);
+    CU_TRY(cudaGetLastError());
+    return LIDFE_OK;
+  }
+
   long long grid = p->n_tiles < h->grid_cap ? p->n_tiles : h->grid_cap;
   if (grid < 1) grid = 1;
   fbank_fn fn = pick_kernel(h);
-  const bool prof = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
+  bool prof = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
+  if (prof) prof = (h->prof_calls++ % (h->prof_stride > 0 ? h->prof_stride : 1)) == 0;
   if (prof) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
   fn<<<static_cast<unsigned>(grid), kThreads, h->smem_bytes, st>>>(P);
   g_launches.fetch_add(1);
@@ -596,7 +680,16 @@ int lidfe_profile_begin(lidfe_handle h, int max_launches) {
   h->prof_events = new (std::nothrow) std::vector<cudaEvent_t>(static_cast<size_t>(max_launches) * 2);
   if (!h->prof_events) return LIDFE_E_NOMEM;
   h->prof_used = 0;
+  h->prof_calls = 0;
+  if (h->prof_stride <= 0) h->prof_stride = 1;
   for (auto& ev : *h->prof_events) CU_TRY(cudaEventCreate(&ev));
+  return LIDFE_OK;
+}
+
+int lidfe_profile_set_stride(lidfe_handle h, int stride) {
+  if (!h) return LIDFE_E_NULL;
+  if (stride < 1) return LIDFE_E_ARG;
+  h->prof_stride = stride;
   return LIDFE_OK;
 }
 

@@ -912,6 +912,141 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// MFCC as a second kernel: ceps = (log-mel @ DCT) * lifter  (ta: compliance/kaldi.py:648-666,786-796).
+// The in-kernel DCT epilogue of fbank_kernel re-reads the 80x40 matrix from shared memory for every frame pair and
+// drops the fbank kernel to 2 CTAs/SM; when no statistics are needed (cmvn none / global apply) it is ~3x faster to let
+// fbank_kernel write the log-mels to a workspace and run this register-tiled FP32 GEMM: one thread per frame, 40
+// accumulators in registers, the DCT matrix broadcast from shared memory, rows staged through shared memory so that
+// global loads and stores stay coalesced.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDctRows = 128;            // frames per CTA pass = 8 tiles
+constexpr int kDctMaxCeps = 40;          // accumulators per thread (n_ceps <= 40 takes this path)
+
+struct DctParams {
+  const float* logmel;      // workspace [rows][n_mels], same row numbering as out
+  float* out;
+  long long out_ld;
+  const Tile* tiles;
+  int n_tiles;
+  int n_mels, n_ceps;
+  const float* dct;         // [n_mels][n_ceps] device copy
+  const float* lifter;      // [n_ceps]
+  const int* masks;
+  int n_masks;
+  int mode;                 // 0 none, 2 global apply
+  const double* stats_in;   // [2*n_ceps+1] (mode 2)
+};
+
+__global__ void __launch_bounds__(kDctRows) mfcc_dct_kernel(const __grid_constant__ DctParams P) {
+  extern __shared__ __align__(16) float dsm[];
+  const int nm = P.n_mels, nc = P.n_ceps;
+  const int in_stride = nm + 1;                         // conflict-free row reads
+  float* s_in = dsm;                                    // [kDctRows][nm + 1], reused as [kDctRows][nc] for the outputs
+  float* s_dct = s_in + kDctRows * in_stride;           // [nm][kDctMaxCeps] zero padded
+  float* s_lift = s_dct + nm * kDctMaxCeps;             // [kDctMaxCeps]
+  float2* s_norm = reinterpret_cast<float2*>(s_lift + kDctMaxCeps);   // [kDctMaxCeps] (mean, inv)
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nm * kDctMaxCeps; i += kDctRows) {
+    const int m = i / kDctMaxCeps, c = i - m * kDctMaxCeps;
+    s_dct[i] = c < nc ? P.dct[m * nc + c] : 0.f;
+  }
+  if (tid < kDctMaxCeps) {
+    s_lift[tid] = tid < nc ? P.lifter[tid] : 0.f;
+    float mean = 0.f, inv = 1.f;
+    if (P.mode == 2 && tid < nc) {
+      const double n = P.stats_in[2 * nc];
+      const double mu = P.stats_in[tid] / n;
+      double var = (P.stats_in[nc + tid] - P.stats_in[tid] * mu) / (n - 1.0);
+      var = var > 0.0 ? var : 0.0;
+      mean = static_cast<float>(mu);
+      inv = static_cast<float>(1.0 / (sqrt(var) + 1e-9));
+    }
+    s_norm[tid] = make_float2(mean, inv);
+  }
+  const int groups = (P.n_tiles + 7) / 8;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    __syncthreads();                                    // previous pass's stores out of s_in are done; tables visible
+    const int lt = tid >> 4, lr = tid & 15;             // my tile of the group, my row in it
+    const int tix = g * 8 + lt;
+    Tile tl;
+    tl.nframes = -1;
+    if (tix < P.n_tiles) tl = P.tiles[tix];
+    // stage: every tile's rows are contiguous in the workspace (ld = n_mels)
+    for (int q = 0; q < 8; ++q) {
+      const int tq = g * 8 + q;
+      if (tq >= P.n_tiles) break;
+      const Tile t2 = P.tiles[tq];
+      if (t2.nframes <= 0) continue;
+      const float* src = P.logmel + t2.out_row * nm;
+      const int total = t2.nframes * nm;
+      for (int i = tid; i < total; i += kDctRows) {
+        const int r = i / nm, m = i - r * nm;
+        s_in[(q * 16 + r) * in_stride + m] = src[i];
+      }
+    }
+    __syncthreads();
+    float acc[kDctMaxCeps];
+#pragma unroll
+    for (int c = 0; c < kDctMaxCeps; ++c) acc[c] = 0.f;
+    const bool live = tl.nframes > 0 && lr < tl.nframes;
+    if (live) {
+      const float* row = s_in + tid * in_stride;
+      for (int m = 0; m < nm; ++m) {
+        const float l = row[m];
+        const float4* d4 = reinterpret_cast<const float4*>(s_dct + m * kDctMaxCeps);
+#pragma unroll
+        for (int c4 = 0; c4 < kDctMaxCeps / 4; ++c4) {
+          const float4 d = d4[c4];
+          acc[4 * c4 + 0] = fmaf(l, d.x, acc[4 * c4 + 0]);
+          acc[4 * c4 + 1] = fmaf(l, d.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(l, d.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(l, d.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+    __syncthreads();                                    // all rows consumed: s_in becomes the output staging area
+    if (live) {
+      const int tf = tl.t0 + lr;
+      bool zr = false;
+      for (int q = 0; q < P.n_masks; ++q) {
+        const int* mk = P.masks + (static_cast<long long>(tl.utt) * P.n_masks + q) * 4;
+        zr |= (tf >= mk[0] && tf < mk[1]);
+      }
+#pragma unroll
+      for (int c = 0; c < kDctMaxCeps; ++c) {
+        if (c < nc) {
+          float x = __fmul_rn(acc[c], s_lift[c]);
+          if (P.mode == 2) x = (x - s_norm[c].x) * s_norm[c].y;
+          bool z = zr;
+          for (int q = 0; q < P.n_masks; ++q) {
+            const int* mk = P.masks + (static_cast<long long>(tl.utt) * P.n_masks + q) * 4;
+            z |= (c >= mk[2] && c < mk[3]);
+          }
+          s_in[tid * nc + c] = z ? 0.f : x;
+        }
+      }
+    }
+    __syncthreads();
+    for (int q = 0; q < 8; ++q) {
+      const int tq = g * 8 + q;
+      if (tq >= P.n_tiles) break;
+      const Tile t2 = P.tiles[tq];
+      if (t2.nframes > 0) {
+        for (int i = tid; i < t2.nframes * nc; i += kDctRows) {
+          const int r = i / nc, c = i - r * nc;
+          P.out[(t2.out_row + r) * P.out_ld + c] = s_in[(q * 16 + r) * nc + c];
+        }
+      } else if (t2.nframes == 0) {                     // zero-fill tile: pad_sequence's zeros
+        for (int i = tid; i < t2.aux * nc; i += kDctRows) {
+          const int r = i / nc, c = i - r * nc;
+          P.out[(t2.out_row + r) * P.out_ld + c] = 0.f;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // waveform-level stages (ref: lid/audio_processor.py:108-115,129-134).  One CTA per utterance.
 // ------------------------------------------------------------------------------------------------
 struct WaveParams {

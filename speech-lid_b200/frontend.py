@@ -151,7 +151,9 @@ class FrontEnd:
             pass
 
     # ------------------------------------------------------------------ measurement hooks
-    def profile_begin(self, max_launches: int) -> None:
+    def profile_begin(self, max_launches: int, stride: int = 1) -> None:
+        """Bracket the fused fbank kernel of every ``stride``-th featurize call with a CUDA event pair."""
+        _lib.check(self.lib.lidfe_profile_set_stride(self.handle, int(stride)))
         _lib.check(self.lib.lidfe_profile_begin(self.handle, int(max_launches)))
 
     def profile_end(self) -> List[float]:
