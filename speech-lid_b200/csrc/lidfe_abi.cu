@@ -88,7 +88,10 @@ static fbank_fn pick_kernel(const lidfe_ctx* c) {
                                          : pick_kernel_t<float>(mfcc, c->std_mel != 0);
 }
 static size_t smem_for(const lidfe_config& c, int total_taps) {
-  const size_t base = (c.in_dtype == LIDFE_IN_I16) ? SmemLayout<short>::off_melw : SmemLayout<float>::off_melw;
+  const bool mf = c.n_ceps > 0;
+  const size_t base = (c.in_dtype == LIDFE_IN_I16)
+                          ? (mf ? SmemLayout<short, true>::off_melw : SmemLayout<short, false>::off_melw)
+                          : (mf ? SmemLayout<float, true>::off_melw : SmemLayout<float, false>::off_melw);
   size_t extra = static_cast<size_t>(total_taps) * 16;
   if (c.n_ceps > 0) extra += ((static_cast<size_t>(c.n_mels) * c.n_ceps + 3) & ~static_cast<size_t>(3)) + ((c.n_ceps + 3) & ~3);
   return base + extra * sizeof(float);
@@ -612,7 +615,7 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     F.const_bytes = h->blob_bytes_fbank;
     fbank_fn f2 = (h->cfg.in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, h->std_mel != 0)
                                                      : pick_kernel_t<float>(false, h->std_mel != 0);
-    long long g2 = p->n_tiles < static_cast<long long>(h->num_sms) * 3 ? p->n_tiles : static_cast<long long>(h->num_sms) * 3;
+    long long g2 = p->n_tiles < static_cast<long long>(h->num_sms) * 4 ? p->n_tiles : static_cast<long long>(h->num_sms) * 4;
     if (g2 < 1) g2 = 1;
     const bool prof2 = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
     if (prof2) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));

@@ -34,11 +34,14 @@ constexpr int kMaxMels = 80;
 constexpr int kBands = kMaxMels / 16;             // lane t owns output dims t + 16*b
 constexpr int kRowStride = 18;                    // (A,B) pairs per transpose row: 16 + 2 pad -> LDS.128 conflict free
 constexpr int kPlaneFloats = 16 * kRowStride * 2; // one plane (re or im) of a frame pair: 576 floats
-constexpr int kScratchFloats = 2 * kPlaneFloats;  // per half-warp: re plane + im plane (reused for the power bins)
-constexpr int kLogmelOff = 640;                   // MFCC log-mel staging (80 pairs) behind the 257 power pairs
-constexpr int kValsOff = 960;                     // final feature pairs parked for the statistics pass (80 pairs)
+// per half-warp scratch: ONE transpose plane (re, then im, go through it one after the other), reused for the 257 power
+// pairs (floats 0..513); behind them the parked feature pairs of the statistics pass, and for the in-kernel MFCC
+// epilogue the log-mel staging area
+constexpr int kLogmelOff = 520;                   // MFCC log-mel staging (80 pairs)
+__host__ __device__ constexpr int vals_off(bool mfcc) { return mfcc ? 688 : 520; }         // parked feature pairs (80 pairs)
+__host__ __device__ constexpr int scratch_floats(bool mfcc) { return mfcc ? 864 : 704; }
 constexpr int kMaxMasks = 8;
-constexpr int kTileCache = 32;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
+constexpr int kTileCache = 16;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
 // taps per band of the 80-mel / 16 kHz / 512 Kaldi bank
 // (after the host shifts each filter's first tap so that the 16 lanes of a band read 16 distinct bank pairs)
 __host__ __device__ constexpr int std_taps(int b) { return b == 0 ? 3 : b == 1 ? 5 : b == 2 ? 6 : b == 3 ? 10 : 17; }
@@ -249,16 +252,15 @@ struct InTraits<short> {
 };
 
 // shared-memory carve-up (dynamic)
-template <typename TIn>
+template <typename TIn, bool kMfcc>
 struct SmemLayout {
   static constexpr int kInBytes = ((kTileSamplesPad * (int)sizeof(TIn)) + 127) / 128 * 128;
-  static constexpr int off_in0 = 0;
-  static constexpr int off_in1 = kInBytes;
-  static constexpr int off_scratch = 2 * kInBytes;                                 // [2*kWarps][kScratchFloats] floats
-  static constexpr int off_norm = off_scratch + 2 * kWarps * kScratchFloats * 4;   // [80] float2 (mean, inv_std)
+  static constexpr int off_in0 = 0;                                                // ONE input buffer (see the tile loop)
+  static constexpr int off_scratch = kInBytes;                                     // [2*kWarps][scratch_floats] floats
+  static constexpr int off_norm = off_scratch + 2 * kWarps * scratch_floats(kMfcc) * 4;   // [80] float2 (mean, inv_std)
   static constexpr int off_acc = off_norm + kMaxMels * 8;                          // fp64: [kWarps][2][80] per-warp sums + frame count
-  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;      // [2 staged + kWarps private][kMaxMasks][4] int
-  static constexpr int off_bar = off_masks + (2 + kWarps) * kMaxMasks * 16;        // mbarriers: full[2], tables, empty[2]
+  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;      // [1 staged + kWarps private][kMaxMasks][4] int
+  static constexpr int off_bar = off_masks + (1 + kWarps) * kMaxMasks * 16;        // mbarriers: full, tables; then the arrival counter
   static constexpr int off_tiles = off_bar + 48;                                   // [kTileCache] Tile descriptors
   // constant tables, one contiguous block = the device blob (see FbankParams::const_blob)
   static constexpr int off_window = off_tiles + kTileCache * 32;                   // [416]
@@ -272,11 +274,12 @@ struct SmemLayout {
 // the fused front-end kernel
 // ------------------------------------------------------------------------------------------------
 template <typename TIn, bool kMfcc, bool kStdMel>
-__global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constant__ FbankParams P) {
-  using L = SmemLayout<TIn>;
+__global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constant__ FbankParams P) {
+  using L = SmemLayout<TIn, kMfcc>;
+  constexpr int kScratchFloats = scratch_floats(kMfcc);
+  constexpr int kValsOff = vals_off(kMfcc);
   extern __shared__ __align__(128) unsigned char smem[];
-  TIn* const sm_in0 = reinterpret_cast<TIn*>(smem + L::off_in0);
-  TIn* const sm_in1 = reinterpret_cast<TIn*>(smem + L::off_in1);
+  TIn* const sm_in = reinterpret_cast<TIn*>(smem + L::off_in0);
   float* const sm_scratch = reinterpret_cast<float*>(smem + L::off_scratch);
   const float* const sm_window = reinterpret_cast<const float*>(smem + L::off_window);
   const float2* const sm_tw1 = reinterpret_cast<const float2*>(smem + L::off_tw1);
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
   double* const sm_acc = reinterpret_cast<double*>(smem + L::off_acc);
   int* const sm_masks = reinterpret_cast<int*>(smem + L::off_masks);
   uint64_t* const sm_bar = reinterpret_cast<uint64_t*>(smem + L::off_bar);
-  int* const sm_claim = reinterpret_cast<int*>(smem + L::off_bar + 40);   // highest tile sequence number whose staging is taken
+  int* const sm_arrivals = reinterpret_cast<int*>(smem + L::off_bar + 40);   // warps that have consumed the current tile's samples (running count)
   Tile* const sm_tiles = reinterpret_cast<Tile*>(smem + L::off_tiles);
   float* const sm_melw = reinterpret_cast<float*>(smem + L::off_melw);
 
@@ -316,12 +319,9 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
 
   // ---- one-time staging: all constant tables arrive with ONE TMA bulk copy while the CTA sets up the rest ------
   if (tid == 0) {
-    mbar_init(&sm_bar[0], 1);            // full[0]: samples of the tile in buffer 0 have landed
-    mbar_init(&sm_bar[1], 1);            // full[1]
+    mbar_init(&sm_bar[0], 1);            // full: samples (and mask table) of the staged tile have landed
     mbar_init(&sm_bar[2], 1);            // constant tables have landed
-    mbar_init(&sm_bar[3], kWarps);       // empty[0]: every warp has consumed the samples in buffer 0
-    mbar_init(&sm_bar[4], kWarps);       // empty[1]
-    *sm_claim = 0;
+    *sm_arrivals = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&sm_bar[2], static_cast<uint32_t>(P.const_bytes));
     tma_bulk_g2s_plain(smem + L::off_window, P.const_blob, static_cast<uint32_t>(P.const_bytes), &sm_bar[2]);
@@ -346,46 +346,28 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
   }
   __syncthreads();   // mbarriers initialised, descriptors cached
 
-  // Producer side (warp 0): stage a tile's samples -- and its utterance's mask table -- into buffer `buf`.  There is no
-  // CTA-wide barrier per tile: a buffer is re-filled once every warp has arrived on its "empty" mbarrier (after its
-  // stage-0 reads), and consumers wait on the "full" mbarrier, so warps may drift up to two tiles apart.
-  // The producer of a tile is whichever warp reaches the staging point first (smem atomicMax election), so a slow
-  // warp never delays the prefetch.  The bookkeeping (uses per buffer, utterance of the staged masks) is a
-  // function of the tile sequence alone and is tracked identically by every warp.
-  int staged0 = 0, staged1 = 0, staged_utt = -1;
+  // Producer side.  There is ONE input buffer and no CTA-wide barrier per tile: every warp bumps a shared arrival counter
+  // once it has consumed its samples (right after the framing stage, ~15 % into a tile); the warp that arrives last
+  // knows the buffer -- and the staged mask table -- is free and immediately stages the next tile (TMA bulk copy), so
+  // the copy overlaps the remaining ~85 % of the current tile.  Consumers wait on the "full" mbarrier.
   const bool stage_masks = (mode == 0 || mode == 2) && P.n_masks > 0;
-  auto stage_tile = [&](int tile_idx, int buf, int seq) {
+  auto stage_tile = [&](int tile_idx) {          // called by exactly one warp per tile
     if (tile_idx >= tile_end) return;
     const Tile tl = sm_tiles[(tile_idx - tile_begin) % kTileCache];
     if (tl.nframes == 0) return;
-    const int k = buf ? staged1 : staged0;            // uses of this buffer so far
-    if (buf) ++staged1; else ++staged0;
-    const int prev_utt = staged_utt;
-    staged_utt = tl.utt;
-    int mine = 0;
-    if (lane == 0) mine = atomicMax(sm_claim, seq) < seq;
-    mine = __shfl_sync(0xffffffffu, mine, 0);
-    if (!mine) return;
-    if (k > 0) {
-      if (lane == 0) mbar_wait(&sm_bar[3 + buf], static_cast<uint32_t>((k - 1) & 1));
-      __syncwarp();
-    }
     if (stage_masks) {
-      int* ms = sm_masks + buf * kMaxMasks * 4;
-      if (lane < P.n_masks * 4)
-        ms[lane] = (tl.utt == prev_utt) ? sm_masks[(buf ^ 1) * kMaxMasks * 4 + lane]
-                                        : P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + lane];
+      if (lane < P.n_masks * 4) sm_masks[lane] = P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + lane];
       __syncwarp();
     }
     const int nsamp = kFrameShift * tl.nframes + (kFrameLen - kFrameShift);
     const TIn* src = reinterpret_cast<const TIn*>(P.wav) + tl.wav_off;
-    TIn* dst = buf ? sm_in1 : sm_in0;
+    TIn* dst = sm_in;
     if (tl.aux) {
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t bytes = nsamp * (uint32_t)sizeof(TIn);
-        mbar_expect_tx(&sm_bar[buf], bytes);
-        tma_bulk_g2s(dst, src, bytes, &sm_bar[buf], l2_evict_first_policy());
+        mbar_expect_tx(&sm_bar[0], bytes);
+        tma_bulk_g2s(dst, src, bytes, &sm_bar[0], l2_evict_first_policy());
       }
     } else {
       if (!P.center) {
@@ -405,19 +387,24 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm_bar[buf]);       // element-wise staging: plain arrival completes the phase
+      if (lane == 0) mbar_arrive(&sm_bar[0]);         // element-wise staging: plain arrival completes the phase
     }
   };
+  // one arrival per warp and tile; true for the warp that completes the round
+  auto arrive_is_last = [&]() -> bool {
+    int last = 0;
+    if (lane == 0) last = ((atomicAdd(sm_arrivals, 1) % kWarps) == kWarps - 1);
+    return __shfl_sync(0xffffffffu, last, 0) != 0;
+  };
 
-  uint32_t phase0 = 0u, phase1 = 0u;
+  uint32_t phase = 0u;
   float* const my_scratch = sm_scratch + (warp * 2 + half) * kScratchFloats;
-  f2* const T_re = reinterpret_cast<f2*>(my_scratch);
-  f2* const T_im = reinterpret_cast<f2*>(my_scratch + kPlaneFloats);
+  f2* const T_pl = reinterpret_cast<f2*>(my_scratch);      // the transpose plane
   f2* const my_P = reinterpret_cast<f2*>(my_scratch);
   const int partner = (lane & 16) | ((16 - t) & 15);
   const int up_lane = (lane & 16) | ((t - 1) & 15);
 
-  stage_tile(tile_begin, 0, 1);        // first tile's samples are in flight while the tables land (sequence number 1)
+  if (warp == 0) stage_tile(tile_begin);   // first tile's samples are in flight while the tables land
   mbar_wait(&sm_bar[2], 0u);
   int k0[kBands];
 #pragma unroll
@@ -428,10 +415,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
 
   int it = 0;
   for (int tile_idx = tile_begin; tile_idx < tile_end; ++tile_idx, ++it) {
-    const int buf = it & 1;
     const Tile tl = sm_tiles[it % kTileCache];
-    // prefetch the next tile into the other buffer (its previous reader finished before the
-    // __syncthreads that closed the previous iteration)
     if ((it + 1) % kTileCache == 0 && tile_idx + 1 < tile_end) {
       // descriptor cache exhausted (ranges longer than kTileCache tiles): refill.  Everyone has its copy of `tl`.
       __syncthreads();
@@ -441,7 +425,6 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
       for (int i = tid; i < n * 4; i += kThreads) dst[i] = src[i];
       __syncthreads();
     }
-    stage_tile(tile_idx + 1, buf ^ 1, it + 2);
 
     if (tl.nframes == 0) {
       // zero-fill tile: pad_sequence's zeros (ref: lid/raw_datasets.py:347-350)
@@ -451,17 +434,18 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
         const int d = static_cast<int>(i - r * n_out);
         P.out[(tl.out_row + r) * P.out_ld + d] = 0.f;
       }
+      if (arrive_is_last()) stage_tile(tile_idx + 1);
       continue;
     }
 
     // consumer side: wait for this tile's samples (and mask table), take a private copy of the masks
-    if (buf) { mbar_wait(&sm_bar[1], phase1); phase1 ^= 1u; }
-    else     { mbar_wait(&sm_bar[0], phase0); phase0 ^= 1u; }
-    const TIn* in = buf ? sm_in1 : sm_in0;
-    int* const wm = sm_masks + (2 + warp) * kMaxMasks * 4;
+    mbar_wait(&sm_bar[0], phase);
+    phase ^= 1u;
+    const TIn* in = sm_in;
+    int* const wm = sm_masks + (1 + warp) * kMaxMasks * 4;
     if (stage_masks) {
       __syncwarp();                                  // previous tile's readers of this warp's copy are done
-      if (lane < P.n_masks * 4) wm[lane] = sm_masks[buf * kMaxMasks * 4 + lane];
+      if (lane < P.n_masks * 4) wm[lane] = sm_masks[lane];
       __syncwarp();
       if (tl.utt != cur_utt) {
         cur_utt = tl.utt;
@@ -542,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
       // ---- stage 1: 16-point DFT over j, twiddle W256^(K1*t), transpose through shared ------------
       fft16<true>(R, I);
       __syncwarp();   // previous tile's readers of this scratch are done; every lane has consumed its samples
-      if (lane == 0) mbar_arrive(&sm_bar[3 + buf]);   // release the input buffer (and the staged mask table)
+      if (arrive_is_last()) stage_tile(tile_idx + 1);   // the input buffer is free: next tile's TMA overlaps the rest
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int K1 = rev4(p);
@@ -550,16 +534,22 @@ __global__ void __launch_bounds__(kThreads, 3) fbank_kernel(const __grid_constan
           const float2 w = sm_tw1[K1 * 16 + t];
           cmul2(R[p], I[p], w.x, w.y);
         }
-        T_re[K1 * kRowStride + t] = R[p];
-        T_im[K1 * kRowStride + t] = I[p];
+        T_pl[K1 * kRowStride + t] = R[p];
       }
       __syncwarp();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 a = *reinterpret_cast<const float4*>(T_re + t * kRowStride + 2 * q);
-        const float4 b = *reinterpret_cast<const float4*>(T_im + t * kRowStride + 2 * q);
+      for (int q = 0; q < 8; ++q) {                      // real parts back, transposed
+        const float4 a = *reinterpret_cast<const float4*>(T_pl + t * kRowStride + 2 * q);
         R[2 * q] = make_float2(a.x, a.y);
         R[2 * q + 1] = make_float2(a.z, a.w);
+      }
+      __syncwarp();   // one plane: the imaginary parts go through it after the real parts have been read back
+#pragma unroll
+      for (int p = 0; p < 16; ++p) T_pl[rev4(p) * kRowStride + t] = I[p];
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(T_pl + t * kRowStride + 2 * q);
         I[2 * q] = make_float2(b.x, b.y);
         I[2 * q + 1] = make_float2(b.z, b.w);
       }
