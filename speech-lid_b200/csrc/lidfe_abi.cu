@@ -364,8 +364,8 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
       fbank_fn f2 = (cfg->in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, c->std_mel != 0)
                                                       : pick_kernel_t<float>(false, c->std_mel != 0);
       e = cudaFuncSetAttribute(f2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes_fbank));
-      c->smem_bytes_dct = (static_cast<size_t>(kDctRows) * (cfg->n_mels + 1) + static_cast<size_t>(cfg->n_mels) * kDctMaxCeps +
-                           kDctMaxCeps + 2 * kDctMaxCeps) * sizeof(float);
+      c->smem_bytes_dct = (static_cast<size_t>(kDctStages) * kDctMaxTiles * kDctThreads * 4 +
+                           static_cast<size_t>(cfg->n_mels) * kDctMaxCeps + kDctMaxCeps + 2 * kDctMaxCeps) * sizeof(float);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(mfcc_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes_dct));
     }
@@ -598,12 +598,13 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   if (cmvn_mode == LIDFE_POST_TOPDB)
     CU_TRY(cudaMemsetAsync(p->d_utt_max, 0, static_cast<size_t>(p->B) * sizeof(unsigned), st));
 
-  const bool mfcc2 = h->cfg.n_ceps > 0 && h->cfg.n_ceps <= kDctMaxCeps &&
+  const bool mfcc2 = h->cfg.n_ceps > 0 && h->cfg.n_ceps <= kDctMaxCeps && h->cfg.n_mels % 4 == 0 &&
                      (cmvn_mode == LIDFE_CMVN_NONE || cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL);
   if (mfcc2) {
     // MFCC without statistics: fbank-only kernel into the log-mel workspace, then the register-tiled DCT kernel
     if (!p->d_logmel)
-      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&p->d_logmel), static_cast<size_t>(p->max_row) * h->cfg.n_mels * sizeof(float)));
+      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&p->d_logmel),
+                        static_cast<size_t>(p->n_tiles) * kTileFrames * h->cfg.n_mels * sizeof(float)));   // tile-blocked
     FbankParams F = P;
     F.out = p->d_logmel;
     F.out_ld = h->cfg.n_mels;
@@ -612,6 +613,7 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     F.masks = nullptr;
     F.n_masks = 0;
     F.mode = LIDFE_CMVN_NONE;
+    F.ws_blocked = 1;
     F.const_bytes = h->blob_bytes_fbank;
     fbank_fn f2 = (h->cfg.in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, h->std_mel != 0)
                                                      : pick_kernel_t<float>(false, h->std_mel != 0);
@@ -640,10 +642,11 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     D.n_masks = masks_dev ? n_masks : 0;
     D.mode = cmvn_mode;
     D.stats_in = stats_in_dev;
-    long long groups = (p->n_tiles + 7) / 8;
+    // 4 CTAs of 128 threads per SM resident; the tiles are dealt out evenly inside the kernel (one per warp at least)
+    long long groups = (p->n_tiles + 3) / 4;
     long long gd = groups < static_cast<long long>(h->num_sms) * 4 ? groups : static_cast<long long>(h->num_sms) * 4;
     if (gd < 1) gd = 1;
-    mfcc_dct_kernel<<<static_cast<unsigned>(gd), kDctRows, h->smem_bytes_dct, st>>>(D);
+    mfcc_dct_kernel<<<static_cast<unsigned>(gd), kDctThreads, h->smem_bytes_dct, st>>>(D);
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
     return LIDFE_OK;

@@ -83,6 +83,10 @@ struct FbankParams {
   const double* stats_in;   // [2*n_out+1]
   double* stats_out;        // [2*n_out+1]
   double* utt_stats;        // [B][2][n_out]
+  // two-kernel MFCC path: `out` is the log-mel workspace in the tile-blocked layout mfcc_dct_kernel reads,
+  // [tile][n_out / 4][16 frames][4 dims] (a 16-byte chunk = 4 consecutive dims of one frame; the 16 frames of a tile
+  // sit next to each other so that a half-warp of the DCT kernel loads 256 contiguous bytes)
+  int ws_blocked;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
 
     if (tl.nframes == 0) {
       // zero-fill tile: pad_sequence's zeros (ref: lid/raw_datasets.py:347-350)
-      const long long total = static_cast<long long>(tl.aux) * n_out;
+      const long long total = P.ws_blocked ? 0 : static_cast<long long>(tl.aux) * n_out;   // (the DCT kernel fills them)
       for (long long i = tid; i < total; i += kThreads) {
         const long long r = i / n_out;
         const int d = static_cast<int>(i - r * n_out);
@@ -640,19 +644,32 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
             rowB |= (tfA + 1 >= m0 && tfA + 1 < m1);
           }
         }
-        float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
+        if (P.ws_blocked) {
+          // tile-blocked log-mel workspace: dim d = t + 16 b of frame r lives at ((d / 4) * 16 + r) * 4 + d % 4 inside
+          // the tile's block (no masks / normalisation on this path: they belong to the DCT kernel's epilogue)
+          float* o = P.out + static_cast<long long>(tile_idx) * (kTileFrames * n_out) + (t >> 2) * 64 + (t & 3) + flA * 4;
 #pragma unroll
-        for (int b = 0; b < kBands; ++b) {
-          const int d = t + 16 * b;
-          if (d < n_out) {
-            f2 x = val[b];
-            if (mode == 2) {
-              const float2 nm = sm_norm[d];
-              x = mul2(sub2(x, bc(nm.x)), bc(nm.y));
+          for (int b = 0; b < kBands; ++b) {
+            if (t + 16 * b < n_out) {
+              if (actA) o[256 * b] = val[b].x;
+              if (actB) o[256 * b + 4] = val[b].y;
             }
-            const bool dz = (dm >> b) & 1u;
-            if (actA) orow[16 * b] = (dz || rowA) ? 0.f : x.x;
-            if (actB) orow[P.out_ld + 16 * b] = (dz || rowB) ? 0.f : x.y;
+          }
+        } else {
+          float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
+#pragma unroll
+          for (int b = 0; b < kBands; ++b) {
+            const int d = t + 16 * b;
+            if (d < n_out) {
+              f2 x = val[b];
+              if (mode == 2) {
+                const float2 nm = sm_norm[d];
+                x = mul2(sub2(x, bc(nm.x)), bc(nm.y));
+              }
+              const bool dz = (dm >> b) & 1u;
+              if (actA) orow[16 * b] = (dz || rowA) ? 0.f : x.x;
+              if (actB) orow[P.out_ld + 16 * b] = (dz || rowB) ? 0.f : x.y;
+            }
           }
         }
       }
@@ -903,22 +920,35 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
 
 // ------------------------------------------------------------------------------------------------
 // MFCC as a second kernel: ceps = (log-mel @ DCT) * lifter  (ta: compliance/kaldi.py:648-666,786-796).
-// The in-kernel DCT epilogue of fbank_kernel re-reads the 80x40 matrix from shared memory for every frame pair and
-// drops the fbank kernel to 2 CTAs/SM; when no statistics are needed (cmvn none / global apply) it is ~3x faster to let
-// fbank_kernel write the log-mels to a workspace and run this register-tiled FP32 GEMM: one thread per frame, 40
-// accumulators in registers, the DCT matrix broadcast from shared memory, rows staged through shared memory so that
-// global loads and stores stay coalesced.
+// The in-kernel DCT epilogue of fbank_kernel re-reads the 80x40 matrix from shared memory for every frame pair (+65 %
+// shared-memory wavefronts on a kernel that is bound by exactly that pipe); when no statistics are needed (cmvn none /
+// global apply) fbank_kernel writes the log-mels to a tile-blocked workspace (FbankParams::ws_blocked) and this FP32
+// GEMM [rows x n_mels] . [n_mels x n_ceps] finishes the job.
+//   * a warp works on up to 4 tiles (64 frames) at a time: lane l owns frame l % 16 of each of them and the column
+//     half l / 16, i.e. a register tile of 4 rows x 20 columns (80 accumulators, packed FFMA2; 16 warps per SM).  A
+//     DCT-row load is one 16-byte address per half-warp (5 LDS.128 feed 40 FFMA2), so the FMA pipe is the limit;
+//   * the log-mels arrive through a private 4-stage cp.async ring (16 B per row and stage, 3 stages in flight).  In the
+//     blocked layout the 16 lanes of a half-warp copy 256 contiguous bytes per row and stage (a row-major workspace
+//     cost 28 shared-memory wavefronts per cp.async instruction instead of 4); every thread only reads what it copied
+//     itself, so nothing is synchronised after the table load;
+//   * tiles are dealt out evenly: every warp gets n_tiles / n_warps consecutive tiles, give or take one (a fixed 4-tile
+//     unit would leave 1.35 units per warp on cfg3, i.e. two rounds where 1.35 are needed) and takes them 4, 2 and 1
+//     at a time.
+// Summation order is m = 0..n_mels-1 with fused multiply-adds, the same as a scalar loop.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDctRows = 128;            // frames per CTA pass = 8 tiles
-constexpr int kDctMaxCeps = 40;          // accumulators per thread (n_ceps <= 40 takes this path)
+constexpr int kDctThreads = 128;
+constexpr int kDctMaxTiles = 4;          // tiles (rows per thread) per pass
+constexpr int kDctStages = 4;            // cp.async ring depth
+constexpr int kDctMaxCeps = 40;          // n_ceps <= 40 takes this path
+constexpr int kDctCols = kDctMaxCeps / 2;   // accumulator columns per thread (the other half lives 16 lanes away)
 
 struct DctParams {
-  const float* logmel;      // workspace [rows][n_mels], same row numbering as out
+  const float* logmel;      // workspace [n_tiles][n_mels / 4][16][4]
   float* out;
   long long out_ld;
   const Tile* tiles;
   int n_tiles;
-  int n_mels, n_ceps;
+  int n_mels, n_ceps;       // n_mels % 4 == 0
   const float* dct;         // [n_mels][n_ceps] device copy
   const float* lifter;      // [n_ceps]
   const int* masks;
@@ -927,18 +957,118 @@ struct DctParams {
   const double* stats_in;   // [2*n_ceps+1] (mode 2)
 };
 
-__global__ void __launch_bounds__(kDctRows) mfcc_dct_kernel(const __grid_constant__ DctParams P) {
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// One pass: this thread's frame (row g) of TM consecutive tiles, columns c0 .. c0+19.  `ring` is the thread's slot of
+// stage 0 / row 0; stage s, row i lives at ring[(s * kDctMaxTiles + i) * kDctThreads].
+template <int TM>
+__device__ __forceinline__ void dct_pass(const DctParams& P, int tile0, int g, int c0, const float* s_dct,
+                                         const float* s_lift, const float2* s_norm, float4* ring, bool vec_out) {
+  const int nm = P.n_mels, nc = P.n_ceps;
+  const int nsteps = nm >> 2;
+  const float* src = P.logmel + static_cast<long long>(tile0) * (kTileFrames * nm) + g * 4;   // + i * 16 nm + s * 64
+
+  f2 acc[TM][kDctCols / 2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < kDctCols / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  s_dct += c0;                                          // this thread's column half
+
+  auto issue = [&](int s) {
+    if (s < nsteps) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+        cp_async16(ring + ((s % kDctStages) * kDctMaxTiles + i) * kDctThreads, src + i * (kTileFrames * nm) + s * 64);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kDctStages - 1; ++s) issue(s);
+#pragma unroll 1
+  for (int s = 0; s < nsteps; ++s) {
+    issue(s + kDctStages - 1);
+    cp_async_wait<kDctStages - 1>();                    // step s has landed (only this thread reads it)
+    float4 cur[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) cur[i] = ring[((s % kDctStages) * kDctMaxTiles + i) * kDctThreads];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4* d4 = reinterpret_cast<const float4*>(s_dct + (4 * s + kk) * kDctMaxCeps);
+      f2 l[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) l[i] = bc(kk == 0 ? cur[i].x : kk == 1 ? cur[i].y : kk == 2 ? cur[i].z : cur[i].w);
+#pragma unroll
+      for (int j = 0; j < kDctCols / 4; ++j) {
+        const float4 d = d4[j];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          acc[i][2 * j] = fma2(l[i], make_float2(d.x, d.y), acc[i][2 * j]);
+          acc[i][2 * j + 1] = fma2(l[i], make_float2(d.z, d.w), acc[i][2 * j + 1]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // lifter, global CMVN, SpecAugment zero-fill, store
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const Tile tl = P.tiles[tile0 + i];
+    if (g >= tl.nframes) continue;                      // short last tile of an utterance / zero-fill tile
+    const int tf = tl.t0 + g;
+    const int* mk = P.masks + static_cast<long long>(tl.utt) * P.n_masks * 4;
+    unsigned cm = 0u;                                   // bit k: column c0 + k is zero-filled (time or frequency mask)
+    for (int qm = 0; qm < P.n_masks; ++qm) {
+      if (tf >= mk[4 * qm] && tf < mk[4 * qm + 1]) cm = 0xffffffffu;
+      const int lo = max(mk[4 * qm + 2] - c0, 0), hi = min(mk[4 * qm + 3] - c0, kDctCols);
+      if (hi > lo) cm |= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+    }
+    float* o = P.out + (tl.out_row + g) * P.out_ld + c0;
+#pragma unroll
+    for (int j = 0; j < kDctCols / 4; ++j) {
+      float x[4] = {acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + 4 * j + e;
+        float v = __fmul_rn(x[e], s_lift[c]);
+        if (P.mode == 2) v = (v - s_norm[c].x) * s_norm[c].y;
+        x[e] = ((cm >> (4 * j + e)) & 1u) ? 0.f : v;
+      }
+      if (vec_out) {
+        if (c0 + 4 * j < nc) *reinterpret_cast<float4*>(o + 4 * j) = make_float4(x[0], x[1], x[2], x[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c0 + 4 * j + e < nc) o[4 * j + e] = x[e];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kDctThreads, 4) mfcc_dct_kernel(const __grid_constant__ DctParams P) {
   extern __shared__ __align__(16) float dsm[];
   const int nm = P.n_mels, nc = P.n_ceps;
-  const int in_stride = nm + 1;                         // conflict-free row reads
-  float* s_in = dsm;                                    // [kDctRows][nm + 1], reused as [kDctRows][nc] for the outputs
-  float* s_dct = s_in + kDctRows * in_stride;           // [nm][kDctMaxCeps] zero padded
+  float4* s_ring = reinterpret_cast<float4*>(dsm);      // [kDctStages][kDctMaxTiles][kDctThreads] float4
+  float* s_dct = dsm + kDctStages * kDctMaxTiles * kDctThreads * 4;   // [nm][kDctMaxCeps] zero padded
   float* s_lift = s_dct + nm * kDctMaxCeps;             // [kDctMaxCeps]
   float2* s_norm = reinterpret_cast<float2*>(s_lift + kDctMaxCeps);   // [kDctMaxCeps] (mean, inv)
   const int tid = threadIdx.x;
-  for (int i = tid; i < nm * kDctMaxCeps; i += kDctRows) {
-    const int m = i / kDctMaxCeps, c = i - m * kDctMaxCeps;
-    s_dct[i] = c < nc ? P.dct[m * nc + c] : 0.f;
+  if (nc == kDctMaxCeps && (reinterpret_cast<uintptr_t>(P.dct) & 15) == 0) {
+    for (int i = tid; i < nm * (kDctMaxCeps / 4); i += kDctThreads)
+      reinterpret_cast<float4*>(s_dct)[i] = __ldg(reinterpret_cast<const float4*>(P.dct) + i);
+  } else {
+    for (int i = tid; i < nm * kDctMaxCeps; i += kDctThreads) {
+      const int m = i / kDctMaxCeps, c = i - m * kDctMaxCeps;
+      s_dct[i] = c < nc ? P.dct[m * nc + c] : 0.f;
+    }
   }
   if (tid < kDctMaxCeps) {
     s_lift[tid] = tid < nc ? P.lifter[tid] : 0.f;
@@ -953,87 +1083,43 @@ __global__ void __launch_bounds__(kDctRows) mfcc_dct_kernel(const __grid_constan
     }
     s_norm[tid] = make_float2(mean, inv);
   }
-  const int groups = (P.n_tiles + 7) / 8;
-  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-    __syncthreads();                                    // previous pass's stores out of s_in are done; tables visible
-    const int lt = tid >> 4, lr = tid & 15;             // my tile of the group, my row in it
-    const int tix = g * 8 + lt;
-    Tile tl;
-    tl.nframes = -1;
-    if (tix < P.n_tiles) tl = P.tiles[tix];
-    // stage: every tile's rows are contiguous in the workspace (ld = n_mels)
-    for (int q = 0; q < 8; ++q) {
-      const int tq = g * 8 + q;
-      if (tq >= P.n_tiles) break;
-      const Tile t2 = P.tiles[tq];
-      if (t2.nframes <= 0) continue;
-      const float* src = P.logmel + t2.out_row * nm;
-      const int total = t2.nframes * nm;
-      for (int i = tid; i < total; i += kDctRows) {
-        const int r = i / nm, m = i - r * nm;
-        s_in[(q * 16 + r) * in_stride + m] = src[i];
-      }
-    }
-    __syncthreads();
-    float acc[kDctMaxCeps];
-#pragma unroll
-    for (int c = 0; c < kDctMaxCeps; ++c) acc[c] = 0.f;
-    const bool live = tl.nframes > 0 && lr < tl.nframes;
-    if (live) {
-      const float* row = s_in + tid * in_stride;
-      for (int m = 0; m < nm; ++m) {
-        const float l = row[m];
-        const float4* d4 = reinterpret_cast<const float4*>(s_dct + m * kDctMaxCeps);
-#pragma unroll
-        for (int c4 = 0; c4 < kDctMaxCeps / 4; ++c4) {
-          const float4 d = d4[c4];
-          acc[4 * c4 + 0] = fmaf(l, d.x, acc[4 * c4 + 0]);
-          acc[4 * c4 + 1] = fmaf(l, d.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(l, d.z, acc[4 * c4 + 2]);
-          acc[4 * c4 + 3] = fmaf(l, d.w, acc[4 * c4 + 3]);
-        }
-      }
-    }
-    __syncthreads();                                    // all rows consumed: s_in becomes the output staging area
-    if (live) {
-      const int tf = tl.t0 + lr;
-      bool zr = false;
-      for (int q = 0; q < P.n_masks; ++q) {
-        const int* mk = P.masks + (static_cast<long long>(tl.utt) * P.n_masks + q) * 4;
-        zr |= (tf >= mk[0] && tf < mk[1]);
-      }
-#pragma unroll
-      for (int c = 0; c < kDctMaxCeps; ++c) {
-        if (c < nc) {
-          float x = __fmul_rn(acc[c], s_lift[c]);
-          if (P.mode == 2) x = (x - s_norm[c].x) * s_norm[c].y;
-          bool z = zr;
-          for (int q = 0; q < P.n_masks; ++q) {
-            const int* mk = P.masks + (static_cast<long long>(tl.utt) * P.n_masks + q) * 4;
-            z |= (c >= mk[2] && c < mk[3]);
-          }
-          s_in[tid * nc + c] = z ? 0.f : x;
-        }
-      }
-    }
-    __syncthreads();
-    for (int q = 0; q < 8; ++q) {
-      const int tq = g * 8 + q;
-      if (tq >= P.n_tiles) break;
-      const Tile t2 = P.tiles[tq];
-      if (t2.nframes > 0) {
-        for (int i = tid; i < t2.nframes * nc; i += kDctRows) {
-          const int r = i / nc, c = i - r * nc;
-          P.out[(t2.out_row + r) * P.out_ld + c] = s_in[(q * 16 + r) * nc + c];
-        }
-      } else if (t2.nframes == 0) {                     // zero-fill tile: pad_sequence's zeros
-        for (int i = tid; i < t2.aux * nc; i += kDctRows) {
-          const int r = i / nc, c = i - r * nc;
-          P.out[(t2.out_row + r) * P.out_ld + c] = 0.f;
-        }
+  __syncthreads();
+
+  const bool vec_out = (nc % 4 == 0) && (P.out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
+  const long long gtid = static_cast<long long>(blockIdx.x) * kDctThreads + tid;
+  const long long nthreads = static_cast<long long>(gridDim.x) * kDctThreads;
+
+  // zero-fill tiles (pad_sequence's zeros): 4 threads per tile
+  for (long long q = gtid; q < static_cast<long long>(P.n_tiles) * 4; q += nthreads) {
+    const Tile tl = P.tiles[q >> 2];
+    if (tl.nframes != 0) continue;
+    for (int r = static_cast<int>(q & 3); r < tl.aux; r += 4) {
+      float* o = P.out + (tl.out_row + r) * P.out_ld;
+      if (vec_out) {
+        for (int c = 0; c < nc; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int c = 0; c < nc; ++c) o[c] = 0.f;
       }
     }
   }
+
+  // frame tiles: the same number of consecutive tiles for every warp, taken 4 / 2 / 1 at a time
+  const int lane = tid & 31;
+  const int g = lane & 15, c0 = (lane >> 4) * kDctCols;
+  const long long warp = gtid >> 5, nwarps = nthreads >> 5;
+  const long long base = P.n_tiles / nwarps, rem = P.n_tiles - base * nwarps;   // the first `rem` warps take one more
+  long long t = warp * base + (warp < rem ? warp : rem);
+  const long long t_end = t + base + (warp < rem ? 1 : 0);
+  float4* ring = s_ring + tid;
+  while (t + 4 <= t_end) {
+    dct_pass<4>(P, static_cast<int>(t), g, c0, s_dct, s_lift, s_norm, ring, vec_out);
+    t += 4;
+  }
+  if (t + 2 <= t_end) {
+    dct_pass<2>(P, static_cast<int>(t), g, c0, s_dct, s_lift, s_norm, ring, vec_out);
+    t += 2;
+  }
+  if (t < t_end) dct_pass<1>(P, static_cast<int>(t), g, c0, s_dct, s_lift, s_norm, ring, vec_out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,7 +12,10 @@ import torch
 import speech_lid_b200 as lid
 
 
-def run(name, fe, B, N, steps=100, warmup=10, dtype=torch.float32, **kw):
+def run(name, fe, B, N, steps=None, warmup=10, dtype=torch.float32, **kw):
+    if ONLY and ONLY not in name:
+        return
+    steps = steps or STEPS
     dev = fe.device
     plan = fe.make_plan([N] * B, padded=True)
     g = torch.Generator(device=dev).manual_seed(1)
@@ -35,6 +38,10 @@ def run(name, fe, B, N, steps=100, warmup=10, dtype=torch.float32, **kw):
     audio_s = B * N / 16000.0
     print(json.dumps({"config": name, "utterances": B, "samples": N, "frames": plan.total_frames, "ms_per_step": round(ms, 5),
                       "audio_s_per_s": round(audio_s / (ms * 1e-3), 1), "rotating_sets": nbuf}), flush=True)
+
+
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""      # substring filter on the config name, e.g. "cfg3"
+STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 
 
 def main():
