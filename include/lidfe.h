@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LIDFE_ABI_VERSION 2
+#define LIDFE_ABI_VERSION 3
 
 /* error codes (negative) */
 #define LIDFE_OK 0
@@ -117,12 +117,18 @@ long long lidfe_num_frames(long long n_samples, const lidfe_config* cfg);
 int lidfe_out_dim(lidfe_handle h);
 
 /*
- * Host-only helper (no device needed): how lidfe_create sparsifies a dense (n_mels x 257) bank.  For every mel bin
- * its first non-zero FFT bin, its tap count, and the (possibly earlier) first tap the kernel reads so that the 16
- * lanes of a band hit 16 distinct shared-memory bank pairs; band_taps_out[5] = tap steps per band of 16 bins.
+ * Host-only helpers (no device needed): how lidfe_create turns the dense (n_mels x 257) bank into the kernel's
+ * segment plan.  The banks on this path (Kaldi / HTK triangles) overlap only with their neighbours, so lane m % 16 of
+ * band m / 16 walks the FFT bins between the centres of filters m and m+1 once, with two weights per bin (its own
+ * down-slope, the next filter's up-slope; slot 0 also takes the bins below the first centre).  Outputs, per slot m:
+ * first bin and length of that run, and the (possibly earlier) first power bin the lane reads so that the 16 lanes of
+ * a band hit 16 distinct shared-memory bank pairs; band_taps_out[5] = steps per band of 16 slots.
+ * LIDFE_E_MELBANK when a bin feeds more than two filters, or two that are not adjacent, or a row is empty.
+ * lidfe_mel_plan_expand replays the plan into dense_out[n_mels * 257]: it must equal the input bank bit for bit.
  */
 int lidfe_mel_plan(int n_mels, const float* melbank_host, int* first_bin_out, int* num_taps_out, int* start_out,
                    int* band_taps_out);
+int lidfe_mel_plan_expand(int n_mels, const float* melbank_host, float* dense_out);
 
 /* -- plan: the segment-offset table of one batch -------------------------------------------------- */
 

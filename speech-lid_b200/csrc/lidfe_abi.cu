@@ -92,21 +92,28 @@ static size_t smem_for(const lidfe_config& c, int total_taps) {
   const size_t base = (c.in_dtype == LIDFE_IN_I16)
                           ? (mf ? SmemLayout<short, true>::off_melw : SmemLayout<short, false>::off_melw)
                           : (mf ? SmemLayout<float, true>::off_melw : SmemLayout<float, false>::off_melw);
-  size_t extra = static_cast<size_t>(total_taps) * 16;
+  size_t extra = static_cast<size_t>(total_taps) * 32;   // (wa, wb) per step and lane
   if (c.n_ceps > 0) extra += ((static_cast<size_t>(c.n_mels) * c.n_ceps + 3) & ~static_cast<size_t>(3)) + ((c.n_ceps + 3) & ~3);
   return base + extra * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Mel tap placement.  In the kernel the 16 lanes of a half-warp read, at tap step i, the power pairs P[start_t + i]
-// (8 bytes each) of "their" filter of the band.  Two lanes collide in shared memory when their starts differ but are
-// congruent mod 16 (same bank pair, different address).  A filter with cnt taps can start anywhere in
-// [k0 + cnt - T, k0] when the band runs T >= cnt steps (leading / trailing weights are zero), so for each band we look
-// for the smallest T and a set of starts without such collisions (lanes sharing the SAME start are a broadcast).
-// Small bounded search: residue classes are claimed by a start value; a lane may evict a class if every evicted lane
-// can be re-seated (depth <= 3).
+// Mel plan.  The banks the reference uses (Kaldi and HTK triangles, ta: compliance/kaldi.py:436-511,
+// functional/functional.py melscale_fbanks) overlap only with their neighbours: the FFT bins between the centres of
+// filters j and j+1 ("segment j+1") carry the down-slope of filter j and the up-slope of filter j+1 and nothing else.
+// So instead of letting every filter gather its whole support (every power bin read twice), slot j = lane j % 16 of
+// band j / 16 walks segment j+1 once with TWO weights per bin -- wa into its own filter j, wb into a carry that the
+// next lane adds to filter j+1 (one shuffle per band).  Segment 0 (bins below the first centre) is prepended to slot
+// 0's run with wb = 0.  257 power bins are read per frame instead of 501 (+ padding), in ~22 steps instead of 41.
+//
+// Tap placement.  At step i the 16 lanes of a half-warp read the power pairs P[start_t + i] (8 bytes each).  Two lanes
+// collide in shared memory when their starts differ but are congruent mod 16 (same bank pair, different address).  A
+// run of len bins can start anywhere in [first + len - T, first] when the band runs T >= len steps (leading / trailing
+// weights are zero), so for each band we look for the smallest T for which the lanes can be matched to 16 distinct
+// residue classes (an exact bipartite matching), or, failing that, share classes between lanes that read the very same
+// address (a bounded search: a lane may evict a class if every evicted lane can be re-seated, depth <= 3).
 // ------------------------------------------------------------------------------------------------------------------
-struct TapPlacer {
+struct TapSharer {   // bounded search that lets lanes with the SAME start share a residue class (a broadcast)
   int lo[16], hi[16], choice[16], n;
   int cls_start[16];                 // start value owning residue class r, or -1
   std::vector<int> cls_lanes[16];
@@ -150,34 +157,141 @@ struct TapPlacer {
   }
 };
 
-// starts[m], band_taps[b] for all bands; falls back to start = k0 (correct, bank-conflicted) if the search fails
-static void place_taps(int n_mels, const int* k0, const int* cnt, int* starts, int* band_taps) {
+struct TapPlacer {   // bipartite matching lanes -> residue classes (Kuhn's augmenting paths; 16 x 16, so exact and tiny)
+  int lo[16], hi[16], choice[16], n;
+  int owner[16];                     // lane holding residue class r, or -1
+
+  bool seat(int l, unsigned& visited) {
+    const int span = hi[l] - lo[l] + 1;
+    for (int d = 0; d < span && d < 16; ++d) {          // latest start first: fewest leading zero weights
+      const int s = hi[l] - d, r = s & 15;
+      if (visited & (1u << r)) continue;
+      visited |= 1u << r;
+      if (owner[r] < 0 || seat(owner[r], visited)) {
+        owner[r] = l;
+        choice[l] = s;
+        return true;
+      }
+    }
+    return false;
+  }
+  bool run() {
+    for (int r = 0; r < 16; ++r) owner[r] = -1;
+    for (int l = 0; l < n; ++l) {
+      unsigned visited = 0u;
+      if (!seat(l, visited)) return false;
+    }
+    return true;
+  }
+};
+
+struct MelPlan {
+  int first[kMaxMels], len[kMaxMels];   // slot m's run of FFT bins (segment m+1; slot 0 also takes segment 0)
+  int start[kMaxMels];                  // first power bin the lane reads (<= first[m])
+  int band_steps[kBands];
+  int total_steps;
+  std::vector<float> w;                 // [total_steps][16 lanes][2] = (wa, wb), bands back to back, unscaled
+};
+
+// starts and steps per band; falls back to start = first (correct, bank-conflicted) if the search fails
+static void place_taps(int n_mels, MelPlan& mp) {
   for (int b = 0; b < kBands; ++b) {
-    band_taps[b] = 0;
+    mp.band_steps[b] = 0;
     const int m0 = 16 * b, m1 = (n_mels < m0 + 16) ? n_mels : m0 + 16;
     if (m1 <= m0) continue;
-    int mx = 0;
-    for (int m = m0; m < m1; ++m) mx = cnt[m] > mx ? cnt[m] : mx;
+    int mx = 1;
+    for (int m = m0; m < m1; ++m) mx = mp.len[m] > mx ? mp.len[m] : mx;
     bool done = false;
     for (int T = mx; T <= mx + 8 && !done; ++T) {
       TapPlacer tp;
       tp.n = m1 - m0;
       for (int m = m0; m < m1; ++m) {
-        const int l = k0[m] + cnt[m] - T;
-        tp.lo[m - m0] = l > 0 ? l : 0;
-        tp.hi[m - m0] = k0[m];
+        int lo, hi;
+        if (mp.len[m] == 0) {            // nothing to read: any start inside the power array will do
+          lo = 0;
+          hi = kBins - T;
+        } else {
+          lo = mp.first[m] + mp.len[m] - T;
+          hi = mp.first[m];
+          if (hi > kBins - T && kBins - T >= lo) hi = kBins - T;   // stay inside the 257 bins when the slack allows
+        }
+        tp.lo[m - m0] = lo > 0 ? lo : 0;
+        tp.hi[m - m0] = hi > 0 ? hi : 0;
       }
-      if (tp.run()) {
-        for (int m = m0; m < m1; ++m) starts[m] = tp.choice[m - m0];
-        band_taps[b] = T;
+      TapSharer ts;
+      ts.n = tp.n;
+      for (int l = 0; l < tp.n; ++l) { ts.lo[l] = tp.lo[l]; ts.hi[l] = tp.hi[l]; }
+      const int* choice = nullptr;
+      if (tp.run()) choice = tp.choice;
+      else if (ts.run()) choice = ts.choice;
+      if (choice) {
+        for (int m = m0; m < m1; ++m) mp.start[m] = choice[m - m0];
+        mp.band_steps[b] = T;
         done = true;
       }
     }
     if (!done) {
-      for (int m = m0; m < m1; ++m) starts[m] = k0[m];
-      band_taps[b] = mx;
+      for (int m = m0; m < m1; ++m) mp.start[m] = mp.first[m];
+      mp.band_steps[b] = mx;
     }
   }
+}
+
+// dense (n_mels x 257) bank -> segment plan; LIDFE_E_MELBANK unless every bin feeds at most two ADJACENT filters and
+// the plan reproduces the bank exactly
+static int build_mel_plan(int n_mels, const float* bank, MelPlan& mp) {
+  auto at = [&](int f, int k) { return bank[static_cast<size_t>(f) * kBins + k]; };
+  std::vector<int> peak(n_mels, -1), seg(kBins, -1);
+  for (int f = 0; f < n_mels; ++f) {
+    float best = 0.f;
+    for (int k = 0; k < kBins; ++k)
+      if (at(f, k) > best) { best = at(f, k); peak[f] = k; }
+    if (peak[f] < 0) return LIDFE_E_MELBANK;               // empty (or non-positive) row
+  }
+  for (int k = 0; k < kBins; ++k) {
+    int lo = -1, n = 0, hi = -1;
+    for (int f = 0; f < n_mels; ++f)
+      if (at(f, k) != 0.f) { if (lo < 0) lo = f; hi = f; ++n; }
+    if (n == 0) continue;
+    if (n > 2 || hi - lo + 1 != n) return LIDFE_E_MELBANK;
+    seg[k] = (n == 2) ? hi : (k <= peak[lo] ? lo : lo + 1);   // a lone weight: up-slope left of the peak, down-slope right
+  }
+  for (int m = 0; m < kMaxMels; ++m) mp.first[m] = mp.len[m] = mp.start[m] = 0;
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1, cnt = 0;
+    for (int k = 0; k < kBins; ++k)
+      if (seg[k] == m + 1 || (m == 0 && seg[k] == 0)) { if (first < 0) first = k; last = k; ++cnt; }
+    if (cnt == 0) continue;
+    if (last - first + 1 != cnt || cnt > 64) return LIDFE_E_MELBANK;   // the run must be contiguous
+    mp.first[m] = first;
+    mp.len[m] = cnt;
+  }
+  place_taps(n_mels, mp);
+  mp.total_steps = 0;
+  for (int b = 0; b < kBands; ++b) mp.total_steps += mp.band_steps[b];
+  mp.w.assign(static_cast<size_t>(mp.total_steps > 0 ? mp.total_steps : 1) * 32, 0.f);
+  std::vector<float> recon(static_cast<size_t>(n_mels) * kBins, 0.f);
+  int off = 0;
+  for (int b = 0; b < kBands; ++b) {
+    for (int t = 0; t < 16; ++t) {
+      const int m = t + 16 * b;
+      if (m >= n_mels) continue;
+      for (int i = 0; i < mp.len[m]; ++i) {
+        const int k = mp.first[m] + i;
+        const float wa = at(m, k);
+        const float wb = (m + 1 < n_mels && seg[k] == m + 1) ? at(m + 1, k) : 0.f;
+        const size_t e = ((static_cast<size_t>(off) + (mp.first[m] - mp.start[m]) + i) * 16 + t) * 2;
+        mp.w[e] = wa;
+        mp.w[e + 1] = wb;
+        recon[static_cast<size_t>(m) * kBins + k] += wa;
+        if (m + 1 < n_mels) recon[static_cast<size_t>(m + 1) * kBins + k] += wb;
+      }
+    }
+    off += mp.band_steps[b];
+  }
+  for (size_t i = 0; i < recon.size(); ++i)
+    if (recon[i] != bank[i]) return LIDFE_E_MELBANK;
+  return LIDFE_OK;
 }
 
 extern "C" {
@@ -218,24 +332,46 @@ int lidfe_mel_plan(int n_mels, const float* melbank_host, int* first_bin_out, in
                    int* band_taps_out) {
   if (!melbank_host || !first_bin_out || !num_taps_out || !start_out || !band_taps_out) return LIDFE_E_NULL;
   if (n_mels < 4 || n_mels > kMaxMels) return LIDFE_E_CONFIG;
-  std::vector<int> k0(kMaxMels, 0), cnt(kMaxMels, 0), starts(kMaxMels, 0);
+  MelPlan mp;
+  const int rc = build_mel_plan(n_mels, melbank_host, mp);
+  if (rc != LIDFE_OK) return rc;
   for (int m = 0; m < n_mels; ++m) {
-    const float* row = melbank_host + static_cast<size_t>(m) * kBins;
-    int first = -1, last = -1;
-    for (int k = 0; k < kBins; ++k)
-      if (row[k] != 0.f) {
-        if (first < 0) first = k;
-        last = k;
-      }
-    if (first < 0 || last - first + 1 > 64) return LIDFE_E_MELBANK;
-    k0[m] = first;
-    cnt[m] = last - first + 1;
+    first_bin_out[m] = mp.first[m];
+    num_taps_out[m] = mp.len[m];
+    start_out[m] = mp.start[m];
   }
-  place_taps(n_mels, k0.data(), cnt.data(), starts.data(), band_taps_out);
-  for (int m = 0; m < n_mels; ++m) {
-    first_bin_out[m] = k0[m];
-    num_taps_out[m] = cnt[m];
-    start_out[m] = starts[m];
+  for (int b = 0; b < kBands; ++b) band_taps_out[b] = mp.band_steps[b];
+  return LIDFE_OK;
+}
+
+int lidfe_mel_plan_expand(int n_mels, const float* melbank_host, float* dense_out) {
+  if (!melbank_host || !dense_out) return LIDFE_E_NULL;
+  if (n_mels < 4 || n_mels > kMaxMels) return LIDFE_E_CONFIG;
+  MelPlan mp;
+  const int rc = build_mel_plan(n_mels, melbank_host, mp);
+  if (rc != LIDFE_OK) return rc;
+  // replay the kernel's loop: slot m adds wa * P[start + i] to filter m and wb * P[start + i] to filter m + 1
+  for (size_t i = 0; i < static_cast<size_t>(n_mels) * kBins; ++i) dense_out[i] = 0.f;
+  int off = 0;
+  for (int b = 0; b < kBands; ++b) {
+    for (int t = 0; t < 16; ++t) {
+      const int m = t + 16 * b;
+      if (m >= n_mels) continue;
+      for (int i = 0; i < mp.band_steps[b]; ++i) {
+        const int k = mp.start[m] + i;
+        const float wa = mp.w[((static_cast<size_t>(off) + i) * 16 + t) * 2], wb = mp.w[((static_cast<size_t>(off) + i) * 16 + t) * 2 + 1];
+        if (k >= kBins) {
+          if (wa != 0.f || wb != 0.f) return LIDFE_E_MELBANK;
+          continue;
+        }
+        dense_out[static_cast<size_t>(m) * kBins + k] += wa;
+        if (wb != 0.f) {
+          if (m + 1 >= n_mels) return LIDFE_E_MELBANK;
+          dense_out[static_cast<size_t>(m + 1) * kBins + k] += wb;
+        }
+      }
+    }
+    off += mp.band_steps[b];
   }
   return LIDFE_OK;
 }
@@ -250,7 +386,8 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
       !(cfg->preemph >= 0.f && cfg->preemph <= 1.f) ||
       (cfg->framing != LIDFE_FRAMING_KALDI && cfg->framing != LIDFE_FRAMING_CENTER) || cfg->pad < 0 ||
       cfg->pad > 4096 || (cfg->framing == LIDFE_FRAMING_KALDI && cfg->pad != 0) ||
-      (cfg->log_kind != LIDFE_LOG_NATURAL && cfg->log_kind != LIDFE_LOG_DB10) || !(cfg->log_floor > 0.f))
+      (cfg->log_kind != LIDFE_LOG_NATURAL && cfg->log_kind != LIDFE_LOG_DB10) ||
+      !(cfg->log_floor >= 1.17549435e-38f))   // a normal float: the kernel's log takes no denormals
     return LIDFE_E_CONFIG;
   if (cfg->n_ceps > 0 && !dct_host) return LIDFE_E_NULL;
 
@@ -260,56 +397,25 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   c->cfg = *cfg;
   c->n_out = cfg->n_ceps > 0 ? cfg->n_ceps : cfg->n_mels;
 
-  // ---- sparsify the dense bank: per mel bin the first non-zero FFT bin and a contiguous run of taps
-  std::vector<int> k0(kMaxMels, 0), cnt(kMaxMels, 0);
-  int maxt = 1;
-  for (int m = 0; m < cfg->n_mels; ++m) {
-    const float* row = melbank_host + static_cast<size_t>(m) * kBins;
-    int first = -1, last = -1;
-    for (int k = 0; k < kBins; ++k)
-      if (row[k] != 0.f) {
-        if (first < 0) first = k;
-        last = k;
-      }
-    if (first < 0) {
+  // ---- dense bank -> segment plan (see build_mel_plan).  The kernel leaves the power bins scaled by 4 (it skips the
+  //      1/2 of the real-FFT split), so the weights carry the exact factor 1/4.
+  MelPlan mp;
+  {
+    const int rc = build_mel_plan(cfg->n_mels, melbank_host, mp);
+    if (rc != LIDFE_OK) {
       delete c;
-      return LIDFE_E_MELBANK;
+      return rc;
     }
-    k0[m] = first;
-    cnt[m] = last - first + 1;
-    if (cnt[m] > 64) {
-      delete c;
-      return LIDFE_E_MELBANK;
-    }
-    if (cnt[m] > maxt) maxt = cnt[m];
   }
-  (void)maxt;
-  // per band b (output dims t + 16 b): [taps_b][16] weights, bands back to back, filter m's taps starting at
-  // starts[m] <= k0[m] (see place_taps).  The kernel leaves the power bins scaled by 4 (it skips the 1/2 of the
-  // real-FFT split), so the weights carry the exact factor 1/4.
-  std::vector<int> starts(kMaxMels, 0);
-  place_taps(cfg->n_mels, k0.data(), cnt.data(), starts.data(), c->band_taps);
-  int total_taps = 0;
+  const int total_taps = mp.total_steps;
   c->std_mel = 1;
   for (int b = 0; b < kBands; ++b) {
+    c->band_taps[b] = mp.band_steps[b];
     if (c->band_taps[b] != std_taps(b)) c->std_mel = 0;
-    total_taps += c->band_taps[b];
   }
-  std::vector<float> melw(static_cast<size_t>(total_taps > 0 ? total_taps : 1) * 16, 0.f);
-  {
-    int off = 0;
-    for (int b = 0; b < kBands; ++b) {
-      for (int t = 0; t < 16; ++t) {
-        const int m = t + 16 * b;
-        if (m >= cfg->n_mels) continue;
-        for (int i = 0; i < cnt[m]; ++i)
-          melw[(static_cast<size_t>(off) + (k0[m] - starts[m]) + i) * 16 + t] =
-              0.25f * melbank_host[static_cast<size_t>(m) * kBins + k0[m] + i];
-      }
-      off += c->band_taps[b];
-    }
-  }
-  k0 = starts;   // the kernel's per-filter first tap
+  std::vector<float> melw(mp.w);
+  for (float& v : melw) v *= 0.25f;
+  std::vector<int> k0(mp.start, mp.start + kMaxMels);   // the kernel's per-lane first power bin
 
   // ---- twiddles, rounded once from fp64
   std::vector<float2> tw1(256), tw2(128);
@@ -341,7 +447,7 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   append(tw1.data(), tw1.size() * sizeof(float2));
   append(tw2.data(), tw2.size() * sizeof(float2));
   append(k0.data(), static_cast<size_t>(kMaxMels) * sizeof(int));
-  if (total_taps > 0) append(melw.data(), static_cast<size_t>(total_taps) * 16 * sizeof(float));
+  if (total_taps > 0) append(melw.data(), static_cast<size_t>(total_taps) * 32 * sizeof(float));
   c->blob_bytes_fbank = static_cast<int>(blob.size());
   if (cfg->n_ceps > 0) {
     c->dct_off = static_cast<int>(blob.size());

@@ -44,7 +44,7 @@ constexpr int kMaxMasks = 8;
 constexpr int kTileCache = 16;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
 // taps per band of the 80-mel / 16 kHz / 512 Kaldi bank
 // (after the host shifts each filter's first tap so that the 16 lanes of a band read 16 distinct bank pairs)
-__host__ __device__ constexpr int std_taps(int b) { return b == 0 ? 3 : b == 1 ? 5 : b == 2 ? 6 : b == 3 ? 10 : 17; }
+__host__ __device__ constexpr int std_taps(int b) { return b == 0 ? 2 : b == 1 ? 2 : b == 2 ? 4 : b == 3 ? 6 : 9; }
 
 struct Tile {
   long long wav_off;    // first sample of the tile's first frame in the packed buffer
@@ -63,11 +63,11 @@ struct FbankParams {
   int n_tiles;
   // constant tables: ONE device blob laid out exactly like the kernel's shared-memory table area, so a single TMA
   // bulk copy stages it:  window[416] | tw1[16][16] float2 = W256^(K1*t) | tw2[8][16] float2 = W512^(t+16i) |
-  // mel_k0[80] int | mel_w per band [taps_b][16] (x 0.25: the power bins are left scaled by 4) |
+  // mel_k0[80] int | mel (wa, wb) pairs per band [steps_b][16] (x 0.25: the power bins are left scaled by 4) |
   // dct[n_mels][n_ceps] | lifter[n_ceps]   (each section padded to 16 bytes)
   const void* const_blob;
   int const_bytes;
-  int band_taps[kBands];    // taps per band
+  int band_taps[kBands];    // mel steps per band (segment plan, see build_mel_plan in lidfe_abi.cu)
   int n_mels, n_ceps, n_out;
   float preemph, log_floor, log_of_floor, in_scale;   // log_of_floor = the reference's log of the floor, rounded on the host
   float log_scale;          // lg2(x) * log_scale: ln 2 (natural log) or 10 log10(2) (dB)
@@ -156,6 +156,13 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ f2 bc(float s) { return make_float2(s, s); }
 __device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+// one MUFU.LG2: the argument is always above the log floor, a normal number (lidfe_create checks), so the denormal
+// pre-scaling __log2f wraps around the instruction (6 more instructions per value) is dead weight here
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // (R + iI) *= (wr + i wi), both frames at once, one scalar twiddle
 __device__ __forceinline__ void cmul2(f2& R, f2& I, float wr, float wi) {
@@ -271,7 +278,7 @@ struct SmemLayout {
   static constexpr int off_tw1 = off_window + 416 * 4;                             // [16][16] float2
   static constexpr int off_tw2 = off_tw1 + 256 * 8;                                // [8][16] float2
   static constexpr int off_k0 = off_tw2 + 128 * 8;                                 // [80] int
-  static constexpr int off_melw = off_k0 + kMaxMels * 4;                           // sum(band_taps)*16 floats, then dct, lifter
+  static constexpr int off_melw = off_k0 + kMaxMels * 4;                           // sum(band_taps)*16 float2, then dct, lifter
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
     taps[b] = kStdMel ? std_taps(b) : P.band_taps[b];
     tap_off[b + 1] = tap_off[b] + taps[b];
   }
-  float* const sm_dct = sm_melw + tap_off[kBands] * 16;
+  float* const sm_dct = sm_melw + tap_off[kBands] * 32;
   float* const sm_lifter = sm_dct + (kMfcc ? ((P.n_mels * P.n_ceps + 3) & ~3) : 0);   // sections padded to 16 B
 
   // this CTA's contiguous tile range (neighbouring tiles share their halo in L2 and their utterance's statistics)
@@ -591,21 +598,43 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
       __syncwarp();
 
       // ---- sparse triangular mel + log (ta: compliance/kaldi.py:621-633) ---------------------------
+      // Segment form: this lane walks the bins between the centres of filters d = t + 16 b and d + 1 once, with the
+      // down-slope weight of its own filter (wa) and the up-slope weight of the next one (wb); the wb sum travels one
+      // lane up (lane 15's goes to lane 0 of the next band).
+      {
+        f2 carry15 = make_float2(0.f, 0.f);                   // lane 0: what lane 15 accumulated for it in the last band
+        const int src = (lane & 16) | ((t - 1) & 15);
 #pragma unroll
-      for (int b = 0; b < kBands; ++b) {
-        f2 acc = make_float2(0.f, 0.f);
-        const f2* pp = my_P + k0[b];
-        const float* wp = sm_melw + tap_off[b] * 16 + t;
-        if (kStdMel) {
+        for (int b = 0; b < kBands; ++b) {
+          f2 own = make_float2(0.f, 0.f), nxt = make_float2(0.f, 0.f);
+          const f2* pp = my_P + k0[b];
+          const float2* wp = reinterpret_cast<const float2*>(sm_melw) + tap_off[b] * 16 + t;
+          if (kStdMel) {
 #pragma unroll
-          for (int i = 0; i < std_taps(b); ++i) acc = fma2(pp[i], bc(wp[i * 16]), acc);
-        } else {
+            for (int i = 0; i < std_taps(b); ++i) {
+              const f2 p = pp[i];
+              const float2 w = wp[i * 16];
+              own = fma2(p, bc(w.x), own);
+              nxt = fma2(p, bc(w.y), nxt);
+            }
+          } else {
 #pragma unroll 2
-          for (int i = 0; i < taps[b]; ++i) acc = fma2(pp[i], bc(wp[i * 16]), acc);
+            for (int i = 0; i < taps[b]; ++i) {
+              const f2 p = pp[i];
+              const float2 w = wp[i * 16];
+              own = fma2(p, bc(w.x), own);
+              nxt = fma2(p, bc(w.y), nxt);
+            }
+          }
+          f2 got;
+          got.x = __shfl_sync(0xffffffffu, nxt.x, src);
+          got.y = __shfl_sync(0xffffffffu, nxt.y, src);
+          const f2 acc = add2(own, t == 0 ? carry15 : got);
+          carry15 = got;
+          // lg2.approx (abs. error ~1e-7 in the log) except at the floor, where the reference's log(eps) is returned exactly
+          val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.x) * P.log_scale,
+                               acc.y <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.y) * P.log_scale);
         }
-        // lg2.approx (abs. error ~1e-7 in the log) except at the floor, where the reference's log(eps) is returned exactly
-        val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : __log2f(acc.x) * P.log_scale,
-                             acc.y <= P.log_floor ? P.log_of_floor : __log2f(acc.y) * P.log_scale);
       }
 
       // ---- MFCC: DCT-II + lifter (ta: compliance/kaldi.py:648-666,786-796) --------------------------
@@ -692,10 +721,17 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
       for (int d = lane; d < n_out; d += 32) {
         const f2 p0 = *reinterpret_cast<const f2*>(v0 + 2 * d), p1 = *reinterpret_cast<const f2*>(v1 + 2 * d);
         double a1 = wacc[d], a2 = wacc[kMaxMels + d];
-        if (f0 + 0 < tl.nframes) { const double x = p0.x; a1 += x; a2 = fma(x, x, a2); }
-        if (f0 + 1 < tl.nframes) { const double x = p0.y; a1 += x; a2 = fma(x, x, a2); }
-        if (f0 + 2 < tl.nframes) { const double x = p1.x; a1 += x; a2 = fma(x, x, a2); }
-        if (f0 + 3 < tl.nframes) { const double x = p1.y; a1 += x; a2 = fma(x, x, a2); }
+        if (f0 + 3 < tl.nframes) {   // all four frames live (every tile but an utterance's last): no predicates
+          const double x0 = p0.x, x1 = p0.y, x2 = p1.x, x3 = p1.y;
+          a1 += x0; a2 = fma(x0, x0, a2);
+          a1 += x1; a2 = fma(x1, x1, a2);
+          a1 += x2; a2 = fma(x2, x2, a2);
+          a1 += x3; a2 = fma(x3, x3, a2);
+        } else {
+          if (f0 + 0 < tl.nframes) { const double x = p0.x; a1 += x; a2 = fma(x, x, a2); }
+          if (f0 + 1 < tl.nframes) { const double x = p0.y; a1 += x; a2 = fma(x, x, a2); }
+          if (f0 + 2 < tl.nframes) { const double x = p1.x; a1 += x; a2 = fma(x, x, a2); }
+        }
         wacc[d] = a1;
         wacc[kMaxMels + d] = a2;
       }

@@ -63,7 +63,7 @@ def _check_fbank(got, want, what, all_bins=False):
 
 def test_extension_is_loaded(lid):
     lib = lid.load_library()
-    assert lib.lidfe_abi_version() == 2
+    assert lib.lidfe_abi_version() == 3
     with open("/proc/self/maps") as f:
         assert "liblidfe.so" in f.read()
 

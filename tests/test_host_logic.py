@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, "liblidfe.so does not export %s" % missing
     assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
-    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 3
 
 
 def _cfg(**kw):
@@ -114,31 +114,52 @@ def test_melspec_tables_and_centered_frame_count():
 
 def test_mel_plan_is_sparse_exact_and_bank_conflict_free():
     lib = lid.load_library()
-    for n in (80, 64, 40, 23):
-        banks = tables.mel_banks(n, 512, 16000.0).contiguous()
-        k0, cnt, st = (C.c_int * 80)(), (C.c_int * 80)(), (C.c_int * 80)()
+    cases = [(n, tables.mel_banks(n, 512, 16000.0).contiguous()) for n in (80, 64, 40, 23)]
+    cases += [(n, tables.htk_mel_banks(n, 512).contiguous()) for n in (80, 64)]
+    for ci, (n, banks) in enumerate(cases):
+        first, cnt, st = (C.c_int * 80)(), (C.c_int * 80)(), (C.c_int * 80)()
         bt = (C.c_int * 5)()
-        assert lib.lidfe_mel_plan(n, banks.data_ptr(), k0, cnt, st, bt) == 0
-        taps = list(bt)
-        nz = banks > 0
+        assert lib.lidfe_mel_plan(n, banks.data_ptr(), first, cnt, st, bt) == 0
+        steps = list(bt)
+        nz = banks != 0
+        # every bin feeds at most two adjacent filters; slot m's run = the bins shared by filters m and m+1
+        # (slot 0 also takes the bins below the first centre), each non-zero bin in exactly one run
+        owner = {}
         for m in range(n):
-            idx = nz[m].nonzero().flatten()
-            assert k0[m] == int(idx[0]) and cnt[m] == int(idx[-1] - idx[0] + 1) == len(idx)   # contiguous support
             band = m // 16
-            assert st[m] <= k0[m] and st[m] + taps[band] >= k0[m] + cnt[m]
+            assert st[m] <= first[m] or cnt[m] == 0
+            assert cnt[m] == 0 or st[m] + steps[band] >= first[m] + cnt[m]
+            for k in range(first[m], first[m] + cnt[m]):
+                assert k not in owner
+                owner[k] = m
+                fs = nz[:, k].nonzero().flatten().tolist()
+                assert set(fs) <= {m, m + 1}, (m, k, fs)
+        assert sorted(owner) == nz.any(0).nonzero().flatten().tolist()
+        # 16 lanes of a band: distinct addresses fall into distinct 8-byte bank pairs at every step
         for band in range(5):
             ms = list(range(16 * band, min(n, 16 * band + 16)))
-            for i in range(taps[band]):
+            for i in range(steps[band]):
                 by_bank = {}
                 for m in ms:
                     by_bank.setdefault((st[m] + i) % 16, set()).add(st[m] + i)
                 assert all(len(v) == 1 for v in by_bank.values()), "bank conflict in band %d" % band
-        if n == 80:
-            assert int(nz.sum()) == 501 and taps == [3, 5, 6, 10, 17]      # the fully-unrolled kernel variant
-    assert lib.lidfe_mel_plan(80, None, k0, cnt, st, bt) == _lib.E_NULL
-    assert lib.lidfe_mel_plan(200, banks.data_ptr(), k0, cnt, st, bt) == _lib.E_CONFIG
+        # replaying the plan gives back the dense bank bit for bit
+        dense = torch.full((n, 257), 7.0)
+        assert lib.lidfe_mel_plan_expand(n, banks.data_ptr(), dense.data_ptr()) == 0
+        assert torch.equal(dense, banks)
+        if ci == 0:
+            assert int(nz.sum()) == 501 and steps == [2, 2, 4, 6, 9]      # the fully-unrolled kernel variant
+            assert sum(cnt[m] for m in range(n)) == 255                   # bins 1..255, each read once
+    banks = cases[0][1]
+    first, cnt, st = (C.c_int * 80)(), (C.c_int * 80)(), (C.c_int * 80)()
+    bt = (C.c_int * 5)()
+    assert lib.lidfe_mel_plan(80, None, first, cnt, st, bt) == _lib.E_NULL
+    assert lib.lidfe_mel_plan(200, banks.data_ptr(), first, cnt, st, bt) == _lib.E_CONFIG
     empty = torch.zeros(80, 257)
-    assert lib.lidfe_mel_plan(80, empty.data_ptr(), k0, cnt, st, bt) == _lib.E_MELBANK
+    assert lib.lidfe_mel_plan(80, empty.data_ptr(), first, cnt, st, bt) == _lib.E_MELBANK
+    dense3 = banks.clone()
+    dense3[10, 200] = 0.5                                             # a filter reaching far outside its neighbours
+    assert lib.lidfe_mel_plan(80, dense3.data_ptr(), first, cnt, st, bt) == _lib.E_MELBANK
 
 
 def test_draw_masks_consumes_rng_like_the_reference(golden_dir):
