@@ -17,6 +17,7 @@
 // 1 wavefront/clk/SM measured) are the binding resource, not FP32 issue: see DESIGN.md.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <stdint.h>
 
 namespace lidfe {
@@ -507,29 +508,34 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
           mB = __fdiv_rn(sum.y, static_cast<float>(kFrameLen));
         }
         const float c = P.preemph;
-        f2 to_prev = make_float2(0.f, 0.f);
+        // One pass over the 13 sample pairs: (A,B) pairs are formed by the mean subtraction itself (scalar FADDs write
+        // straight into the pair halves); x[2n-1] - mean lives in lane t-1 (same j), lane 0 takes lane 15's value of
+        // step j-1, and the very first sample of the frame replicates itself (ta: compliance/kaldi.py:193-198).
+        // x[j] - c * x[j-1]: product and difference rounded separately, as the reference's two tensor ops; with the
+        // reference's c == 1.0 the product is exact, so that (warp-uniform) variant skips the multiplies.
+        auto frame_pass = [&](auto unit_tag) {
+          constexpr bool kUnit = decltype(unit_tag)::value;
+          f2 to_prev = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 13; ++j) {
-          const int n = t + 16 * j;
-          const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
-          // (A,B) pairs are formed by the subtraction itself: scalar FADDs write straight into the pair halves
-          const f2 te = make_float2(__fsub_rn(x[j].x, mA), __fsub_rn(x[j + 5].x, mB));   // x[2n]   - mean
-          const f2 to = make_float2(__fsub_rn(x[j].y, mA), __fsub_rn(x[j + 5].y, mB));   // x[2n+1] - mean
-          // x[2n-1] - mean lives in lane t-1 (same j); lane 0 takes lane 15's value of step j-1, and the very
-          // first sample of the frame replicates itself (ta: compliance/kaldi.py:193-198)
-          const f2 send = (t == 15) ? to_prev : to;
-          f2 tp;
-          tp.x = __shfl_sync(0xffffffffu, send.x, up_lane);
-          tp.y = __shfl_sync(0xffffffffu, send.y, up_lane);
-          if (j == 0 && t == 0) tp = te;
-          to_prev = to;
-          // x[j] - c * x[j-1]: product and difference rounded separately, as the reference's two tensor ops
-          // (c == 1.0 in the reference's call: the product is then exact and costs one FMUL2)
-          const f2 se = sub2(te, mul2(tp, bc(c)));
-          const f2 so = sub2(to, mul2(te, bc(c)));
-          R[j] = mul2(se, bc(w.x));
-          I[j] = mul2(so, bc(w.y));
-        }
+          for (int j = 0; j < 13; ++j) {
+            const int n = t + 16 * j;
+            const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
+            const f2 te = make_float2(__fsub_rn(x[j].x, mA), __fsub_rn(x[j + 5].x, mB));   // x[2n]   - mean
+            const f2 to = make_float2(__fsub_rn(x[j].y, mA), __fsub_rn(x[j + 5].y, mB));   // x[2n+1] - mean
+            const f2 send = (t == 15) ? to_prev : to;
+            f2 tp;
+            tp.x = __shfl_sync(0xffffffffu, send.x, up_lane);
+            tp.y = __shfl_sync(0xffffffffu, send.y, up_lane);
+            if (j == 0 && t == 0) tp = te;
+            to_prev = to;
+            const f2 se = kUnit ? sub2(te, tp) : sub2(te, mul2(tp, bc(c)));
+            const f2 so = kUnit ? sub2(to, te) : sub2(to, mul2(te, bc(c)));
+            R[j] = mul2(se, bc(w.x));
+            I[j] = mul2(so, bc(w.y));
+          }
+        };
+        if (c == 1.f) frame_pass(std::true_type{});
+        else frame_pass(std::false_type{});
         if (t >= 8) R[12] = I[12] = make_float2(0.f, 0.f);
         R[13] = R[14] = R[15] = I[13] = I[14] = I[15] = make_float2(0.f, 0.f);
       }

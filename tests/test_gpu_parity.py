@@ -46,6 +46,20 @@ def _norm_rel(got, want):
 
 LOW_BINS = 3            # mel bins 0..2: cancellation dominated for white noise through the 1.0 pre-emphasis
 NORM_REL_LOW = 3e-4
+DEEP_NULL = 9.2         # nepers (40 dB) below the mel bin's median energy over the utterance
+DEEP_NULL_ENERGY = 1e-6  # allowed |E_gpu - E_ref| there, in units of that median energy (about 8 fp32 ulps of it)
+
+
+def _deep_nulls(want):
+    """Deep spectral nulls: frames whose energy in a mel bin lies more than 40 dB under that bin's median.  The FFT
+    round-off of ANY fp32 pipeline is relative to the typical magnitude in the frame, not to the nearly empty bin, so
+    the log amplifies it without bound there (one such point per ~1e5 in white noise; the fp32 reference itself is off
+    by 3e-4 .. 1e-3 against fp64 on them, and WHICH way depends on the host CPU's FFT kernels).  They are checked in
+    the energy domain against the fp32 resolution of the bin's typical energy instead."""
+    live = want != 0.0                                     # SpecAugment zeros are compared exactly elsewhere
+    med = torch.where(live, want, torch.full_like(want, float("nan"))).nanmedian(0).values
+    med = torch.nan_to_num(med, nan=0.0)
+    return live & (want < med - DEEP_NULL), med
 
 
 def _check_fbank(got, want, what, all_bins=False):
@@ -53,10 +67,16 @@ def _check_fbank(got, want, what, all_bins=False):
     assert got.shape == want.shape, what
     assert torch.isfinite(got).all(), what
     scale = want.abs().max()
-    hi = float((got[:, LOW_BINS:] - want[:, LOW_BINS:]).abs().max() / scale)
-    lo = float((got[:, :LOW_BINS] - want[:, :LOW_BINS]).abs().max() / scale)
+    deep, med = _deep_nulls(want)
+    err = (got - want).abs().masked_fill(deep, 0.0)
+    hi = float(err[:, LOW_BINS:].max() / scale)
+    lo = float(err[:, :LOW_BINS].max() / scale)
     assert hi <= NORM_REL, "%s: norm-relative error %g on bins >= %d" % (what, hi, LOW_BINS)
     assert lo <= (NORM_REL if all_bins else NORM_REL_LOW), "%s: norm-relative error %g on bins < %d" % (what, lo, LOW_BINS)
+    if deep.any():
+        assert deep.float().mean().item() <= 1e-3, "%s: %d deep nulls?" % (what, int(deep.sum()))
+        e = ((got.double().exp() - want.double().exp()).abs() / med.double().exp())[deep].max().item()
+        assert e <= DEEP_NULL_ENERGY, "%s: energy error %g (x median bin energy) in a deep null" % (what, e)
     bad = 1.0 - torch.isclose(got, want, rtol=1e-4, atol=5e-4).float().mean().item()
     assert bad <= 1e-4, "%s: %.4f %% of elements outside rtol=1e-4, atol=5e-4" % (what, 100 * bad)
 
@@ -101,15 +121,19 @@ def test_no_worse_than_reference_vs_fp64(fe):
     """Metric (iv): both fp32 pipelines against an fp64 evaluation with the same fp32 tables.  The error of a
     cancellation-dominated low bin is heavy tailed (the log amplifies the FFT round-off wherever the bin is nearly
     empty), so the distributions are compared at their median and 99th percentile, pooled over 4 utterances, plus
-    a loose bound on the maximum."""
+    a loose bound on the maximum outside the deep nulls (see _deep_nulls), which are bounded in the energy domain."""
     groups = ((0, 3), (3, 10), (10, 80))
     ref_e, gpu_e = [], []
     for seed in range(4):
         x = O.synth_noise(128000, 200 + seed)
         got = fe.featurize([x])[0][0].cpu().double()
         truth = O.truth64_fbank(x)
-        ref_e.append((O.kaldi_fbank(x).double() - truth).abs())
-        gpu_e.append((got - truth).abs())
+        deep, med = _deep_nulls(truth.float())
+        if deep.any():
+            e = ((got.exp() - truth.exp()).abs() / med.double().exp())[deep].max().item()
+            assert e <= DEEP_NULL_ENERGY, "energy error %g (x median bin energy) in a deep null" % e
+        ref_e.append((O.kaldi_fbank(x).double() - truth).abs().masked_fill(deep, 0.0))
+        gpu_e.append((got - truth).abs().masked_fill(deep, 0.0))
     ref_e, gpu_e = torch.cat(ref_e), torch.cat(gpu_e)
     for a, b in groups:
         r, g = ref_e[:, a:b].flatten(), gpu_e[:, a:b].flatten()
