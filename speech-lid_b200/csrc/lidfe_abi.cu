@@ -22,7 +22,8 @@ struct lidfe_ctx {
   int num_sms;
   int n_out;
   int band_taps[kBands];
-  int std_mel;    // band_taps == kStdTaps -> fully unrolled mel loop
+  int std_mel;    // kernel variant: 1 = Kaldi-80 bank + DC removal + pre-emphasis 1.0, 2 = HTK-80 bank + window-only
+                  // framing (both with the mel loop fully unrolled), 0 = generic (runtime loops and switches)
   // device tables
   unsigned char* d_blob;   // window | tw1 | tw2 | mel_k0 | mel_w | dct | lifter, laid out like the kernel's shared memory
   int blob_bytes;
@@ -78,14 +79,14 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 
 typedef void (*fbank_fn)(const FbankParams);
 template <typename TIn>
-static fbank_fn pick_kernel_t(bool mfcc, bool std_mel) {
-  if (mfcc) return std_mel ? fbank_kernel<TIn, true, true> : fbank_kernel<TIn, true, false>;
-  return std_mel ? fbank_kernel<TIn, false, true> : fbank_kernel<TIn, false, false>;
+static fbank_fn pick_kernel_t(bool mfcc, int std_mel) {
+  if (mfcc) return std_mel == 1 ? fbank_kernel<TIn, true, 1> : std_mel == 2 ? fbank_kernel<TIn, true, 2> : fbank_kernel<TIn, true, 0>;
+  return std_mel == 1 ? fbank_kernel<TIn, false, 1> : std_mel == 2 ? fbank_kernel<TIn, false, 2> : fbank_kernel<TIn, false, 0>;
 }
 static fbank_fn pick_kernel(const lidfe_ctx* c) {
   const bool mfcc = c->cfg.n_ceps > 0;
-  return c->cfg.in_dtype == LIDFE_IN_I16 ? pick_kernel_t<short>(mfcc, c->std_mel != 0)
-                                         : pick_kernel_t<float>(mfcc, c->std_mel != 0);
+  return c->cfg.in_dtype == LIDFE_IN_I16 ? pick_kernel_t<short>(mfcc, c->std_mel)
+                                         : pick_kernel_t<float>(mfcc, c->std_mel);
 }
 static size_t smem_for(const lidfe_config& c, int total_taps) {
   const bool mf = c.n_ceps > 0;
@@ -408,11 +409,16 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
     }
   }
   const int total_taps = mp.total_steps;
-  c->std_mel = 1;
-  for (int b = 0; b < kBands; ++b) {
-    c->band_taps[b] = mp.band_steps[b];
-    if (c->band_taps[b] != std_taps(b)) c->std_mel = 0;
+  for (int b = 0; b < kBands; ++b) c->band_taps[b] = mp.band_steps[b];
+  c->std_mel = 0;
+  for (int kind = 1; kind <= 2 && !c->std_mel; ++kind) {
+    bool same = true;
+    for (int b = 0; b < kBands; ++b) same = same && (c->band_taps[b] == std_taps(kind, b));
+    if (same) c->std_mel = kind;
   }
+  // the unrolled variants also hard-wire the framing of the call they belong to (see the kernel)
+  if (c->std_mel == 1 && !(cfg->remove_dc && cfg->preemph == 1.f)) c->std_mel = 0;
+  if (c->std_mel == 2 && !(!cfg->remove_dc && cfg->preemph == 0.f)) c->std_mel = 0;
   std::vector<float> melw(mp.w);
   for (float& v : melw) v *= 0.25f;
   std::vector<int> k0(mp.start, mp.start + kMaxMels);   // the kernel's per-lane first power bin
@@ -467,8 +473,8 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
       lidfe_config fb = *cfg;
       fb.n_ceps = 0;
       c->smem_bytes_fbank = smem_for(fb, total_taps);
-      fbank_fn f2 = (cfg->in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, c->std_mel != 0)
-                                                      : pick_kernel_t<float>(false, c->std_mel != 0);
+      fbank_fn f2 = (cfg->in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, c->std_mel)
+                                                      : pick_kernel_t<float>(false, c->std_mel);
       e = cudaFuncSetAttribute(f2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes_fbank));
       c->smem_bytes_dct = (static_cast<size_t>(kDctStages) * kDctMaxTiles * kDctThreads * 4 +
                            static_cast<size_t>(cfg->n_mels) * kDctMaxCeps + kDctMaxCeps + 2 * kDctMaxCeps) * sizeof(float);
@@ -721,8 +727,8 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     F.mode = LIDFE_CMVN_NONE;
     F.ws_blocked = 1;
     F.const_bytes = h->blob_bytes_fbank;
-    fbank_fn f2 = (h->cfg.in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, h->std_mel != 0)
-                                                     : pick_kernel_t<float>(false, h->std_mel != 0);
+    fbank_fn f2 = (h->cfg.in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, h->std_mel)
+                                                     : pick_kernel_t<float>(false, h->std_mel);
     long long g2 = p->n_tiles < static_cast<long long>(h->num_sms) * 4 ? p->n_tiles : static_cast<long long>(h->num_sms) * 4;
     if (g2 < 1) g2 = 1;
     const bool prof2 = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));

@@ -45,7 +45,12 @@ constexpr int kMaxMasks = 8;
 constexpr int kTileCache = 16;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
 // taps per band of the 80-mel / 16 kHz / 512 Kaldi bank
 // (after the host shifts each filter's first tap so that the 16 lanes of a band read 16 distinct bank pairs)
-__host__ __device__ constexpr int std_taps(int b) { return b == 0 ? 2 : b == 1 ? 2 : b == 2 ? 4 : b == 3 ? 6 : 9; }
+// mel steps per band of the two banks the reference uses, for the fully unrolled kernel variants:
+// kind 1 = Kaldi 80 x 257 (20 Hz .. 8 kHz, mel = 1127 ln(1 + f/700)), kind 2 = HTK 80 x 257 (0 .. 8 kHz, 2595 log10)
+__host__ __device__ constexpr int std_taps(int kind, int b) {
+  return kind == 1 ? (b == 0 ? 2 : b == 1 ? 2 : b == 2 ? 4 : b == 3 ? 6 : 9)
+                   : (b == 0 ? 1 : b == 1 ? 3 : b == 2 ? 4 : b == 3 ? 6 : 10);
+}
 
 struct Tile {
   long long wav_off;    // first sample of the tile's first frame in the packed buffer
@@ -285,7 +290,7 @@ struct SmemLayout {
 // ------------------------------------------------------------------------------------------------
 // the fused front-end kernel
 // ------------------------------------------------------------------------------------------------
-template <typename TIn, bool kMfcc, bool kStdMel>
+template <typename TIn, bool kMfcc, int kStdMel>
 __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constant__ FbankParams P) {
   using L = SmemLayout<TIn, kMfcc>;
   constexpr int kScratchFloats = scratch_floats(kMfcc);
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
   tap_off[0] = 0;
 #pragma unroll
   for (int b = 0; b < kBands; ++b) {
-    taps[b] = kStdMel ? std_taps(b) : P.band_taps[b];
+    taps[b] = kStdMel ? std_taps(kStdMel, b) : P.band_taps[b];
     tap_off[b + 1] = tap_off[b] + taps[b];
   }
   float* const sm_dct = sm_melw + tap_off[kBands] * 32;
@@ -488,22 +493,22 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
           const int n = t + 16 * j;
           x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
         }
-        f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-          if (j < 12 || t < 8) {
-            sA = add2(sA, x[j]);
-            sB = add2(sB, x[j + 5]);
-          }
-        }
-        f2 sum = make_float2(sA.x + sA.y, sB.x + sB.y);
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) {
-          sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
-          sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
-        }
         float mA = 0.f, mB = 0.f;
-        if (P.remove_dc) {
+        if (kStdMel == 1 || (kStdMel == 0 && P.remove_dc)) {
+          f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 13; ++j) {
+            if (j < 12 || t < 8) {
+              sA = add2(sA, x[j]);
+              sB = add2(sB, x[j + 5]);
+            }
+          }
+          f2 sum = make_float2(sA.x + sA.y, sB.x + sB.y);
+#pragma unroll
+          for (int o = 8; o >= 1; o >>= 1) {
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+          }
           mA = __fdiv_rn(sum.x, static_cast<float>(kFrameLen));
           mB = __fdiv_rn(sum.y, static_cast<float>(kFrameLen));
         }
@@ -534,8 +539,22 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
             I[j] = mul2(so, bc(w.y));
           }
         };
-        if (c == 1.f) frame_pass(std::true_type{});
-        else frame_pass(std::false_type{});
+        // The framing flavour is fixed per kernel variant (kStdMel: 1 = the reference's Kaldi call, DC removal +
+        // coefficient 1.0; 2 = its torch.stft call, window only; 0 = anything else), so that every instantiation
+        // carries one copy of this loop: the tile body has to stay inside the 32 KB instruction cache.
+        if (kStdMel == 2) {
+          // window only; the (A,B) pairs are formed by the scalar multiplies themselves
+#pragma unroll
+          for (int j = 0; j < 13; ++j) {
+            const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * (t + 16 * j));
+            R[j] = make_float2(__fmul_rn(x[j].x, w.x), __fmul_rn(x[j + 5].x, w.x));
+            I[j] = make_float2(__fmul_rn(x[j].y, w.y), __fmul_rn(x[j + 5].y, w.y));
+          }
+        } else if (kStdMel == 1) {
+          frame_pass(std::true_type{});
+        } else {
+          frame_pass(std::false_type{});
+        }
         if (t >= 8) R[12] = I[12] = make_float2(0.f, 0.f);
         R[13] = R[14] = R[15] = I[13] = I[14] = I[15] = make_float2(0.f, 0.f);
       }
@@ -617,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
           const float2* wp = reinterpret_cast<const float2*>(sm_melw) + tap_off[b] * 16 + t;
           if (kStdMel) {
 #pragma unroll
-            for (int i = 0; i < std_taps(b); ++i) {
+            for (int i = 0; i < std_taps(kStdMel, b); ++i) {
               const f2 p = pp[i];
               const float2 w = wp[i * 16];
               own = fma2(p, bc(w.x), own);
