@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
     const int nsamp = kFrameShift * tl.nframes + (kFrameLen - kFrameShift);
     const TIn* src = reinterpret_cast<const TIn*>(P.wav) + tl.wav_off;
     TIn* dst = sm_in;
-    if (tl.aux) {
+    if (__builtin_expect(tl.aux != 0, 1)) {
       if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t bytes = nsamp * (uint32_t)sizeof(TIn);
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
   int it = 0;
   for (int tile_idx = tile_begin; tile_idx < tile_end; ++tile_idx, ++it) {
     const Tile tl = sm_tiles[it % kTileCache];
-    if ((it + 1) % kTileCache == 0 && tile_idx + 1 < tile_end) {
+    if (__builtin_expect((it + 1) % kTileCache == 0 && tile_idx + 1 < tile_end, 0)) {
       // descriptor cache exhausted (ranges longer than kTileCache tiles): refill.  Everyone has its copy of `tl`.
       __syncthreads();
       const int n = min(tile_end - (tile_idx + 1), kTileCache);
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
       __syncthreads();
     }
 
-    if (tl.nframes == 0) {
+    if (__builtin_expect(tl.nframes == 0, 0)) {
       // zero-fill tile: pad_sequence's zeros (ref: lid/raw_datasets.py:347-350)
       const long long total = P.ws_blocked ? 0 : static_cast<long long>(tl.aux) * n_out;   // (the DCT kernel fills them)
       for (long long i = tid; i < total; i += kThreads) {
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
       __syncwarp();                                  // previous tile's readers of this warp's copy are done
       if (lane < P.n_masks * 4) wm[lane] = sm_masks[lane];
       __syncwarp();
-      if (tl.utt != cur_utt) {
+      if (__builtin_expect(tl.utt != cur_utt, 0)) {
         cur_utt = tl.utt;
         dim_masked = 0u;
         for (int q = 0; q < P.n_masks; ++q) {
@@ -757,11 +757,9 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
         const f2 p0 = *reinterpret_cast<const f2*>(v0 + 2 * d), p1 = *reinterpret_cast<const f2*>(v1 + 2 * d);
         double a1 = wacc[d], a2 = wacc[kMaxMels + d];
         if (f0 + 3 < tl.nframes) {   // all four frames live (every tile but an utterance's last): no predicates
-          const double x0 = p0.x, x1 = p0.y, x2 = p1.x, x3 = p1.y;
-          a1 += x0; a2 = fma(x0, x0, a2);
-          a1 += x1; a2 = fma(x1, x1, a2);
-          a1 += x2; a2 = fma(x2, x2, a2);
-          a1 += x3; a2 = fma(x3, x3, a2);
+          const double x0 = p0.x, x1 = p0.y, x2 = p1.x, x3 = p1.y;       // short dependency chains: a tree per tile
+          a1 += (x0 + x1) + (x2 + x3);
+          a2 += fma(x1, x1, x0 * x0) + fma(x3, x3, x2 * x2);
         } else {
           if (f0 + 0 < tl.nframes) { const double x = p0.x; a1 += x; a2 = fma(x, x, a2); }
           if (f0 + 1 < tl.nframes) { const double x = p0.y; a1 += x; a2 = fma(x, x, a2); }
@@ -792,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
         const Tile nx = sm_tiles[(it + 1) % kTileCache];
         flush = (nx.nframes == 0) || (nx.utt != tl.utt);
       }
-      if (flush) {
+      if (__builtin_expect(flush, 0)) {
         __syncthreads();   // every warp's running maximum covers this tile
         if (tid == 0) {
           float m = sm_wmax[0];
@@ -812,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
         flush = (nx.nframes == 0) || (mode == 1 && nx.utt != tl.utt);
       }
       if (mode == 3 && tid == kThreads - 1) sm_acc[kWarps * 2 * kMaxMels] += static_cast<double>(tl.nframes);
-      if (flush) {     // combine the warps' accumulators
+      if (__builtin_expect(flush, 0)) {     // combine the warps' accumulators
         __syncthreads();   // every warp has added this tile
         for (int e = tid; e < 2 * kMaxMels; e += kThreads) {
           const int which = e / kMaxMels, d = e - which * kMaxMels;

@@ -208,6 +208,43 @@ def test_mfcc_vs_fixtures_and_oracle(lid, golden_dir):
         assert _norm_rel(feats[i].cpu(), O.kaldi_mfcc(w)) <= NORM_REL
 
 
+def test_generic_kernel_variant_configs(lid):
+    """Configurations outside the two unrolled kernel variants (Kaldi-80 call, HTK-80 stft call) run the generic
+    variant: runtime mel loop, coefficient-c pre-emphasis, in-kernel DCT epilogue when n_mels % 4 != 0 or statistics
+    are needed.  Oracle = the same torchaudio arithmetic with those arguments."""
+    for n_mels, pre in ((40, 0.97), (64, 1.0), (23, 0.97)):
+        fe = lid.FrontEnd(n_mels=n_mels, preemph=pre)
+        for kind, gen, all_bins in (("noise", O.synth_noise, False), ("speech", O.synth_speechlike, True)):
+            wavs = [gen(n, 900 + i) for i, n in enumerate((32000, 5000, 16000))]
+            feats, _ = fe.featurize(wavs)
+            feats = feats.cpu()
+            for i, w in enumerate(wavs):
+                want = O.kaldi_fbank(w, n_mels=n_mels, preemph=pre)
+                _check_fbank(feats[i, :want.shape[0]], want, "%s n_mels=%d preemph=%g utt %d" % (kind, n_mels, pre, i),
+                             all_bins=all_bins)
+                assert torch.all(feats[i, want.shape[0]:] == 0)
+    # classic Kaldi MFCC: 13 cepstra of 23 mel bins, 0.97 pre-emphasis (DCT epilogue inside the fbank kernel)
+    mf = lid.FrontEnd(n_mels=23, n_ceps=13, preemph=0.97)
+    wavs = [O.synth_noise(n, 950 + i) for i, n in enumerate((32000, 7000))]
+    feats, _ = mf.featurize(wavs)
+    assert feats.shape == (2, 198, 13)
+    for i, w in enumerate(wavs):
+        want = O.kaldi_mfcc(w, num_ceps=13, n_mels=23, preemph=0.97)
+        assert _norm_rel(feats[i, :want.shape[0]].cpu(), want) <= NORM_REL
+    # MFCC-40 + per-utterance CMVN: statistics force the in-kernel DCT variant; tight against the device's own raw
+    # cepstra, loose against the oracle chain (1/std amplifies the fbank round-off)
+    mf = lid.FrontEnd(n_mels=80, n_ceps=40)
+    wavs = [O.synth_speechlike(n, 960 + i) for i, n in enumerate((48000, 20000))]
+    raw, _ = mf.featurize(wavs)
+    norm, _ = mf.featurize(wavs, cmvn="utt")
+    for i, w in enumerate(wavs):
+        T = O.kaldi_num_frames(w.shape[-1])
+        want = O.cmvn_per_utt(raw[i, :T].cpu())
+        assert torch.allclose(norm[i, :T].cpu(), want, rtol=1e-4, atol=2e-4), (norm[i, :T].cpu() - want).abs().max()
+        full = O.cmvn_per_utt(O.kaldi_mfcc(w))
+        assert torch.allclose(norm[i, :T].cpu(), full, rtol=1e-3, atol=5e-3), (norm[i, :T].cpu() - full).abs().max()
+
+
 def test_specaug_masks_bit_exact(fe, lid, golden_dir):
     """Masks drawn on the host from the reference's RNG stream, applied in the kernel epilogue: the masked
     positions are exactly the reference's, and every unmasked value equals the unmasked run bit for bit."""
