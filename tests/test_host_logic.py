@@ -228,3 +228,39 @@ def test_audio_processor_surface_matches_reference_signatures():
         ap.spectrogram_augment(spec, mask_times=1, t_stretch=True)
     with pytest.raises(NotImplementedError):
         ap.wav2mel(torch.zeros(1, 16000), n_fft=400)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/lidfe.h compiles as C99 with no torch / CUDA headers in sight, and a C program linked against
+    liblidfe.so can call the host-only entry points (what a cgo / JNI / ctypes binding relies on)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    lid.load_library()                                        # raises if the library is not built
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "speech-lid_b200")
+    src = tmp_path / "use_lidfe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "lidfe.h"
+int main(void) {
+  lidfe_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.sample_rate = 16000; cfg.frame_len = 400; cfg.frame_shift = 160; cfg.fft_len = 512; cfg.n_mels = 80;
+  if (lidfe_num_frames(128000, &cfg) != 798) return 1;
+  if (lidfe_num_frames(399, &cfg) != 0) return 2;
+  if (lidfe_abi_version() != LIDFE_ABI_VERSION) return 3;
+  if (strstr(lidfe_strerror(LIDFE_E_SHORT), "shorter than one frame") == NULL) return 4;
+  if (lidfe_create(NULL, &cfg, NULL, NULL, NULL, NULL) != LIDFE_E_NULL) return 5;
+  printf("ok %d\n", lidfe_abi_version());
+  return 0;
+}
+''')
+    exe = tmp_path / "use_lidfe"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-llidfe", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("ok ")
