@@ -854,7 +854,7 @@ static int launch_wave(lidfe_handle h, lidfe_plan p, const void* in, int in_i16,
   W.dither = dither;
   W.noise = noise_dev;
   W.preemph = preemph;
-  wave_stages_kernel<<<static_cast<unsigned>(p->B), 512, 0, static_cast<cudaStream_t>(stream)>>>(W);
+  wave_stages_kernel<<<static_cast<unsigned>(p->B) * kWaveCluster, kWaveThreads, 0, static_cast<cudaStream_t>(stream)>>>(W);
   g_launches.fetch_add(1);
   CU_TRY(cudaGetLastError());
   return LIDFE_OK;

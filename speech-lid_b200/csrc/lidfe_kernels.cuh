@@ -16,6 +16,7 @@
 // lane t with lane 16-t through warp shuffles.  Shared-memory wavefronts + shuffles (one shared pipe,
 // 1 wavefront/clk/SM measured) are the binding resource, not FP32 issue: see DESIGN.md.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <type_traits>
 #include <stdint.h>
@@ -1207,10 +1208,22 @@ struct WaveParams {
   float preemph;
 };
 
-__global__ void __launch_bounds__(512) wave_stages_kernel(const __grid_constant__ WaveParams P) {
-  __shared__ double s_red[2][16];
-  __shared__ float s_mean, s_div;
-  const int u = blockIdx.x;
+// One thread-block CLUSTER of kWaveCluster CTAs per utterance: every CTA owns a contiguous slice of the samples, the
+// partial sums of the two-pass mean / variance meet through distributed shared memory (each CTA reads its peers'
+// partials after a cluster barrier and adds them in rank order, so all of them hold the same bits), and the slice is
+// re-read from L2 for the elementwise pass.  (One CTA per utterance left 3/4 of the SMs idle on a 32-utterance chunk
+// and serialised 128 000 fp64 adds per thread block.)
+constexpr int kWaveCluster = 8;
+constexpr int kWaveThreads = 512;
+
+__global__ void __cluster_dims__(kWaveCluster, 1, 1) __launch_bounds__(kWaveThreads)
+    wave_stages_kernel(const __grid_constant__ WaveParams P) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ double s_red[kWaveThreads / 32];
+  __shared__ double s_part[2];                           // this CTA's partial sum / partial sum of squared deviations
+  const int u = blockIdx.x / kWaveCluster;
+  const int rank = static_cast<int>(cluster.block_rank());
   const long long off = P.offsets[u], n = P.lengths[u];
   const float* xf = reinterpret_cast<const float*>(P.in) + off;
   const short* xs = reinterpret_cast<const short*>(P.in) + off;
@@ -1218,34 +1231,43 @@ __global__ void __launch_bounds__(512) wave_stages_kernel(const __grid_constant_
   const float* nz = P.noise ? P.noise + off : nullptr;
   float* y = P.out + off;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long per = (n + kWaveCluster - 1) / kWaveCluster;
+  const long long lo = per * rank < n ? per * rank : n, hi = lo + per < n ? lo + per : n;
+
+  // CTA-wide fp64 sum of `v`, left in s_part[slot]
+  auto cta_sum = [&](double v, int slot) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kWaveThreads / 32; ++w) t += s_red[w];
+      s_part[slot] = t;
+    }
+  };
+  auto cluster_total = [&](int slot) -> double {
+    cluster.sync();                                      // every CTA's partial is written (and visible cluster-wide)
+    double t = 0.0;
+    for (int r = 0; r < kWaveCluster; ++r) t += cluster.map_shared_rank(s_part, r)[slot];
+    return t;
+  };
+
   float mean = 0.f, div = 1.f;
   if (P.normalize) {
     // two-pass mean / unbiased variance in fp64 (torch.std_mean accumulates in fp32 with a cascade)
     double s = 0.0;
-    for (long long i = tid; i < n; i += blockDim.x) s += ld(i);
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_red[0][warp] = s;
-    __syncthreads();
-    double tot = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[0][w];
-    const double m = tot / static_cast<double>(n);
+    for (long long i = lo + tid; i < hi; i += kWaveThreads) s += ld(i);
+    cta_sum(s, 0);
+    const double m = cluster_total(0) / static_cast<double>(n);
     double q = 0.0;
-    for (long long i = tid; i < n; i += blockDim.x) {
+    for (long long i = lo + tid; i < hi; i += kWaveThreads) {
       const double dlt = ld(i) - m;
       q += dlt * dlt;
     }
-    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (lane == 0) s_red[1][warp] = q;
-    __syncthreads();
-    double qt = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) qt += s_red[1][w];
-    if (tid == 0) {
-      s_mean = static_cast<float>(m);
-      s_div = static_cast<float>(sqrt(qt / static_cast<double>(n - 1))) + 1e-6f;
-    }
-    __syncthreads();
-    mean = s_mean;
-    div = s_div;
+    cta_sum(q, 1);
+    const double qt = cluster_total(1);
+    mean = static_cast<float>(m);
+    div = static_cast<float>(sqrt(qt / static_cast<double>(n - 1))) + 1e-6f;
   }
   auto stage1 = [&](long long i) -> float {
     float v = ld(i);
@@ -1253,11 +1275,12 @@ __global__ void __launch_bounds__(512) wave_stages_kernel(const __grid_constant_
     if (P.dither != 0.f) v = __fadd_rn(v, __fmul_rn(P.dither, nz[i]));
     return v;
   };
-  for (long long i = tid; i < n; i += blockDim.x) {
+  for (long long i = lo + tid; i < hi; i += kWaveThreads) {
     float v = stage1(i);
     if (P.preemph != 0.f && i > 0) v = __fsub_rn(v, __fmul_rn(P.preemph, stage1(i - 1)));
     y[i] = v;
   }
+  cluster.sync();                                        // no CTA exits while a peer may still read its partials
 }
 
 }  // namespace lidfe

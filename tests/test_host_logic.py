@@ -264,3 +264,10 @@ int main(void) {
                     "-o", str(exe), "-L", libdir, "-llidfe", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert out.startswith("ok ")
+
+
+def test_graft_entry_build_passes():
+    """build() is what the driver calls: it must compile (or find the library fresh), import the package and pass its
+    own export / ABI-version checks."""
+    import __graft_entry__ as g
+    g.build()
