@@ -1193,7 +1193,7 @@ __global__ void __launch_bounds__(kDctThreads, 4) mfcc_dct_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-// waveform-level stages (ref: lid/audio_processor.py:108-115,129-134).  One CTA per utterance.
+// waveform-level stages (ref: lid/audio_processor.py:108-115,129-134).  One 8-CTA cluster per utterance.
 // ------------------------------------------------------------------------------------------------
 struct WaveParams {
   const void* in;             // float32 or int16 samples
