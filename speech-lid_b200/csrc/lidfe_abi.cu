@@ -414,7 +414,7 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   for (int kind = 1; kind <= 2 && !c->std_mel; ++kind) {
     bool same = true;
     for (int b = 0; b < kBands; ++b) same = same && (c->band_taps[b] == std_taps(kind, b));
-    if (same) c->std_mel = kind;
+    if (same && cfg->n_mels == 80) c->std_mel = kind;      // (the kernel variants hard-wire 80 output dims)
   }
   // the unrolled variants also hard-wire the framing of the call they belong to (see the kernel)
   if (c->std_mel == 1 && !(cfg->remove_dc && cfg->preemph == 1.f)) c->std_mel = 0;

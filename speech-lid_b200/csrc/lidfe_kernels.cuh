@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
   const int lane = tid & 31;
   const int t = lane & 15;       // lane inside the half-warp
   const int half = lane >> 4;    // which frame pair of the warp
-  const int n_out = P.n_out;
+  // the two unrolled variants are only selected for 80 mel bins, so without the DCT epilogue the output width is a
+  // compile-time constant there (no per-band bound checks, immediate store offsets)
+  const int n_out = (kStdMel != 0 && !kMfcc) ? 80 : P.n_out;
   const int mode = P.mode;
   const bool want_stats = (mode == 1) || (mode == 3);
 
