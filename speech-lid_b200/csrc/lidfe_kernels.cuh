@@ -712,8 +712,9 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
               if (actB) o[256 * b + 4] = val[b].y;
             }
           }
-        } else if (mode != 0 && mode != 2 && tl.nframes == kTileFrames) {
-          // full tile, nothing to apply here (statistics modes: masks and normalisation happen in the second pass)
+        } else if (mode != 2 && !(mode == 0 && P.n_masks > 0) && tl.nframes == kTileFrames) {
+          // full tile, nothing to apply here (no masks given, or a statistics mode: masks and normalisation happen in
+          // the second pass)
           float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
 #pragma unroll
           for (int b = 0; b < kBands; ++b) {
