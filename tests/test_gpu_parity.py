@@ -298,6 +298,44 @@ def test_per_utt_cmvn(fe, lid):
         assert torch.all(got[i, T:] == 0)
 
 
+def test_repeated_launches_streams_and_mask_limits(fe, lid):
+    """The per-utterance statistics workspace is double buffered and cleared by the apply kernel of the previous
+    launch: repeated launches on one plan, launches on side streams, and the maximum number of masks must all give the
+    same bits as a first launch."""
+    lens = [48000, 7000, 128000, 16000, 400]
+    wavs = [O.synth_noise(n, 1000 + i).squeeze(0) for i, n in enumerate(lens)]
+    frames = [O.kaldi_num_frames(n) for n in lens]
+    plan = fe.make_plan(lens, padded=True)
+    packed = fe.pack([w.cuda() for w in wavs], plan)
+    torch.manual_seed(11)
+    masks = lid.draw_masks(frames, 80, 0.05, 27, 8).cuda()                 # 8 (time, freq) mask rows: the ABI maximum
+    assert masks.shape[1] == 8
+    same = lambda x, y: torch.equal(torch.nan_to_num(x, nan=-777.0), torch.nan_to_num(y, nan=-777.0))   # noqa: E731
+    first = fe.featurize_packed(packed, plan, masks=masks, cmvn="utt").clone()
+    assert torch.isnan(first[4, 0]).any()      # one frame: the unbiased std of one sample is NaN, as torch.std gives
+    for _ in range(5):                                                     # ping-pong halves, both parities
+        again = fe.featurize_packed(packed, plan, masks=masks, cmvn="utt")
+        assert same(again, first)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    plan2 = fe.make_plan(lens, padded=True)
+    torch.cuda.synchronize()
+    a = fe.featurize_packed(packed, plan, masks=masks, cmvn="utt", stream=s1)
+    b = fe.featurize_packed(packed, plan2, masks=masks, cmvn="utt", stream=s2)    # same handle, other plan, concurrently
+    c = fe.featurize_packed(packed, plan, cmvn="none", stream=s1)
+    torch.cuda.synchronize()
+    assert same(a, first) and same(b, first)
+    raw = fe.featurize_packed(packed, plan, cmvn="none")
+    assert torch.equal(c, raw)
+    # masks land where the table says
+    for i, T in enumerate(frames[:-1]):
+        for q in range(8):
+            t0, t1, f0, f1 = (int(v) for v in masks[i, q])
+            assert torch.all(first[i, t0:t1] == 0) and torch.all(first[i, :T, f0:f1] == 0)
+        assert torch.isfinite(first[i, :T]).all()
+    with pytest.raises(Exception):
+        fe.featurize_packed(packed, plan, masks=torch.zeros(len(lens), 9, 4, dtype=torch.int32).cuda())   # > 8 masks
+
+
 def test_global_cmvn_two_pass(fe):
     lens = [30000, 16000, 64000, 8000]
     wavs = [O.synth_noise(n, 900 + i) for i, n in enumerate(lens)]
