@@ -5,16 +5,19 @@
 //   zero-pad to 512 -> |rfft|^2 -> sparse triangular mel -> log(max(., eps)) [-> DCT + lifter] ->
 //   [global CMVN] -> [SpecAugment zero-fill] -> out, plus per-utterance / global sum & sum-of-squares.
 //
-// Mapping (v2, "frame-pair packed"): a persistent CTA of 4 warps walks a contiguous range of tiles of <= 16
-// consecutive frames of one utterance.  A tile's 160*F+240 samples are staged into shared memory by ONE TMA
-// bulk copy (cp.async.bulk + mbarrier), double buffered so the next tile's copy overlaps this tile's math.
+// Mapping ("frame-pair packed"): a persistent CTA of 4 warps (4 CTAs per SM) walks a contiguous range of tiles of
+// <= 16 consecutive frames of one utterance.  A tile's 160*F+240 samples are staged into shared memory by ONE TMA
+// bulk copy (cp.async.bulk + mbarrier) into a single buffer that the last warp to have consumed the previous tile
+// refills, so the copy overlaps most of the current tile's math and no CTA-wide barrier is needed per tile.
 // A half-warp (16 lanes) owns TWO adjacent frames (A, B) and carries them as the two halves of Blackwell's
 // packed f32x2 registers: every add / mul / fma of the FFT is one FADD2 / FMUL2 / FFMA2 for both frames, and
 // every table value (window, twiddles, mel weights) is loaded once and broadcast to both.  The 512-point real
 // FFT is a 256-point complex FFT of z[n] = x[2n] + i x[2n+1] done as 16 x 16 (two in-register radix-4x4
 // 16-point DFTs per lane, one shared-memory transpose in between) followed by the real-FFT split, which pairs
-// lane t with lane 16-t through warp shuffles.  Shared-memory wavefronts + shuffles (one shared pipe,
-// 1 wavefront/clk/SM measured) are the binding resource, not FP32 issue: see DESIGN.md.
+// lane t with lane 16-t through warp shuffles; the mel stage walks every power bin once ("segment form").
+// The kernel is latency / issue bound with the shared-memory + shuffle pipe at ~70 %, the FMA pipe and the
+// instruction issue at ~50 %; the other kernels of the path (CMVN apply, the MFCC GEMM, the
+// waveform stages) follow further down.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -44,8 +47,6 @@ __host__ __device__ constexpr int vals_off(bool mfcc) { return mfcc ? 688 : 520;
 __host__ __device__ constexpr int scratch_floats(bool mfcc) { return mfcc ? 864 : 704; }
 constexpr int kMaxMasks = 8;
 constexpr int kTileCache = 16;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
-// taps per band of the 80-mel / 16 kHz / 512 Kaldi bank
-// (after the host shifts each filter's first tap so that the 16 lanes of a band read 16 distinct bank pairs)
 // mel steps per band of the two banks the reference uses, for the fully unrolled kernel variants:
 // kind 1 = Kaldi 80 x 257 (20 Hz .. 8 kHz, mel = 1127 ln(1 + f/700)), kind 2 = HTK 80 x 257 (0 .. 8 kHz, 2595 log10)
 __host__ __device__ constexpr int std_taps(int kind, int b) {
