@@ -55,6 +55,8 @@ struct lidfe_plan_s {
   double* d_utt_stats;    // [2 launches][B][2][n_out]: ping-pong, the apply kernel of launch i clears the buffer of launch i+1
   int stats_flip;         // which half the next per-utterance-CMVN launch accumulates into (host-side toggle)
   unsigned* d_utt_max;    // [B] (LIDFE_POST_TOPDB)
+  float* d_tile_min;      // [n_tiles][kWarps] (LIDFE_POST_TOPDB, allocated on first use)
+  long long* d_utt_first_tile;   // [B]
   float* d_logmel;        // [rows][n_mels] log-mel workspace of the two-kernel MFCC path (allocated on first use)
   long long max_row;      // rows of the output matrix this plan touches
 };
@@ -517,9 +519,10 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   if (B <= 0) return LIDFE_E_ARG;
   const size_t in_elt = (h->cfg.in_dtype == LIDFE_IN_I16) ? 2 : 4;
   std::vector<Tile> tiles;
-  std::vector<long long> frames(B);
+  std::vector<long long> frames(B), utt_first_tile(B);
   long long total = 0;
   for (int i = 0; i < B; ++i) {
+    utt_first_tile[i] = static_cast<long long>(tiles.size());
     if (wav_offsets_host[i] < 0 || out_rows_host[i] < 0) return LIDFE_E_OFFSETS;
     const long long T = lidfe_num_frames(wav_lengths_host[i], &h->cfg);
     if (T <= 0) return LIDFE_E_SHORT;
@@ -579,6 +582,8 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   p->d_utt_stats = nullptr;
   p->stats_flip = 0;
   p->d_utt_max = nullptr;
+  p->d_tile_min = nullptr;
+  p->d_utt_first_tile = nullptr;
   p->d_logmel = nullptr;
   p->max_row = 0;
   for (int i = 0; i < B; ++i) {
@@ -590,6 +595,7 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   if (e == cudaSuccess) e = upload(&p->d_out_rows, out_rows_host, static_cast<size_t>(B));
   if (e == cudaSuccess) e = upload(&p->d_offsets, wav_offsets_host, static_cast<size_t>(B));
   if (e == cudaSuccess) e = upload(&p->d_lengths, wav_lengths_host, static_cast<size_t>(B));
+  if (e == cudaSuccess) e = upload(&p->d_utt_first_tile, utt_first_tile.data(), static_cast<size_t>(B));
   if (e == cudaSuccess)
     e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_stats), 2 * static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(p->d_utt_stats, 0, 2 * static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
@@ -612,6 +618,8 @@ int lidfe_plan_destroy(lidfe_plan p) {
   cudaFree(p->d_lengths);
   cudaFree(p->d_utt_stats);
   cudaFree(p->d_utt_max);
+  cudaFree(p->d_tile_min);
+  cudaFree(p->d_utt_first_tile);
   cudaFree(p->d_logmel);
   delete p;
   return LIDFE_OK;
@@ -636,6 +644,8 @@ static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, 
   A.normalize = normalize;
   A.clear_stats = clear_stats;
   A.utt_max = p->d_utt_max;
+  A.tile_min = (normalize == 2) ? p->d_tile_min : nullptr;
+  A.utt_first_tile = p->d_utt_first_tile;
   A.top_db = h->cfg.top_db;
   int rows_per_cta = kApplyRowsDefault;
   if (const char* env = getenv("LIDFE_APPLY_ROWS")) {
@@ -707,8 +717,12 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     P.utt_stats = stats_cur;
     p->stats_flip ^= 1;
   }
-  if (cmvn_mode == LIDFE_POST_TOPDB)
+  if (cmvn_mode == LIDFE_POST_TOPDB) {
     CU_TRY(cudaMemsetAsync(p->d_utt_max, 0, static_cast<size_t>(p->B) * sizeof(unsigned), st));
+    if (!p->d_tile_min)
+      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&p->d_tile_min), static_cast<size_t>(p->n_tiles) * kWarps * sizeof(float)));
+    P.tile_min = p->d_tile_min;
+  }
 
   const bool mfcc2 = h->cfg.n_ceps > 0 && h->cfg.n_ceps <= kDctMaxCeps && h->cfg.n_mels % 4 == 0 &&
                      (cmvn_mode == LIDFE_CMVN_NONE || cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL);

@@ -83,6 +83,8 @@ struct FbankParams {
   const long long* utt_offsets;  // [B] first sample of each utterance (edge tiles of CENTER framing)
   const long long* utt_lengths;  // [B]
   unsigned* utt_max;        // [B] order-preserving encoding of the utterance's max feature (LIDFE_POST_TOPDB)
+  float* tile_min;          // [n_tiles][kWarps] smallest live feature each warp saw in a tile (LIDFE_POST_TOPDB): lets the
+                            // clamp pass skip every block of rows that has nothing below max - top_db
   int remove_dc;
   // epilogue
   const int* masks;         // [B][n_masks][4]
@@ -776,16 +778,22 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
     }
     float* const sm_wmax = reinterpret_cast<float*>(sm_acc + kWarps * 2 * kMaxMels + 2);
     if (mode == 4) {   // AmplitudeToDB(top_db): running max of this warp's live features (ta: functional/functional.py:391-403)
-      float m = -INFINITY;
+      float m = -INFINITY, mn = INFINITY;
 #pragma unroll
       for (int b = 0; b < kBands; ++b)
         if (t + 16 * b < n_out) {
-          if (actA) m = fmaxf(m, val[b].x);
-          if (actB) m = fmaxf(m, val[b].y);
+          if (actA) { m = fmaxf(m, val[b].x); mn = fminf(mn, val[b].x); }
+          if (actB) { m = fmaxf(m, val[b].y); mn = fminf(mn, val[b].y); }
         }
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) sm_wmax[warp] = fmaxf(sm_wmax[warp], m);
+      for (int o = 16; o >= 1; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      if (lane == 0) {
+        sm_wmax[warp] = fmaxf(sm_wmax[warp], m);
+        if (P.tile_min) P.tile_min[static_cast<long long>(tile_idx) * kWarps + warp] = mn;   // every warp writes: no reset needed
+      }
     }
     // No per-tile CTA barrier.  Cross-warp state is only touched when sums / maxima are handed over (utterance change,
     // zero-fill ahead, end of the CTA's range): a CTA-uniform, rare event bracketed by two barriers.
@@ -862,6 +870,8 @@ struct ApplyParams {
   const unsigned* utt_max;       // [B] (normalize == 2)
   float top_db;
   double* clear_stats;           // [B][2][n_out] or NULL: the other half of the ping-pong workspace, zeroed here
+  const float* tile_min;         // [n_tiles][kWarps] or NULL (normalize == 2): per-tile minima written by fbank_kernel
+  const long long* utt_first_tile;   // [B] index of each utterance's first tile
 };
 
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__ ApplyParams P) {
@@ -873,6 +883,15 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   const long long r0 = static_cast<long long>(blockIdx.y) * P.rows_per_cta;
   if (r0 >= T) return;
   const int rows = static_cast<int>(T - r0 < P.rows_per_cta ? T - r0 : P.rows_per_cta);
+  if (P.normalize == 2 && P.n_masks == 0 && P.tile_min) {
+    // AmplitudeToDB's clamp only moves values below max - top_db: if no tile of this block of rows holds one, there
+    // is nothing to do here (the per-tile minima come from fbank_kernel; the block never touches the features)
+    const float floor_db = ord2f(P.utt_max[utt]) - P.top_db;
+    const long long t_lo = P.utt_first_tile[utt] + r0 / kTileFrames, t_hi = P.utt_first_tile[utt] + (r0 + rows - 1) / kTileFrames;
+    int below = 0;
+    for (long long i = t_lo * kWarps + tid; i < (t_hi + 1) * kWarps; i += 256) below |= (P.tile_min[i] < floor_db) ? 1 : 0;
+    if (!__syncthreads_or(below)) return;
+  }
   float* base = P.feats + (P.utt_out_row[utt] + r0) * P.ld;
   const bool vec = (P.n_out % 4 == 0) && (P.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.feats) & 15) == 0);
 

@@ -12,7 +12,7 @@ import torch
 import speech_lid_b200 as lid
 
 
-def run(name, fe, B, N, steps=None, warmup=10, dtype=torch.float32, **kw):
+def run(name, fe, B, N, steps=None, warmup=10, dtype=torch.float32, quiet_tail=False, **kw):
     if ONLY and ONLY not in name:
         return
     steps = steps or STEPS
@@ -23,6 +23,8 @@ def run(name, fe, B, N, steps=None, warmup=10, dtype=torch.float32, **kw):
     ins = []
     for _ in range(nbuf):
         w = torch.randn(B * N, device=dev, generator=g)
+        if quiet_tail:                       # last quarter of every utterance 100 dB down: AmplitudeToDB's clamp is active there
+            w.view(B, N)[:, 3 * N // 4:] *= 1e-5
         ins.append((w * 3000).clamp(-32768, 32767).to(torch.int16) if dtype == torch.int16 else w)
     outs = [torch.empty(B, plan.t_max, fe.n_out, device=dev) for _ in range(nbuf)]
     for i in range(warmup):
@@ -55,7 +57,9 @@ def main():
     mf = lid.FrontEnd(n_mels=80, n_ceps=40)
     run("cfg3: 40 MFCC of 80 mel (DCT epilogue), 512 x 4 s", mf, 512, 64000)
     ms = lid.FrontEnd(kind="melspec_db", pad=16)
-    run("default branch: MelSpectrogram + AmplitudeToDB(top_db=80), pad 16, 256 x 8 s", ms, 256, 128000)
+    run("default branch: MelSpectrogram + AmplitudeToDB(top_db=80), pad 16, 256 x 8 s (white noise: nothing to clamp)", ms, 256, 128000)
+    run("default branch, last quarter of every utterance 100 dB down (clamp active in a quarter of the row blocks)", ms, 256,
+        128000, quiet_tail=True)
     i16 = lid.FrontEnd(n_mels=80, in_dtype=torch.int16, in_scale=1.0 / 32768.0)
     run("kaldi fbank from int16 samples (2 B/sample read), 256 x 8 s", i16, 256, 128000, dtype=torch.int16)
 
