@@ -876,6 +876,7 @@ struct ApplyParams {
 
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__ ApplyParams P) {
   __shared__ float2 s_norm[kMaxMels];       // (mean, 1/(std + 1e-9))
+  __shared__ float s_lo[kMaxMels];          // -(mean - (float)mean) / (std + 1e-9): keeps x - mean accurate when std << |mean|
   __shared__ int s_masks[kMaxMasks * 4];
   const int tid = threadIdx.x;
   const int utt = blockIdx.x;
@@ -916,7 +917,7 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   if (P.clear_stats && blockIdx.y == 0 && tid < 2 * P.n_out)
     P.clear_stats[static_cast<long long>(utt) * 2 * P.n_out + tid] = 0.0;   // next launch's accumulators
   if (tid < P.n_out) {
-    float mean = 0.f, inv = 1.f;
+    float mean = 0.f, inv = 1.f, lo = 0.f;
     if (P.normalize == 1) {
       double n, sm, ss;
       if (P.utt_stats) {
@@ -933,8 +934,10 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
       var = var > 0.0 ? var : (var == var ? 0.0 : var);
       mean = static_cast<float>(mu);
       inv = static_cast<float>(1.0 / (sqrt(var) + 1e-9));
+      lo = static_cast<float>(-(mu - static_cast<double>(mean)) / (sqrt(var) + 1e-9));
     }
     s_norm[tid] = make_float2(mean, inv);
+    s_lo[tid] = lo;
   }
   if (tid < P.n_masks * 4) s_masks[tid] = P.masks[static_cast<long long>(utt) * P.n_masks * 4 + tid];
   __syncthreads();
@@ -943,20 +946,23 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
     if (!live) return;
     const int d = 4 * c;
     const float2 n0 = s_norm[d], n1 = s_norm[d + 1], n2 = s_norm[d + 2], n3 = s_norm[d + 3];
+    const float l0 = s_lo[d], l1 = s_lo[d + 1], l2 = s_lo[d + 2], l3 = s_lo[d + 3];
     bool z0 = false, z1 = false, z2 = false, z3 = false;
-    int t0[kMaxMasks], t1[kMaxMasks];
+    for (int q = 0; q < P.n_masks; ++q) {
+      const int f0 = s_masks[4 * q + 2], f1 = s_masks[4 * q + 3];
+      z0 |= (d + 0 >= f0 && d + 0 < f1);
+      z1 |= (d + 1 >= f0 && d + 1 < f1);
+      z2 |= (d + 2 >= f0 && d + 2 < f1);
+      z3 |= (d + 3 >= f0 && d + 3 < f1);
+    }
+    // time bounds of the first kRegMasks masks live in registers (every shipped config has <= 2 rows), the rest in shared
+    // memory: registers decide this kernel's occupancy
+    constexpr int kRegMasks = 4;
+    int t0[kRegMasks], t1[kRegMasks];
 #pragma unroll
-    for (int q = 0; q < kMaxMasks; ++q) {
-      t0[q] = t1[q] = 0;
-      if (q < P.n_masks) {
-        t0[q] = s_masks[4 * q];
-        t1[q] = s_masks[4 * q + 1];
-        const int f0 = s_masks[4 * q + 2], f1 = s_masks[4 * q + 3];
-        z0 |= (d + 0 >= f0 && d + 0 < f1);
-        z1 |= (d + 1 >= f0 && d + 1 < f1);
-        z2 |= (d + 2 >= f0 && d + 2 < f1);
-        z3 |= (d + 3 >= f0 && d + 3 < f1);
-      }
+    for (int q = 0; q < kRegMasks; ++q) {
+      t0[q] = (q < P.n_masks) ? s_masks[4 * q] : 0;
+      t1[q] = (q < P.n_masks) ? s_masks[4 * q + 1] : 0;
     }
     for (int rb = 0; rb < rows; rb += kU * rstep) {
       if (rb > 0) {
@@ -972,10 +978,10 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
         if (r >= rows) continue;
         float4 v = x[u];
         if (P.normalize == 1) {
-          v.x = (v.x - n0.x) * n0.y;
-          v.y = (v.y - n1.x) * n1.y;
-          v.z = (v.z - n2.x) * n2.y;
-          v.w = (v.w - n3.x) * n3.y;
+          v.x = fmaf(v.x - n0.x, n0.y, l0);      // (x - mean_hi) * inv - mean_lo * inv
+          v.y = fmaf(v.y - n1.x, n1.y, l1);
+          v.z = fmaf(v.z - n2.x, n2.y, l2);
+          v.w = fmaf(v.w - n3.x, n3.y, l3);
         } else if (P.normalize == 2) {
           v.x = fmaxf(v.x, db_floor);
           v.y = fmaxf(v.y, db_floor);
@@ -985,7 +991,8 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
         const int tf = static_cast<int>(r0) + r;
         bool zr = false;
 #pragma unroll
-        for (int q = 0; q < kMaxMasks; ++q) zr |= (tf >= t0[q] && tf < t1[q]);
+        for (int q = 0; q < kRegMasks; ++q) zr |= (tf >= t0[q] && tf < t1[q]);
+        for (int q = kRegMasks; q < P.n_masks; ++q) zr |= (tf >= s_masks[4 * q] && tf < s_masks[4 * q + 1]);
         v.x = (zr || z0) ? 0.f : v.x;
         v.y = (zr || z1) ? 0.f : v.y;
         v.z = (zr || z2) ? 0.f : v.z;
@@ -1000,7 +1007,7 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
       const int d = i - rw * P.n_out;
       float* p = base + static_cast<long long>(rw) * P.ld + d;
       float xv = *p;
-      if (P.normalize == 1) xv = (xv - s_norm[d].x) * s_norm[d].y;
+      if (P.normalize == 1) xv = fmaf(xv - s_norm[d].x, s_norm[d].y, s_lo[d]);
       else if (P.normalize == 2) xv = fmaxf(xv, db_floor);
       const int tf = static_cast<int>(r0) + rw;
       bool z = false;
