@@ -6,9 +6,10 @@ CPU fallback: importing works anywhere, computing needs the built ``liblidfe.so`
 """
 from . import _lib, tables
 from ._lib import LIB_PATH, LidfeError, load_library
+from .collate import DeviceCollate, collate_host_part
 from .frontend import FrontEnd, Plan
 from .sharding import allreduce_stats, finalize_stats, lpt_partition
 from .specaug import draw_masks
 
-__all__ = ["FrontEnd", "Plan", "draw_masks", "lpt_partition", "allreduce_stats", "finalize_stats",
+__all__ = ["FrontEnd", "Plan", "DeviceCollate", "collate_host_part", "draw_masks", "lpt_partition", "allreduce_stats", "finalize_stats",
            "load_library", "LidfeError", "LIB_PATH", "tables"]

@@ -519,3 +519,35 @@ def test_int16_pcm_host_pipeline(fe, lid):
     for i, w in enumerate(pcm):
         want = O.kaldi_fbank(O.normalize_wav(w.float() * (1.0 / 32768.0)))
         _check_fbank(host_out[i, :want.shape[0]], want, "pcm utt %d" % i)
+
+
+def test_device_collate_matches_reference_collate(lid, golden_dir):
+    """DeviceCollate on ``type: wav`` items == the reference's collate on ``type: mel`` items
+    (ref: lid/raw_datasets.py:345-365; golden collate.npz was produced by the reference's wav2mel + pad_sequence)."""
+    z = np.load(os.path.join(golden_dir, "collate.npz"))
+    lang2index = {"Persian": 0, "Swahili": 1, "Vietnamese": 2}
+    g = torch.Generator().manual_seed(8)
+    batch = []
+    for i, lang in enumerate(("Vietnamese", "Persian", "Swahili")):
+        batch.append((torch.from_numpy(z["in_%d" % i]), torch.randint(1, 30, (5 + 3 * i,), generator=g), "f%d.wav" % i, lang))
+    fe = lid.FrontEnd(n_mels=80)
+    wavs, texts, wav_percents, text_percents, paths, langs = lid.DeviceCollate(fe, lang2index)(batch)
+    want = torch.from_numpy(z["wavs"])
+    assert wavs.is_cuda and wavs.shape == want.shape
+    for i in range(3):
+        T = O.kaldi_num_frames(batch[i][0].shape[-1])
+        _check_fbank(wavs[i, :T].cpu(), want[i, :T], "collate utt %d" % i)
+        assert torch.all(wavs[i, T:] == 0)
+    assert torch.allclose(wav_percents, torch.from_numpy(z["wav_percents"]), atol=1e-7) and wav_percents.dtype == torch.float32
+    assert texts.shape == (3, 11) and torch.equal(langs, torch.LongTensor([2, 0, 1])) and paths == ["f0.wav", "f1.wav", "f2.wav"]
+    assert torch.allclose(text_percents, torch.FloatTensor([5 / 11, 8 / 11, 1.0]))
+    # training flavour: the masks come from torch's default generator, like spectrogram_augment
+    torch.manual_seed(42)
+    tw = lid.DeviceCollate(fe, lang2index, train=True, mask_times=2)(batch)[0].cpu()
+    torch.manual_seed(42)
+    frames = [O.kaldi_num_frames(b[0].shape[-1]) for b in batch]
+    m = lid.draw_masks(frames, 80, 0.05, 27, 2)
+    for i in range(3):
+        bounds = [tuple(int(v) for v in m[i, q]) for q in range(2)]
+        ref = O.apply_mask_bounds(wavs[i, :frames[i]].cpu().T.unsqueeze(0), bounds)[0].T
+        assert torch.equal(tw[i, :frames[i]], ref)

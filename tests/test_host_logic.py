@@ -271,3 +271,19 @@ def test_graft_entry_build_passes():
     own export / ABI-version checks."""
     import __graft_entry__ as g
     g.build()
+
+
+def test_collate_host_part_matches_reference_semantics():
+    """texts / text_percents / paths / langs exactly as MergedDataset.collate_fn builds them
+    (ref: lid/raw_datasets.py:353-365), restated inline."""
+    g = torch.Generator().manual_seed(3)
+    lang2index = {"Persian": 0, "Swahili": 1, "Vietnamese": 2}
+    batch = []
+    for i, (n, L, lang) in enumerate(((16000, 7, "Swahili"), (9000, 12, "Persian"), (12345, 1, "Vietnamese"))):
+        batch.append((torch.randn(1, n, generator=g), torch.randint(1, 40, (L,), generator=g), "utt%d.wav" % i, lang))
+    texts, text_percents, paths, langs = lid.collate_host_part(batch, lang2index)
+    want_texts = torch.nn.utils.rnn.pad_sequence([b[1] for b in batch]).transpose(1, 0)
+    assert torch.equal(texts, want_texts) and texts.shape == (3, 12) and texts.dtype == torch.int64
+    assert torch.equal(text_percents, torch.FloatTensor([b[1].shape[-1] / (want_texts.shape[1] + 1e-9) for b in batch]))
+    assert paths == ["utt0.wav", "utt1.wav", "utt2.wav"]
+    assert torch.equal(langs, torch.LongTensor([1, 0, 2])) and langs.dtype == torch.int64
