@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LIDFE_ABI_VERSION 3
+#define LIDFE_ABI_VERSION 4
 
 /* error codes (negative) */
 #define LIDFE_OK 0
@@ -219,6 +219,21 @@ int lidfe_profile_set_stride(lidfe_handle h, int stride);
 int lidfe_profile_end(lidfe_handle h, float* ms_host, int capacity, int* n_out);
 
 /* -- misc ----------------------------------------------------------------------------------------- */
+/* -- polyphase sinc resampler: the DataProcessor in front of the models ------------------------------
+ * Replaces torchaudio.transforms.Resample(orig_freq, 16000) as constructed by the reference for 22.05 and 44.1 kHz
+ * input (ref: lid/ConformerLangModel.py:131-169 -> ta: transforms/_transforms.py Resample, functional/functional.py
+ * _get_sinc_resample_kernel / _apply_sinc_resample_kernel).  kernel_host[new/g][taps] is the FIR bank exactly as
+ * torchaudio builds it (g = gcd, taps = 2 * width + orig / g); the caller computes it with the same torch expressions
+ * (speech_lid_b200.tables.sinc_resample_kernel).  Output sample j of an utterance of n samples exists for
+ * j < ceil(new * n / orig); out_len_dev[i] may ask for fewer (the reference crops to int(percent * padded length)). */
+typedef struct lidfe_resampler_s* lidfe_resampler;
+int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, const float* kernel_host, int taps, int width);
+int lidfe_resampler_destroy(lidfe_resampler r);
+long long lidfe_resample_out_len(lidfe_resampler r, long long n_in);
+int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long long* in_off_dev, const long long* in_len_dev,
+                   float* out_dev, const long long* out_off_dev, const long long* out_len_dev, long long max_out_len,
+                   void* stream);
+
 const char* lidfe_strerror(int rc);
 int lidfe_abi_version(void);
 /* kernels launched by this library in this process so far (bench.py reports it as gpu_launches) */

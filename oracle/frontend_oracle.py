@@ -361,3 +361,52 @@ def synth_speechlike(n: int, seed: int) -> torch.Tensor:
     pink = torch.fft.irfft(spec, n=n)
     pink *= (x.std() / pink.std()) * 10 ** (-30 / 20)
     return normalize_wav((x + pink).float().unsqueeze(0))
+
+
+# --------------------------------------------------------------------------------------
+# f4  resampling DataProcessor                          ref: lid/ConformerLangModel.py:131-178
+#                                                       ta: functional/functional.py _get_sinc_resample_kernel,
+#                                                           _apply_sinc_resample_kernel; transforms Resample
+# --------------------------------------------------------------------------------------
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    import math
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=None)[:, None, None] / new + idx
+    t *= base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * (base_freq / orig)
+    return kernels.to(torch.float32), width, orig, new
+
+
+def resample(wav: torch.Tensor, orig_freq: int, new_freq: int = 16000) -> torch.Tensor:
+    """(N,) or (B, N) fp32 -> resampled, as torchaudio.transforms.Resample(orig_freq, new_freq) with its defaults."""
+    if orig_freq == new_freq:
+        return wav
+    kernel, width, orig, new = sinc_resample_kernel(orig_freq, new_freq)
+    shape = wav.shape
+    x = wav.reshape(-1, shape[-1])
+    length = x.shape[1]
+    x = torch.nn.functional.pad(x, (width, width + orig))
+    y = torch.nn.functional.conv1d(x[:, None], kernel, stride=orig)
+    y = y.transpose(1, 2).reshape(x.shape[0], -1)
+    target = int(torch.ceil(torch.as_tensor(new * length / orig)).long())
+    return y[..., :target].reshape(shape[:-1] + (target,))
+
+
+def data_processor(x: Sequence[torch.Tensor], sample_rate: int) -> Sequence[torch.Tensor]:
+    """DataProcessor.forward (ref: lid/ConformerLangModel.py:146-169)."""
+    if sample_rate not in (22050, 44100):
+        return x
+    longest = max(int(w.shape[-1]) for w in x)
+    percent = [int(w.shape[-1]) / longest for w in x]
+    padded = torch.nn.utils.rnn.pad_sequence(list(x), batch_first=True)
+    y = resample(padded, sample_rate, 16000)
+    lens = [int(p * y.shape[-1]) for p in percent]
+    return [y[i, :lens[i]] for i in range(len(lens))]

@@ -8,8 +8,9 @@ from . import _lib, tables
 from ._lib import LIB_PATH, LidfeError, load_library
 from .collate import DeviceCollate, collate_host_part
 from .frontend import FrontEnd, Plan
+from .resample import Resampler
 from .sharding import allreduce_stats, finalize_stats, lpt_partition
 from .specaug import draw_masks
 
-__all__ = ["FrontEnd", "Plan", "DeviceCollate", "collate_host_part", "draw_masks", "lpt_partition", "allreduce_stats", "finalize_stats",
+__all__ = ["FrontEnd", "Plan", "DeviceCollate", "collate_host_part", "Resampler", "draw_masks", "lpt_partition", "allreduce_stats", "finalize_stats",
            "load_library", "LidfeError", "LIB_PATH", "tables"]

@@ -17,13 +17,14 @@ IN_F32, IN_I16 = 0, 1
 CMVN_NONE, CMVN_PER_UTT, CMVN_APPLY_GLOBAL, CMVN_ACCUM_GLOBAL, POST_TOPDB = 0, 1, 2, 3, 4
 FRAMING_KALDI, FRAMING_CENTER = 0, 1
 LOG_NATURAL, LOG_DB10 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = (
     "lidfe_create", "lidfe_destroy", "lidfe_num_frames", "lidfe_out_dim", "lidfe_plan_create",
     "lidfe_plan_destroy", "lidfe_plan_total_frames", "lidfe_plan_num_tiles", "lidfe_plan_frames",
     "lidfe_featurize", "lidfe_cmvn_apply", "lidfe_wave_stages", "lidfe_wave_stages_i16", "lidfe_mask_apply", "lidfe_strerror",
     "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_profile_set_stride", "lidfe_mel_plan", "lidfe_mel_plan_expand",
+    "lidfe_resampler_create", "lidfe_resampler_destroy", "lidfe_resample_out_len", "lidfe_resample",
 )
 
 
@@ -93,6 +94,14 @@ def load_library() -> C.CDLL:
     lib.lidfe_mel_plan.restype = i32
     lib.lidfe_mel_plan_expand.argtypes = [i32, vp, vp]
     lib.lidfe_mel_plan_expand.restype = i32
+    lib.lidfe_resampler_create.argtypes = [C.POINTER(vp), i32, i32, vp, i32, i32]
+    lib.lidfe_resampler_create.restype = i32
+    lib.lidfe_resampler_destroy.argtypes = [vp]
+    lib.lidfe_resampler_destroy.restype = i32
+    lib.lidfe_resample_out_len.argtypes = [vp, ll]
+    lib.lidfe_resample_out_len.restype = ll
+    lib.lidfe_resample.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, ll, vp]
+    lib.lidfe_resample.restype = i32
     lib.lidfe_wave_stages_i16.argtypes = [vp, vp, vp, f32, vp, i32, f32, vp, f32, vp]
     lib.lidfe_wave_stages_i16.restype = i32
     lib.lidfe_strerror.argtypes = [i32]

@@ -884,4 +884,69 @@ int lidfe_wave_stages_i16(lidfe_handle h, lidfe_plan p, const short* pcm_in_dev,
   return launch_wave(h, p, pcm_in_dev, 1, in_scale, wav_out_dev, normalize, dither, noise_dev, preemph, stream);
 }
 
+// ---- polyphase sinc resampler (row f4) ---------------------------------------------------------------------------
+struct lidfe_resampler_s {
+  int orig, nw, K, K4, width;      // frequencies already divided by their gcd
+  float* d_wt;                     // [K4][nw]
+};
+
+int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, const float* kernel_host, int taps, int width) {
+  if (!out || !kernel_host) return LIDFE_E_NULL;
+  *out = nullptr;
+  if (orig_freq <= 0 || new_freq <= 0 || taps <= 0 || width < 0 || taps > 8192) return LIDFE_E_ARG;
+  int a = orig_freq, b = new_freq;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int orig = orig_freq / a, nw = new_freq / a;
+  if (taps != 2 * width + orig) return LIDFE_E_ARG;     // ta: functional/functional.py _get_sinc_resample_kernel
+  lidfe_resampler_s* r = new (std::nothrow) lidfe_resampler_s();
+  if (!r) return LIDFE_E_NOMEM;
+  r->orig = orig; r->nw = nw; r->K = taps; r->K4 = (taps + 3) & ~3; r->width = width; r->d_wt = nullptr;
+  std::vector<float> wt(static_cast<size_t>(r->K4) * nw, 0.f);
+  for (int p = 0; p < nw; ++p)
+    for (int k = 0; k < taps; ++k) wt[static_cast<size_t>(k) * nw + p] = kernel_host[static_cast<size_t>(p) * taps + k];
+  cudaError_t e = upload(&r->d_wt, wt.data(), wt.size());
+  const size_t smem = static_cast<size_t>(kRsFrames) * r->K4 * sizeof(float);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(r->d_wt);
+    delete r;
+    return static_cast<int>(e);
+  }
+  *out = r;
+  return LIDFE_OK;
+}
+
+int lidfe_resampler_destroy(lidfe_resampler r) {
+  if (!r) return LIDFE_E_NULL;
+  cudaFree(r->d_wt);
+  delete r;
+  return LIDFE_OK;
+}
+
+long long lidfe_resample_out_len(lidfe_resampler r, long long n_in) {
+  if (!r || n_in < 0) return 0;
+  return (static_cast<long long>(r->nw) * n_in + r->orig - 1) / r->orig;      // ceil(new * n / orig)
+}
+
+int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long long* in_off_dev, const long long* in_len_dev,
+                   float* out_dev, const long long* out_off_dev, const long long* out_len_dev, long long max_out_len,
+                   void* stream) {
+  if (!r || !in_dev || !in_off_dev || !in_len_dev || !out_dev || !out_off_dev || !out_len_dev) return LIDFE_E_NULL;
+  if (B <= 0 || max_out_len < 0) return LIDFE_E_ARG;
+  if (max_out_len == 0) return LIDFE_OK;
+  ResampleParams P;
+  P.in = in_dev; P.in_off = in_off_dev; P.in_len = in_len_dev;
+  P.out = out_dev; P.out_off = out_off_dev; P.out_len = out_len_dev;
+  P.wt = r->d_wt; P.orig = r->orig; P.nw = r->nw; P.K = r->K; P.K4 = r->K4; P.width = r->width;
+  const long long frames = (max_out_len + r->nw - 1) / r->nw;
+  const long long gx = (frames + kRsFrames - 1) / kRsFrames;
+  if (gx > 0x7fffffffLL || B > 65535) return LIDFE_E_ARG;
+  const size_t smem = static_cast<size_t>(kRsFrames) * r->K4 * sizeof(float);
+  resample_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(B)), kRsThreads, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  g_launches.fetch_add(1);
+  CU_TRY(cudaGetLastError());
+  return LIDFE_OK;
+}
+
 }  // extern "C"

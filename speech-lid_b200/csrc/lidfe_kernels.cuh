@@ -1313,4 +1313,70 @@ __global__ void __cluster_dims__(kWaveCluster, 1, 1) __launch_bounds__(kWaveThre
   cluster.sync();                                        // no CTA exits while a peer may still read its partials
 }
 
+// ------------------------------------------------------------------------------------------------
+// Polyphase sinc resampler (row f4: the DataProcessor in front of the models, ref: lid/ConformerLangModel.py:131-169 ->
+// ta: functional/functional.py _apply_sinc_resample_kernel).  With orig / new reduced by their gcd, output sample
+// i * new + p is  sum_k W[p][k] * xpad[i * orig + k],  xpad = x with `width` zeros in front and width + orig behind:
+// a GEMM [new x K] . [K x frames] whose right-hand columns are overlapping windows of the waveform.  One CTA computes
+// 16 consecutive frames i of one utterance for all phases p: the 16 windows sit in shared memory (one row each, so a
+// 4-tap LDS.128 is a pure broadcast), every thread owns one phase and 16 accumulators, and the weights stream from the
+// L2-resident transposed table [K][new] with coalesced loads -- 128 FFMA per 16 LDS.128 and 4 LDG.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRsFrames = 16;
+constexpr int kRsThreads = 160;
+
+struct ResampleParams {
+  const float* in;              // packed waveforms
+  const long long* in_off;      // [B]
+  const long long* in_len;      // [B]
+  float* out;
+  const long long* out_off;     // [B]
+  const long long* out_len;     // [B] samples to write (<= ceil(new * in_len / orig))
+  const float* wt;              // [K4][new] transposed kernel, rows K..K4-1 zero
+  int orig, nw, K, K4, width;
+};
+
+__global__ void __launch_bounds__(kRsThreads) resample_kernel(const __grid_constant__ ResampleParams P) {
+  extern __shared__ __align__(16) float rs_x[];           // [kRsFrames][K4]
+  const int b = blockIdx.y;
+  const long long n_in = P.in_len[b], n_out = P.out_len[b];
+  const long long f0 = static_cast<long long>(blockIdx.x) * kRsFrames;
+  if (f0 * P.nw >= n_out) return;
+  const float* x = P.in + P.in_off[b];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kRsFrames * P.K4; i += kRsThreads) {
+    const int f = i / P.K4, k = i - f * P.K4;
+    const long long j = (f0 + f) * P.orig + k - P.width;   // index into the unpadded waveform
+    rs_x[i] = (k < P.K && j >= 0 && j < n_in) ? x[j] : 0.f;
+  }
+  __syncthreads();
+  float* y = P.out + P.out_off[b];
+  for (int pc = 0; pc < P.nw; pc += kRsThreads) {
+    const int p = pc + tid;
+    if (p >= P.nw) continue;
+    float acc[kRsFrames];
+#pragma unroll
+    for (int f = 0; f < kRsFrames; ++f) acc[f] = 0.f;
+    const float* w = P.wt + p;
+#pragma unroll 1
+    for (int k = 0; k < P.K4; k += 4) {
+      const float w0 = __ldg(w + static_cast<long long>(k) * P.nw), w1 = __ldg(w + static_cast<long long>(k + 1) * P.nw);
+      const float w2 = __ldg(w + static_cast<long long>(k + 2) * P.nw), w3 = __ldg(w + static_cast<long long>(k + 3) * P.nw);
+#pragma unroll
+      for (int f = 0; f < kRsFrames; ++f) {
+        const float4 xv = *reinterpret_cast<const float4*>(rs_x + f * P.K4 + k);
+        acc[f] = fmaf(w0, xv.x, acc[f]);
+        acc[f] = fmaf(w1, xv.y, acc[f]);
+        acc[f] = fmaf(w2, xv.z, acc[f]);
+        acc[f] = fmaf(w3, xv.w, acc[f]);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kRsFrames; ++f) {
+      const long long o = (f0 + f) * P.nw + p;
+      if (o < n_out) y[o] = acc[f];
+    }
+  }
+}
+
 }  // namespace lidfe

@@ -94,3 +94,24 @@ def htk_mel_banks(n_mels: int, fft_len: int, sample_rate: int = 16000, f_min: fl
     rising = slopes[:, 2:] / f_diff[1:]
     fb = torch.max(torch.zeros(1), torch.min(falling, rising))     # (n_freqs, n_mels)
     return fb.t().contiguous()
+
+
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """Hann-windowed sinc FIR bank of ``torchaudio.transforms.Resample(orig_freq, new_freq)`` with its defaults, built
+    with the same torch expressions in float64 and cast to float32 (ta: functional/functional.py
+    _get_sinc_resample_kernel).  Returns ``(kernel (new/g, 2*width + orig/g) float32, width)``, g = gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(orig, new)
+    base_freq *= rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=None)[:, None, None] / new + idx
+    t *= base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * scale
+    return kernels.to(dtype=torch.float32)[:, 0, :].contiguous(), width

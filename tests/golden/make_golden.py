@@ -116,6 +116,23 @@ def main():
     ct["wav_percents"] = np.array([r.shape[0] / wavs.shape[1] for r in rows], dtype=np.float32)
     np.savez_compressed(os.path.join(HERE, "collate.npz"), **ct)
 
+    # ---- resampling DataProcessor (row f4): the reference's own module on ragged 44.1 / 22.05 kHz batches ----------
+    rs = {}
+    sys.modules.setdefault("torchmetrics", types.ModuleType("torchmetrics"))
+    for n in ("WER", "CharErrorRate", "Accuracy", "WordErrorRate"):
+        setattr(sys.modules["torchmetrics"], n, type(n, (), {"__init__": lambda self, *a, **k: None}))
+    sys.path.insert(0, "/root/reference/lid")
+    from lid.ConformerLangModel import DataProcessor            # noqa: E402  (ref: lid/ConformerLangModel.py:131-178)
+    dp = DataProcessor(16000)
+    g = torch.Generator().manual_seed(61)
+    for rate, lens in ((44100, (22050, 9001, 13333)), (22050, (11025, 4000, 7777, 300))):
+        xs = [torch.randn(n, generator=g) * 0.3 for n in lens]
+        ys = dp(xs, rate)
+        for i, (x, y) in enumerate(zip(xs, ys)):
+            rs["in_%d_%d" % (rate, i)] = x.numpy()
+            rs["out_%d_%d" % (rate, i)] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "resample.npz"), **rs)
+
     with open(os.path.join(HERE, "VERSIONS.txt"), "w") as f:
         f.write("generated by tests/golden/make_golden.py from /root/reference (kouyt5/speech-lid)\n")
         for k, v in meta.items():

@@ -83,7 +83,7 @@ def _check_fbank(got, want, what, all_bins=False):
 
 def test_extension_is_loaded(lid):
     lib = lid.load_library()
-    assert lib.lidfe_abi_version() == 3
+    assert lib.lidfe_abi_version() == lid._lib.ABI_VERSION
     with open("/proc/self/maps") as f:
         assert "liblidfe.so" in f.read()
 
@@ -551,3 +551,36 @@ def test_device_collate_matches_reference_collate(lid, golden_dir):
         bounds = [tuple(int(v) for v in m[i, q]) for q in range(2)]
         ref = O.apply_mask_bounds(wavs[i, :frames[i]].cpu().T.unsqueeze(0), bounds)[0].T
         assert torch.equal(tw[i, :frames[i]], ref)
+
+
+def test_resampler_matches_reference_data_processor(lid, golden_dir):
+    """Row f4: the polyphase resampling kernel against the reference's DataProcessor outputs (golden) and against the
+    oracle for other rate pairs (down- and up-sampling).  fp32 FIR of up to 475 taps in a different summation order:
+    1e-5 absolute on signals of unit scale."""
+    z = np.load(os.path.join(golden_dir, "resample.npz"))
+    for rate, n in ((44100, 3), (22050, 4)):
+        rs = lid.Resampler(rate, 16000)
+        xs = [torch.from_numpy(z["in_%d_%d" % (rate, i)]) for i in range(n)]
+        ys = rs.data_processor(xs)
+        for i in range(n):
+            want = torch.from_numpy(z["out_%d_%d" % (rate, i)])
+            assert ys[i].is_cuda and ys[i].shape == want.shape, (rate, i, ys[i].shape, want.shape)
+            assert torch.allclose(ys[i].cpu(), want, rtol=0, atol=1e-5), (rate, i, (ys[i].cpu() - want).abs().max())
+    g = torch.Generator().manual_seed(5)
+    for orig in (48000, 8000, 11025, 44100):
+        rs = lid.Resampler(orig, 16000)
+        xs = [torch.randn(n, generator=g) for n in (orig // 2 + 17, 999, 1)]
+        ys = rs.resample_list(xs)
+        for x, y in zip(xs, ys):
+            want = O.resample(x, orig, 16000)
+            assert y.shape == want.shape == (rs.out_len(x.numel()),)
+            assert torch.allclose(y.cpu(), want, rtol=0, atol=1e-5), (orig, x.numel(), (y.cpu() - want).abs().max())
+    same = lid.Resampler(16000, 16000).resample_list([xs[0]])[0]
+    assert torch.equal(same.cpu(), xs[0])
+    # resampled audio feeds the front-end: 44.1 kHz in, 16 kHz fbank out
+    rs = lid.Resampler(44100, 16000)
+    x = torch.randn(44100, generator=g)
+    y = rs.resample_list([x])[0]
+    feats, _ = lid.FrontEnd(n_mels=80).featurize([y])
+    want = O.kaldi_fbank(O.resample(x, 44100, 16000))
+    _check_fbank(feats[0].cpu(), want, "resample -> fbank")

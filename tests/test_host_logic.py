@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, "liblidfe.so does not export %s" % missing
     assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
-    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 4
 
 
 def _cfg(**kw):
@@ -287,3 +287,14 @@ def test_collate_host_part_matches_reference_semantics():
     assert torch.equal(text_percents, torch.FloatTensor([b[1].shape[-1] / (want_texts.shape[1] + 1e-9) for b in batch]))
     assert paths == ["utt0.wav", "utt1.wav", "utt2.wav"]
     assert torch.equal(langs, torch.LongTensor([1, 0, 2])) and langs.dtype == torch.int64
+
+
+def test_resample_tables_bit_identical_to_torchaudio():
+    import math
+    import torchaudio.functional.functional as TF
+    for orig in (44100, 22050, 48000, 8000, 11025):
+        k, w = tables.sinc_resample_kernel(orig, 16000)
+        kr, wr = TF._get_sinc_resample_kernel(orig, 16000, math.gcd(orig, 16000))
+        assert w == wr and torch.equal(k, kr[:, 0, :])
+        ko, wo, _, _ = O.sinc_resample_kernel(orig, 16000)
+        assert wo == w and torch.equal(ko[:, 0, :], k)

@@ -139,3 +139,18 @@ def test_cmvn_definition():
     mean, std = O.cmvn_finalize(O.cmvn_stats(feats))
     allf = torch.cat(feats).double()
     assert torch.allclose(mean, allf.mean(0), atol=1e-10) and torch.allclose(std, allf.std(0), atol=1e-9)
+
+
+def test_oracle_data_processor_matches_reference_resampling(golden_dir):
+    """Row f4: DataProcessor.forward of the reference (ref: lid/ConformerLangModel.py:131-178) on ragged 44.1 / 22.05 kHz
+    batches; the oracle restates torchaudio's polyphase sinc resampler and the reference's crop rule."""
+    z = np.load(os.path.join(golden_dir, "resample.npz"))
+    for rate, n in ((44100, 3), (22050, 4)):
+        xs = [torch.from_numpy(z["in_%d_%d" % (rate, i)]) for i in range(n)]
+        ys = O.data_processor(xs, rate)
+        for i in range(n):
+            want = torch.from_numpy(z["out_%d_%d" % (rate, i)])
+            assert ys[i].shape == want.shape, (rate, i)
+            assert torch.allclose(ys[i], want, rtol=0, atol=1e-6), (rate, i, (ys[i] - want).abs().max())
+    x = torch.randn(2, 3000)
+    assert torch.equal(O.data_processor([x[0], x[1]], 16000)[0], x[0])         # other rates pass through untouched
