@@ -62,6 +62,48 @@ def main():
         128000, quiet_tail=True)
     i16 = lid.FrontEnd(n_mels=80, in_dtype=torch.int16, in_scale=1.0 / 32768.0)
     run("kaldi fbank from int16 samples (2 B/sample read), 256 x 8 s", i16, 256, 128000, dtype=torch.int16)
+    run_resample("resample 44.1 kHz -> 16 kHz (475-tap polyphase FIR), 256 x 8 s", 44100, 256, 8.0)
+    run_resample("resample 22.05 kHz -> 16 kHz (459-tap polyphase FIR), 256 x 8 s", 22050, 256, 8.0)
+
+
+def run_resample(name, orig, B, seconds, steps=None, warmup=5):
+    if ONLY and ONLY not in name:
+        return
+    steps = steps or STEPS
+    rs = lid.Resampler(orig, 16000)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = int(orig * seconds)
+    wavs = [torch.randn(n, device="cuda", generator=g) for _ in range(B)]
+    for _ in range(warmup):
+        rs.resample_list(wavs)
+    # time the kernel itself: the list API concatenates its inputs first, which is not part of the resampling
+    import ctypes as C
+    packed = torch.cat(wavs)
+    n_out = rs.out_len(n)
+    stride = (n_out + 3) // 4 * 4
+    out = torch.empty(B * stride, device="cuda")
+    tab = torch.tensor([[i * n for i in range(B)], [n] * B, [i * stride for i in range(B)], [n_out] * B], dtype=torch.int64,
+                       device="cuda")
+    lib = lid.load_library()
+
+    def launch():
+        rc = lib.lidfe_resample(rs.handle, B, packed.data_ptr(), tab[0].data_ptr(), tab[1].data_ptr(), out.data_ptr(),
+                                tab[2].data_ptr(), tab[3].data_ptr(), n_out, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+    for _ in range(warmup):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    taps = rs.kernel.shape[1]
+    print(json.dumps({"config": name, "utterances": B, "in_samples": n, "out_samples": n_out, "taps": taps,
+                      "ms_per_step": round(ms, 5), "audio_s_per_s": round(B * seconds / (ms * 1e-3), 1),
+                      "fp32_tflops": round(2.0 * B * n_out * taps / (ms * 1e-3) / 1e12, 2)}), flush=True)
 
 
 if __name__ == "__main__":
