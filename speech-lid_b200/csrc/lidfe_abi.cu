@@ -887,7 +887,9 @@ int lidfe_wave_stages_i16(lidfe_handle h, lidfe_plan p, const short* pcm_in_dev,
 // ---- polyphase sinc resampler (row f4) ---------------------------------------------------------------------------
 struct lidfe_resampler_s {
   int orig, nw, K, K4, width;      // frequencies already divided by their gcd
-  float* d_wt;                     // [K4][nw]
+  float* d_wt;                     // [K4][nw] transposed bank (FP32 kernel)
+  int K8, KS, use_mma;             // tensor-core path (nw % 16 == 0): taps padded to 8, shared-memory row stride
+  float* d_w;                      // [nw][K8] row-major bank (tensor-core kernel)
 };
 
 int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, const float* kernel_host, int taps, int width) {
@@ -907,9 +909,25 @@ int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, co
   cudaError_t e = upload(&r->d_wt, wt.data(), wt.size());
   const size_t smem = static_cast<size_t>(kRsFrames) * r->K4 * sizeof(float);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  r->K8 = (taps + 7) & ~7;
+  r->KS = r->K8 + 4;
+  r->d_w = nullptr;
+  const char* ev = getenv("LIDFE_RESAMPLE_MMA");
+  r->use_mma = (nw % 16 == 0) && !(ev && ev[0] == '0') &&
+               static_cast<size_t>(kRmFrames) * r->KS * sizeof(float) <= 200 * 1024;
+  if (e == cudaSuccess && r->use_mma) {
+    std::vector<float> w(static_cast<size_t>(nw) * r->K8, 0.f);
+    for (int p = 0; p < nw; ++p)
+      for (int k = 0; k < taps; ++k) w[static_cast<size_t>(p) * r->K8 + k] = kernel_host[static_cast<size_t>(p) * taps + k];
+    e = upload(&r->d_w, w.data(), w.size());
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(resample_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(static_cast<size_t>(kRmFrames) * r->KS * sizeof(float)));
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     cudaFree(r->d_wt);
+    cudaFree(r->d_w);
     delete r;
     return static_cast<int>(e);
   }
@@ -920,6 +938,7 @@ int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, co
 int lidfe_resampler_destroy(lidfe_resampler r) {
   if (!r) return LIDFE_E_NULL;
   cudaFree(r->d_wt);
+  cudaFree(r->d_w);
   delete r;
   return LIDFE_OK;
 }
@@ -935,6 +954,20 @@ int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long lon
   if (!r || !in_dev || !in_off_dev || !in_len_dev || !out_dev || !out_off_dev || !out_len_dev) return LIDFE_E_NULL;
   if (B <= 0 || max_out_len < 0) return LIDFE_E_ARG;
   if (max_out_len == 0) return LIDFE_OK;
+  if (r->use_mma) {
+    ResampleMmaParams M;
+    M.in = in_dev; M.in_off = in_off_dev; M.in_len = in_len_dev;
+    M.out = out_dev; M.out_off = out_off_dev; M.out_len = out_len_dev;
+    M.w = r->d_w; M.orig = r->orig; M.nw = r->nw; M.K = r->K; M.K8 = r->K8; M.KS = r->KS; M.width = r->width;
+    const long long fr = (max_out_len + r->nw - 1) / r->nw;
+    const long long gxm = (fr + kRmFrames - 1) / kRmFrames;
+    if (gxm > 0x7fffffffLL || B > 65535) return LIDFE_E_ARG;
+    resample_mma_kernel<<<dim3(static_cast<unsigned>(gxm), static_cast<unsigned>(B)), kRmWarps * 32,
+                          static_cast<size_t>(kRmFrames) * r->KS * sizeof(float), static_cast<cudaStream_t>(stream)>>>(M);
+    g_launches.fetch_add(1);
+    CU_TRY(cudaGetLastError());
+    return LIDFE_OK;
+  }
   ResampleParams P;
   P.in = in_dev; P.in_off = in_off_dev; P.in_len = in_len_dev;
   P.out = out_dev; P.out_off = out_off_dev; P.out_len = out_len_dev;

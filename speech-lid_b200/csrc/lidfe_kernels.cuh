@@ -1379,4 +1379,105 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same resampler on the tensor cores: the GEMM [new x K] . [K x frames] as 3xTF32 (hi*hi + hi*lo + lo*hi with
+// hi = tf32(v), lo = v - hi: ~21 mantissa bits per product, fp32 accumulation) with mma.sync.m16n8k8.  A CTA of 5 warps
+// computes 32 frames of one utterance for all phases: the 32 windows sit in shared memory as fp32 (row stride = 4 mod 32
+// floats, so the B-fragment loads -- lane (g, tig) reads window g, tap tig -- are conflict free), every warp takes two
+// 16-phase M tiles at a time against the four 8-frame N tiles, loads its A fragments straight from the L2-resident
+// fp32 table [new][K8] and splits both operands in registers.  Used when new % 16 == 0 (160 and 320 for the
+// reference's two rates); the FP32 kernel above remains the general path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRmFrames = 32;
+constexpr int kRmWarps = 5;
+
+struct ResampleMmaParams {
+  const float* in;
+  const long long* in_off;
+  const long long* in_len;
+  float* out;
+  const long long* out_off;
+  const long long* out_len;
+  const float* w;               // [nw][K8] row-major fp32, taps K..K8-1 zero
+  int orig, nw, K, K8, KS, width;   // KS = shared-memory row stride (K8 + 4)
+};
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  lo = __float_as_uint(v - __uint_as_float(hi));          // the MMA reads its top 19 bits
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kRmWarps * 32) resample_mma_kernel(const __grid_constant__ ResampleMmaParams P) {
+  extern __shared__ __align__(16) float rm_x[];           // [kRmFrames][KS]
+  const int b = blockIdx.y;
+  const long long n_in = P.in_len[b], n_out = P.out_len[b];
+  const long long f0 = static_cast<long long>(blockIdx.x) * kRmFrames;
+  if (f0 * P.nw >= n_out) return;
+  const float* x = P.in + P.in_off[b];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  for (int i = tid; i < kRmFrames * P.KS; i += kRmWarps * 32) {
+    const int f = i / P.KS, k = i - f * P.KS;
+    const long long j = (f0 + f) * P.orig + k - P.width;
+    rm_x[i] = (k < P.K && j >= 0 && j < n_in) ? x[j] : 0.f;
+  }
+  __syncthreads();
+  float* y = P.out + P.out_off[b];
+  const int m_tiles = P.nw >> 4;
+  for (int mt0 = warp * 2; mt0 < m_tiles; mt0 += kRmWarps * 2) {       // two M tiles (32 phases) per pass
+    const int n_m = (mt0 + 1 < m_tiles) ? 2 : 1;
+    float acc[2][kRmFrames / 8][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < kRmFrames / 8; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.f;
+    const float* w0 = P.w + static_cast<long long>(mt0 * 16 + g) * P.K8 + tig;       // rows g / g+8 of M tile mt0
+    const float* w1 = w0 + static_cast<long long>(n_m == 2 ? 16 : 0) * P.K8;          // (a missing second tile aliases the first)
+    const float* xr = rm_x + g * P.KS + tig;                                            // window g of N tile 0
+#pragma unroll 1
+    for (int k = 0; k < P.K8; k += 8) {
+      uint32_t ah[2][4], al[2][4];
+      {
+        const float a0 = __ldg(w0 + k), a1 = __ldg(w0 + 8 * P.K8 + k), a2 = __ldg(w0 + k + 4), a3 = __ldg(w0 + 8 * P.K8 + k + 4);
+        split_tf32(a0, ah[0][0], al[0][0]); split_tf32(a1, ah[0][1], al[0][1]);
+        split_tf32(a2, ah[0][2], al[0][2]); split_tf32(a3, ah[0][3], al[0][3]);
+        const float c0 = __ldg(w1 + k), c1 = __ldg(w1 + 8 * P.K8 + k), c2 = __ldg(w1 + k + 4), c3 = __ldg(w1 + 8 * P.K8 + k + 4);
+        split_tf32(c0, ah[1][0], al[1][0]); split_tf32(c1, ah[1][1], al[1][1]);
+        split_tf32(c2, ah[1][2], al[1][2]); split_tf32(c3, ah[1][3], al[1][3]);
+      }
+#pragma unroll
+      for (int n = 0; n < kRmFrames / 8; ++n) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(xr[n * 8 * P.KS + k], bh0, bl0);            // (tap k + tig, frame 8 n + g)
+        split_tf32(xr[n * 8 * P.KS + k + 4], bh1, bl1);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_tf32(acc[m][n], al[m], bh0, bh1);                // small terms first
+          mma_tf32(acc[m][n], ah[m], bl0, bl1);
+          mma_tf32(acc[m][n], ah[m], bh0, bh1);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      if (m >= n_m) continue;
+#pragma unroll
+      for (int n = 0; n < kRmFrames / 8; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int phase = (mt0 + m) * 16 + g + ((e & 2) ? 8 : 0);
+          const long long frame = f0 + n * 8 + 2 * tig + (e & 1);
+          const long long o = frame * P.nw + phase;
+          if (o < n_out) y[o] = acc[m][n][e];
+        }
+    }
+  }
+}
+
 }  // namespace lidfe
