@@ -1420,10 +1420,13 @@ __global__ void __launch_bounds__(kRmWarps * 32) resample_mma_kernel(const __gri
   if (f0 * P.nw >= n_out) return;
   const float* x = P.in + P.in_off[b];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
-  for (int i = tid; i < kRmFrames * P.KS; i += kRmWarps * 32) {
-    const int f = i / P.KS, k = i - f * P.KS;
-    const long long j = (f0 + f) * P.orig + k - P.width;
-    rm_x[i] = (k < P.K && j >= 0 && j < n_in) ? x[j] : 0.f;
+  for (int f = warp; f < kRmFrames; f += kRmWarps) {     // one window per warp and turn: coalesced, no divisions
+    const long long j0 = (f0 + f) * P.orig - P.width;
+    float* row = rm_x + f * P.KS;
+    for (int k = lane; k < P.KS; k += 32) {
+      const long long j = j0 + k;
+      row[k] = (k < P.K && j >= 0 && j < n_in) ? x[j] : 0.f;
+    }
   }
   __syncthreads();
   float* y = P.out + P.out_off[b];
@@ -1437,32 +1440,40 @@ __global__ void __launch_bounds__(kRmWarps * 32) resample_mma_kernel(const __gri
       for (int n = 0; n < kRmFrames / 8; ++n)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.f;
-    const float* w0 = P.w + static_cast<long long>(mt0 * 16 + g) * P.K8 + tig;       // rows g / g+8 of M tile mt0
-    const float* w1 = w0 + static_cast<long long>(n_m == 2 ? 16 : 0) * P.K8;          // (a missing second tile aliases the first)
-    const float* xr = rm_x + g * P.KS + tig;                                            // window g of N tile 0
+    // running pointers: rows g and g+8 of the two M tiles (a missing second tile aliases the first), window g of the
+    // four N tiles
+    const float* wa = P.w + static_cast<long long>(mt0 * 16 + g) * P.K8 + tig;
+    const float* wb = wa + 8 * P.K8;
+    const float* wc = wa + static_cast<long long>(n_m == 2 ? 16 : 0) * P.K8;
+    const float* wd = wc + 8 * P.K8;
+    const float* xr = rm_x + g * P.KS + tig;
+    const int xs = 8 * P.KS;
 #pragma unroll 1
-    for (int k = 0; k < P.K8; k += 8) {
+    for (int k = 0; k < P.K8; k += 8, wa += 8, wb += 8, wc += 8, wd += 8, xr += 8) {
       uint32_t ah[2][4], al[2][4];
-      {
-        const float a0 = __ldg(w0 + k), a1 = __ldg(w0 + 8 * P.K8 + k), a2 = __ldg(w0 + k + 4), a3 = __ldg(w0 + 8 * P.K8 + k + 4);
-        split_tf32(a0, ah[0][0], al[0][0]); split_tf32(a1, ah[0][1], al[0][1]);
-        split_tf32(a2, ah[0][2], al[0][2]); split_tf32(a3, ah[0][3], al[0][3]);
-        const float c0 = __ldg(w1 + k), c1 = __ldg(w1 + 8 * P.K8 + k), c2 = __ldg(w1 + k + 4), c3 = __ldg(w1 + 8 * P.K8 + k + 4);
-        split_tf32(c0, ah[1][0], al[1][0]); split_tf32(c1, ah[1][1], al[1][1]);
-        split_tf32(c2, ah[1][2], al[1][2]); split_tf32(c3, ah[1][3], al[1][3]);
-      }
+      split_tf32(__ldg(wa), ah[0][0], al[0][0]); split_tf32(__ldg(wb), ah[0][1], al[0][1]);
+      split_tf32(__ldg(wa + 4), ah[0][2], al[0][2]); split_tf32(__ldg(wb + 4), ah[0][3], al[0][3]);
+      split_tf32(__ldg(wc), ah[1][0], al[1][0]); split_tf32(__ldg(wd), ah[1][1], al[1][1]);
+      split_tf32(__ldg(wc + 4), ah[1][2], al[1][2]); split_tf32(__ldg(wd + 4), ah[1][3], al[1][3]);
+      uint32_t bh[kRmFrames / 8][2], bl[kRmFrames / 8][2];
 #pragma unroll
       for (int n = 0; n < kRmFrames / 8; ++n) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(xr[n * 8 * P.KS + k], bh0, bl0);            // (tap k + tig, frame 8 n + g)
-        split_tf32(xr[n * 8 * P.KS + k + 4], bh1, bl1);
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          mma_tf32(acc[m][n], al[m], bh0, bh1);                // small terms first
-          mma_tf32(acc[m][n], ah[m], bl0, bl1);
-          mma_tf32(acc[m][n], ah[m], bh0, bh1);
-        }
+        split_tf32(xr[n * xs], bh[n][0], bl[n][0]);            // (tap k + tig, frame 8 n + g)
+        split_tf32(xr[n * xs + 4], bh[n][1], bl[n][1]);
       }
+      // three sweeps over the 8 accumulator tiles, small terms first: consecutive MMAs never touch the same tile
+#pragma unroll
+      for (int n = 0; n < kRmFrames / 8; ++n)
+#pragma unroll
+        for (int m = 0; m < 2; ++m) mma_tf32(acc[m][n], al[m], bh[n][0], bh[n][1]);
+#pragma unroll
+      for (int n = 0; n < kRmFrames / 8; ++n)
+#pragma unroll
+        for (int m = 0; m < 2; ++m) mma_tf32(acc[m][n], ah[m], bl[n][0], bl[n][1]);
+#pragma unroll
+      for (int n = 0; n < kRmFrames / 8; ++n)
+#pragma unroll
+        for (int m = 0; m < 2; ++m) mma_tf32(acc[m][n], ah[m], bh[n][0], bh[n][1]);
     }
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
