@@ -11,9 +11,16 @@ per-utterance CMVN on a batch of 256 x 8-s 16 kHz utterances per GPU (synthetic,
 One JSON line on rank 0.  `value` = whole-job audio-s/s with inputs resident in HBM (weak scaling: every rank
 processes its own 256-utterance batch; utterances are independent, no data-path collective).  `e2e` = the same
 metric through the public host API with pinned HOST buffers (H2D of the waveforms and D2H of the features inside
-the timed region).  `roofline` describes the dominant kernel (the fused fbank kernel) from CUDA-event timings of
-every launch inside the timed region.  `cpu_baseline` = the oracle port of the reference path on the box's host
-cores (rank 0, N=1 only).  --impl reference times that CPU path as the reference arm.
+the timed region).  `roofline` describes the dominant kernel (the fused fbank kernel, which since round 2 also
+normalises: the step is ONE kernel) from CUDA-event timings inside the timed region, against the binding bound --
+FP32 flops, whose ceiling is measured in the same run by an FFMA probe -- with the HBM figure beside it.
+`sustained` repeats the step for >= 2 s with the clocks sampled throughout.  `cfg4` (every N, strong scaling) is
+BASELINE config 4: 10 000 utterances of 1-20 s (seed 3) packed by an offset table, LPT-sharded by utterance,
+global CMVN = accumulate -> ONE all-reduce of 161 doubles -> apply, the all-reduce inside the timed region.
+`e2e_ragged` feeds a different ragged batch every step through DeviceCollate (plan creation inside the timed
+region).  `cpu_baseline` = the reference path (torchaudio's kaldi.fbank + masking transforms, as
+lid/audio_processor.py calls them) on the box's host cores (rank 0, N=1 only), all cores and one core.
+--impl reference times that CPU path as the reference arm.
 """
 import argparse
 import json
@@ -47,23 +54,57 @@ def _cpu_worker_init():
     torch.set_num_threads(1)
 
 
+def _reference_path():
+    """(wav2mel, augment, name): the reference's per-utterance calls.  With torchaudio importable these ARE the library
+    calls lid/audio_processor.py makes (ref: lid/audio_processor.py:54-65, 225-227); otherwise the oracle's restatement
+    of them with the same torch CPU ops."""
+    import torch
+    from oracle import frontend_oracle as O
+    try:
+        import torchaudio
+        from torchaudio.compliance import kaldi as K
+        tm = {}
+
+        def wav2mel(x):
+            f = K.fbank(x, num_mel_bins=N_MELS, dither=0.0, frame_length=25, frame_shift=10,
+                        preemphasis_coefficient=1.0, sample_frequency=SR)
+            return f.transpose(0, 1).unsqueeze(0)
+
+        def augment(spec):
+            T = spec.shape[-1]
+            for _ in range(MASK_TIMES):
+                key = int(T * T_MASK)
+                if key not in tm:
+                    tm[key] = torchaudio.transforms.TimeMasking(key)
+                spec = tm[key](spec)
+                spec = tm.setdefault("f", torchaudio.transforms.FrequencyMasking(F_MASK))(spec)
+            return spec
+        return wav2mel, augment, "torchaudio %s kaldi.fbank + Time/FrequencyMasking" % torchaudio.__version__
+    except Exception:
+        gen = torch.Generator().manual_seed(7)
+        return (O.wav2mel_kaldi,
+                lambda spec: O.spectrogram_augment(spec, T_MASK, F_MASK, MASK_TIMES, generator=gen),
+                "oracle restatement (torchaudio not importable)")
+
+
 def _cpu_worker(args):
     """Reference path for a share of the batch, exactly as MergedDataset.__getitem__ runs it per utterance
-    (ref: lid/raw_datasets.py:270-305): wav2mel(use_kaildi=True) -> spectrogram_augment -> [our CMVN]."""
+    (ref: lid/raw_datasets.py:270-305): wav2mel(use_kaildi=True) -> [our CMVN] -> spectrogram_augment."""
     import torch
     from oracle import frontend_oracle as O
     seed, n_utts, n_samples, reps = args
     g = torch.Generator().manual_seed(seed)
     wavs = [O.normalize_wav(torch.randn(1, n_samples, generator=g)) for _ in range(n_utts)]
-    gen = torch.Generator().manual_seed(seed + 1)
+    torch.manual_seed(seed + 1)
+    wav2mel, augment, _ = _reference_path()
     times = []
     acc = 0.0
     for _ in range(reps):
         t0 = time.perf_counter()
         for w in wavs:
-            spec = O.wav2mel_kaldi(w)                                            # (1, 80, T)
+            spec = wav2mel(w)                                                    # (1, 80, T)
             feat = O.cmvn_per_utt(spec[0].T)                                     # (T, 80)
-            spec = O.spectrogram_augment(feat.T.unsqueeze(0), T_MASK, F_MASK, MASK_TIMES, generator=gen)
+            spec = augment(feat.T.unsqueeze(0))
             acc += float(spec[0, 0, 0])
         times.append(time.perf_counter() - t0)
     return times, acc
@@ -87,14 +128,31 @@ def run_cpu_arm(steps, warmup, n_utts_total=B_UTTS, n_samples=N_SAMPLES):
     return audio_s / sec, sec, workers, wall
 
 
+def run_cpu_single_core(n_utts=4, n_samples=N_SAMPLES):
+    """The same per-utterance path on ONE core (torch threads = 1), a few utterances: audio-s/s."""
+    import torch
+    torch.set_num_threads(1)
+    times, _ = _cpu_worker((999, n_utts, n_samples, 2))
+    return n_utts * n_samples / SR / times[1]
+
+
+def config_dict(world):
+    """Identical in both arms."""
+    return {"workload": WORKLOAD, "utterances_per_gpu": B_UTTS, "samples_per_utterance": N_SAMPLES,
+            "frames_per_gpu_step": B_UTTS * (1 + (N_SAMPLES - 400) // 160),
+            "parallelism": "utterance-sharded x%d" % world,
+            "l2": "3 rotating input/output sets (196 MB per step > 126 MB L2)"}
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """Samples SM clock + throttle reasons of one GPU while the timed region runs (pynvml; nvidia-smi fallback)."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         self.index = index
+        self.period = period
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -134,7 +192,7 @@ class ClockSampler:
     def _loop(self):
         while not self._stop.is_set():
             self.sample_once()
-            self._stop.wait(0.002)
+            self._stop.wait(self.period)
 
     def start(self):
         if self._h is not None:
@@ -162,13 +220,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def fp32_peak_probe(torch, device):
-    """FFMA micro-benchmark through torch (plumbing only; not on the hot path): a long chain of fused multiply-adds
-    is not expressible in eager torch, so the FP32 ceiling is taken from SM count x 128 lanes x 2 x clock."""
-    props = torch.cuda.get_device_properties(device)
-    return props.multi_processor_count
-
-
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -211,7 +262,8 @@ def run_gpu_arm(args):
         step(i)
     barrier()
 
-    sampler = ClockSampler(torch.cuda._get_nvml_device_index(dev) if hasattr(torch.cuda, "_get_nvml_device_index") else local_rank)
+    nvml_index = torch.cuda._get_nvml_device_index(dev) if hasattr(torch.cuda, "_get_nvml_device_index") else local_rank
+    sampler = ClockSampler(nvml_index)
     prof_stride = 4 if args.steps >= 16 else 1     # sample the kernel timing: an event record between kernels costs ~us
     fe.profile_begin(args.steps, stride=prof_stride)
     launches0 = lib.lidfe_launch_count()
@@ -235,6 +287,25 @@ def run_gpu_arm(args):
     ms_step = float(t.item()) / args.steps
     value = world * AUDIO_S_PER_BATCH / (ms_step * 1e-3)
 
+    # ---- sustained: the same step back to back for >= 2 s, clocks sampled throughout (the headline region lasts a few
+    #      tens of ms; this shows whether the figure holds once the boost budget is spent) --------------------------
+    sus_steps = max(args.steps, int(2.2 / (ms_step * 1e-3)))
+    sus_sampler = ClockSampler(nvml_index, period=0.01)
+    barrier()
+    sus_sampler.start()
+    ev0.record()
+    for i in range(sus_steps):
+        step(i)
+    ev1.record()
+    barrier()
+    sus_clocks = sus_sampler.stop()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sus_ms = float(t.item())
+    sustained = {"value": round(world * AUDIO_S_PER_BATCH * sus_steps / (sus_ms * 1e-3), 1), "unit": "audio-s/s",
+                 "steps": sus_steps, "seconds": round(sus_ms * 1e-3, 3), "clocks": sus_clocks}
+
     # ---- e2e: public host API, pinned host buffers, H2D + kernels + D2H per step --------------------------
     host_in = torch.empty(B_UTTS * N_SAMPLES, dtype=torch.float32).pin_memory()
     host_in.copy_(ins[0].cpu())
@@ -249,8 +320,8 @@ def run_gpu_arm(args):
     e2e_steps = max(3, min(args.steps, 20))
     E2E_BLOCKS = 3
 
-    def timed_blocks(step_fn):
-        """Seconds per step: median over E2E_BLOCKS blocks of e2e_steps steps (the PCIe link is shared with whatever else
+    def timed_blocks(step_fn, n_steps=e2e_steps):
+        """Seconds per step: median over E2E_BLOCKS blocks of n_steps steps (the PCIe link is shared with whatever else
         runs on the host; one disturbed block would otherwise decide the number)."""
         for _ in range(2):
             step_fn()
@@ -258,32 +329,73 @@ def run_gpu_arm(args):
         for _ in range(E2E_BLOCKS):
             barrier()
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
+            for _ in range(n_steps):
                 step_fn()
             torch.cuda.synchronize(dev)
-            secs.append((time.perf_counter() - t0) / e2e_steps)
+            secs.append((time.perf_counter() - t0) / n_steps)
         return sorted(secs)[len(secs) // 2]
 
-    e2e_sec = timed_blocks(e2e_step)
-    t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * AUDIO_S_PER_BATCH / float(t.item())
+    def over_ranks(sec):
+        tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    e2e_value = world * AUDIO_S_PER_BATCH / over_ranks(timed_blocks(e2e_step))
     h2d = host_in.numel() * 4 + host_masks.numel() * 4
     d2h = host_out.numel() * 4
 
-    # informational: the same step fed with raw int16 PCM (2 B/sample over PCIe; 1/32768 scaling + normalize_wav on the
-    # device, row f2).  NOT the headline e2e: the reference's wav2mel boundary takes float32 waveforms.
+    # informational: the same step fed with raw int16 PCM (2 B/sample over PCIe) into an int16 front-end: 1/32768
+    # scaling + normalize_wav are fused into the kernel's sample load (row f2; statistics pre-pass + ONE fused kernel).
+    # NOT the headline e2e: the reference's wav2mel boundary takes float32 waveforms.
+    fe16 = lid.FrontEnd(n_mels=N_MELS, device=dev, in_dtype=torch.int16, in_scale=1.0 / 32768.0)
+    plan16 = fe16.make_plan([N_SAMPLES] * B_UTTS, padded=True)
     host_pcm = (ins[0].cpu() * 3000.0).clamp(-32768, 32767).to(torch.int16).pin_memory()
 
     def pcm_step():
-        fe.featurize_host(host_pcm, plan, host_out, masks=host_masks, cmvn="utt", chunks=e2e_chunks)
+        fe16.featurize_host(host_pcm, plan16, host_out, masks=host_masks, cmvn="utt", chunks=e2e_chunks)
 
-    pcm_sec = timed_blocks(pcm_step)
-    t = torch.tensor([pcm_sec], dtype=torch.float64, device=dev)
+    pcm_value = world * AUDIO_S_PER_BATCH / over_ranks(timed_blocks(pcm_step))
+
+    # ---- e2e with a DIFFERENT ragged batch every step through DeviceCollate (cfg4-like lengths, B = 256): plan creation
+    #      (host-side fill + one async copy from the handle's pool), packing, H2D, the kernel and a D2H read of the
+    #      result are all inside the timed region (ref: lid/raw_datasets.py:345-365 -- every real batch has its own
+    #      length signature) ------------------------------------------------------------------------------------
+    gl = torch.Generator().manual_seed(77 + rank)
+    n_rag = 6
+    rag_batches = []
+    for _ in range(n_rag):
+        lens = torch.randint(16000, 320001, (B_UTTS,), generator=gl).tolist()
+        items = [(torch.randn(n, generator=gl).pin_memory(), torch.zeros(3, dtype=torch.long), "p", "a") for n in lens]
+        rag_batches.append((items, sum(lens) / SR))
+    collate = lid.DeviceCollate(fe, {"a": 0}, train=True, t_mask=T_MASK, f_mask=F_MASK, mask_times=MASK_TIMES, cmvn="utt")
+    rag_state = {"i": 0, "audio": 0.0}
+
+    def ragged_step():
+        items, audio = rag_batches[rag_state["i"] % n_rag]
+        rag_state["i"] += 1
+        rag_state["audio"] += audio
+        feats = collate(items)[0]
+        float(feats[0, 0, 0])          # D2H read of the step's result
+
+    for _ in range(n_rag):
+        ragged_step()                  # warm the plan pool / allocator
+    torch.cuda.synchronize(dev)
+    rag_state["audio"] = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2 * n_rag):
+        ragged_step()
+    torch.cuda.synchronize(dev)
+    rag_sec = over_ranks(time.perf_counter() - t0)
+    ta = torch.tensor([rag_state["audio"]], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    pcm_value = world * AUDIO_S_PER_BATCH / float(t.item())
+        dist.all_reduce(ta)
+    ragged = {"value": round(float(ta.item()) / rag_sec, 1), "unit": "audio-s/s", "steps": 2 * n_rag,
+              "utterances_per_step": B_UTTS, "lengths": "U[1 s, 20 s], a new draw every step",
+              "note": "DeviceCollate: plan + pack + H2D (pageable->pinned staging) + fused kernel + D2H read, per step"}
+
+    cfg4 = run_cfg4(lid, fe, dev, rank, world, barrier)
 
     if rank != 0:
         if world > 1:
@@ -292,22 +404,26 @@ def run_gpu_arm(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak_src = "fallback"
+    peak_src = "fallback (B200_PROFILING.md)"
     hbm_peak = 6650.0
     if os.path.exists(peaks_path):
         try:
             hbm_peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "measured"
+            peak_src = "MEASURED_PEAKS.json"
         except Exception:
             pass
     k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
     alg_bytes = frames_per_step * ALG_BYTES_PER_FRAME
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    hbm_achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    clk = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965) * 1e6
-    fp32_peak_at_clock = sms * 128 * 2 * clk / 1e12
-    fp32_peak_boost = sms * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
+    fp32_theory = sms * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
+    import ctypes
+    tf = ctypes.c_double(0.0)
+    lid._lib.check(lib.lidfe_fp32_probe(30.0, ctypes.byref(tf), torch.cuda.current_stream(dev).cuda_stream))
+    fp32_peak = float(tf.value)                      # FFMA loop on every SM, measured in this run
     fp32_achieved = frames_per_step * ALG_FLOP_PER_FRAME / (k_ms * 1e-3) / 1e12
+    hbm_floor_us = alg_bytes / (hbm_peak * 1e9) * 1e6
+    fp32_floor_us = frames_per_step * ALG_FLOP_PER_FRAME / (fp32_peak * 1e12) * 1e6
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -315,42 +431,125 @@ def run_gpu_arm(args):
             traffic = json.load(open(tp)).get("fbank_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "fbank_kernel<float,false>", "achieved": round(achieved, 1),
-                "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+    # the bound that binds is the slower floor: FP32 flops here (41-44 us vs 30 us of HBM time)
+    fp32_binds = fp32_floor_us >= hbm_floor_us
+    roofline = {"bound": "fp32" if fp32_binds else "hbm", "kernel": "fbank_kernel<float,false,1> (framing+FFT+mel+log+CMVN+masks, one kernel per step)",
+                "achieved": round(fp32_achieved if fp32_binds else hbm_achieved, 2),
+                "peak": round(fp32_peak if fp32_binds else hbm_peak, 2),
+                "peak_source": "in-run FFMA probe (lidfe_fp32_probe)" if fp32_binds else peak_src,
+                "unit": "TFLOP/s" if fp32_binds else "GB/s",
+                "frac": round((fp32_achieved / fp32_peak) if fp32_binds else (hbm_achieved / hbm_peak), 4),
                 "traffic": traffic, "kernel_ms": round(k_ms, 5), "kernel_share_of_step": round(k_ms / ms_step, 3),
                 "kernel_timing": "CUDA event pair around every %d-th launch of the timed region (%d samples)" % (prof_stride, len(kernel_ms)),
-                "alg_bytes_per_launch": alg_bytes,
-                "fp32": {"achieved_tflops": round(fp32_achieved, 2), "peak_tflops_at_sampled_clock": round(fp32_peak_at_clock, 1),
-                         "peak_tflops_at_max_clock": round(fp32_peak_boost, 1),
-                         "frac_at_max_clock": round(fp32_achieved / fp32_peak_boost, 4),
-                         "note": "algorithmic 15.0 kflop/frame (SURVEY.md 8d); peak = SMs x 128 lanes x 2 x clock"}}
+                "alg_flop_per_launch": frames_per_step * ALG_FLOP_PER_FRAME, "alg_bytes_per_launch": alg_bytes,
+                "floors_us": {"fp32": round(fp32_floor_us, 1), "hbm": round(hbm_floor_us, 1)},
+                "fp32": {"achieved_tflops": round(fp32_achieved, 2), "peak_tflops_measured": round(fp32_peak, 2),
+                         "peak_tflops_theoretical_at_max_clock": round(fp32_theory, 1),
+                         "frac_of_measured": round(fp32_achieved / fp32_peak, 4),
+                         "frac_at_max_clock": round(fp32_achieved / fp32_theory, 4),
+                         "note": "algorithmic 15.0 kflop/frame (SURVEY.md 8d)"},
+                "hbm": {"achieved_gbs": round(hbm_achieved, 1), "peak_gbs": hbm_peak, "peak_source": peak_src,
+                        "frac": round(hbm_achieved / hbm_peak, 4)}}
 
     cpu = None
     if world == 1 and not args.no_cpu:
         v, sec, cores, wall = run_cpu_arm(steps=1, warmup=1)
+        single = run_cpu_single_core()
         cpu = {"value": round(v, 1), "unit": "audio-s/s", "cores": cores, "kind": "port",
-               "sample": "1 timed pass (after 1 warm-up) of the full 256 x 8-s batch, oracle port of wav2mel(use_kaildi=True)"
-                         "+spectrogram_augment+CMVN, one process per core, torch threads=1; %.1f s wall incl. start-up" % wall}
+               "single_core": round(single, 1),
+               "sample": "1 timed pass (after 1 warm-up) of the full 256 x 8-s batch, %s + CMVN, one process per core, "
+                         "torch threads=1; %.1f s wall incl. start-up; single_core = 4 x 8-s utterances on one core"
+                         % (_reference_path()[2], wall)}
 
     line = {"metric": METRIC, "value": round(value, 1), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "utterances_per_gpu": B_UTTS, "samples_per_utterance": N_SAMPLES,
-                       "frames_per_gpu_step": frames_per_step, "parallelism": "utterance-sharded x%d" % world,
-                       "l2": "3 rotating input/output sets (196 MB per step > 126 MB L2)"},
+            "config": config_dict(world),
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "blocks": E2E_BLOCKS,
                     "agg": "median block", "pipeline_chunks": e2e_chunks},
             "e2e_int16_pcm": {"value": round(pcm_value, 1), "unit": "audio-s/s", "h2d_bytes_per_step": host_pcm.numel() * 2,
                               "d2h_bytes_per_step": d2h,
-                              "note": "informational: host ships int16 PCM, scaling + normalize_wav on the device"},
+                              "note": "informational: host ships int16 PCM; scaling + normalize_wav fused into the kernel's sample load"},
+            "e2e_ragged": ragged,
+            "sustained": sustained,
+            "cfg4": cfg4,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_cfg4(lid, fe, dev, rank, world, barrier, n_utts=None, steps=3):
+    """BASELINE config 4: 10 000 utterances of 1-20 s (seed 3), packed by an offset table, sharded by
+    utterance with the deterministic LPT partition, generated on the device (seed 3000 + rank); per pass:
+    featurize(global_accum) -> all_reduce(161 fp64) -> cmvn_apply + masks.  STRONG scaling: the 10 k utterances are the
+    whole job at every N.  Returns the sub-record (same on every rank)."""
+    import torch
+    import torch.distributed as dist
+    n_utts = int(os.environ.get("LIDFE_CFG4_UTTS", "10000")) if n_utts is None else n_utts
+    g = torch.Generator().manual_seed(3)
+    lengths = torch.randint(16000, 320001, (n_utts,), generator=g).tolist()
+    shards = lid.lpt_partition(lengths, world)
+    mine = [lengths[i] for i in shards[rank]]
+    plan = fe.make_plan(mine, padded=False)
+    gd = torch.Generator(device=dev).manual_seed(3000 + rank)
+    packed = torch.randn(plan.total_samples, device=dev, generator=gd)
+    torch.manual_seed(99 + rank)
+    masks = lid.draw_masks(plan.frames, N_MELS, T_MASK, F_MASK, MASK_TIMES).to(dev)
+    out = torch.empty(plan.rows, N_MELS, device=dev)
+    stats = torch.zeros(2 * N_MELS + 1, dtype=torch.float64, device=dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def one_pass(timed=False):
+        stats.zero_()
+        if timed:
+            evs[0].record()
+        fe.featurize_packed(packed, plan, out=out, cmvn="global_accum", stats_out=stats)
+        if timed:
+            evs[1].record()
+        lid.allreduce_stats(stats)
+        if timed:
+            evs[2].record()
+        fe.cmvn_apply(out, plan, stats, masks=masks)
+        if timed:
+            evs[3].record()
+
+    one_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_pass()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    one_pass(timed=True)
+    torch.cuda.synchronize(dev)
+    split = torch.tensor([evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])],
+                         dtype=torch.float64, device=dev)
+    load = torch.tensor([float(sum(mine))], dtype=torch.float64, device=dev)
+    lo, hi = load.clone(), load.clone()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(split, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    total_frames = int(stats[2 * N_MELS].item())
+    audio_s = sum(lengths) / SR
+    rec = {"workload": "cfg4: %d utterances 1-20 s (seed 3) packed, LPT-sharded x%d, global CMVN: accumulate -> "
+                       "all_reduce(161 fp64) -> apply+masks, all-reduce inside the timed region" % (n_utts, world),
+           "scaling": "strong", "n_gpus": world, "value": round(audio_s / (float(ms.item()) * 1e-3), 1), "unit": "audio-s/s",
+           "ms_per_pass": round(float(ms.item()), 3), "steps": steps, "audio_s": round(audio_s, 1), "total_frames": total_frames,
+           "split_ms_max_over_ranks": {"accumulate_kernel": round(float(split[0]), 3), "all_reduce": round(float(split[1]), 3),
+                                        "apply_kernel": round(float(split[2]), 3)},
+           "lpt_imbalance": round(float(hi.item() / lo.item()), 5),
+           "comm": "1 x all_reduce(SUM, float64[161]) per pass over NCCL" if world > 1 else "none (N=1 base of the strong-scaling series)"}
+    del packed, out
+    return rec
 
 
 def run_reference_arm(args):
@@ -364,10 +563,10 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 1), "unit": "audio-s/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "utterances_per_gpu": B_UTTS, "samples_per_utterance": N_SAMPLES},
+            "config": config_dict(world),
             "cpu_baseline": {"value": round(v, 1), "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": "every step = the full 256 x 8-s batch split over %d single-thread worker "
-                                       "processes (oracle port: same torch CPU ops as the reference's torchaudio path)" % cores},
+                                       "processes; per utterance: %s + CMVN" % (cores, _reference_path()[2])},
             "e2e": {"value": round(v, 1), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

@@ -14,8 +14,14 @@
  *   - Return value: 0 = OK; < 0 = contract error (LIDFE_E_*); > 0 = a cudaError_t.  Nothing throws,
  *     nothing calls exit().  lidfe_strerror() maps any return value to text.
  *   - A handle is immutable after lidfe_create(); a plan is immutable after lidfe_plan_create().
- *     All device work is enqueued asynchronously on `stream`; no call synchronises the device
- *     except lidfe_create / lidfe_plan_create (table upload).
+ *     All device work is enqueued asynchronously on `stream`.  lidfe_create uploads its tables and returns after they
+ *     have landed (one synchronisation, once).  lidfe_plan_create_async fills a pinned staging buffer and enqueues ONE
+ *     copy on the caller's stream: plans take their device / pinned memory from a pool owned by the handle, so a new
+ *     batch shape every step (ragged training batches) costs no cudaMalloc / cudaFree / device synchronisation once the
+ *     pool is warm.  lidfe_plan_create is the same followed by a wait on that copy.
+ *   - Ordering contract: a plan's tables are uploaded on the stream handed to lidfe_plan_create_async; use the plan
+ *     on that stream (or order other streams after it yourself).  A plan owns device workspace, so it is in flight on
+ *     one stream at a time.
  *   - There is no CPU implementation behind this ABI.  Without a CUDA device every compute entry
  *     point returns a cudaError_t.
  */
@@ -28,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LIDFE_ABI_VERSION 4
+#define LIDFE_ABI_VERSION 5
 
 /* error codes (negative) */
 #define LIDFE_OK 0
@@ -90,7 +96,23 @@ typedef struct {
   int pad;           /* MelSpectrogram(pad=...): zeros added on both sides (CENTER framing only) */
   int log_kind;      /* LIDFE_LOG_NATURAL | LIDFE_LOG_DB10                       */
   float top_db;      /* LIDFE_POST_TOPDB: 80.0 in the reference                  */
+  /* -- waveform dither inside the fused kernel (ref: lid/audio_processor.py:129 wav += 1e-5 * U[0,1); the kaldi call of
+   *    the reference passes dither=0.0, ref: lid/audio_processor.py:57) -- */
+  float dither;      /* 0 -> off (reference's wav2mel); > 0 -> x += dither * U[0,1) while the samples are staged,
+                        Philox4x32-10 keyed by (seed, utterance, sample).  KALDI framing only                          */
+  int window_type;   /* LIDFE_WINDOW_*: which window window_host holds (recorded and validated; the table itself is
+                        built by the caller with the reference's fp32 arithmetic, ta: compliance/kaldi.py:86-113)      */
+  unsigned long long seed;
 } lidfe_config;
+
+/* window kinds of torchaudio.compliance.kaldi._feature_window_function (ta: compliance/kaldi.py:86-113) plus the periodic
+ * Hann of torch.stft (ref: lid/audio_processor.py:91-103) */
+#define LIDFE_WINDOW_POVEY 0
+#define LIDFE_WINDOW_HANNING 1
+#define LIDFE_WINDOW_HAMMING 2
+#define LIDFE_WINDOW_RECTANGULAR 3
+#define LIDFE_WINDOW_BLACKMAN 4
+#define LIDFE_WINDOW_HANN_PERIODIC 5
 
 /* -- lifetime ------------------------------------------------------------------------------------- */
 
@@ -147,15 +169,27 @@ int lidfe_mel_plan_expand(int n_mels, const float* melbank_host, float* dense_ou
 int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* wav_offsets_host,
                       const long long* wav_lengths_host, const long long* out_rows_host,
                       const long long* pad_rows_host);
+/* The same without waiting: the table upload is ONE cudaMemcpyAsync from a pinned staging buffer on `stream`; memory
+ * comes from the handle's pool (see Conventions).  This is what a training loop calls once per (ragged) batch. */
+int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long long* wav_offsets_host,
+                            const long long* wav_lengths_host, const long long* out_rows_host,
+                            const long long* pad_rows_host, void* stream);
+/* Returns the plan's memory to the handle's pool (no cudaFree; the pool is released by lidfe_destroy). */
 int lidfe_plan_destroy(lidfe_plan p);
+/* Pool bookkeeping (tests / monitoring): allocations made for plans since lidfe_create, and blocks currently free. */
+int lidfe_pool_stats(lidfe_handle h, long long* blocks_allocated, long long* blocks_free);
 long long lidfe_plan_total_frames(lidfe_plan p);
 long long lidfe_plan_num_tiles(lidfe_plan p);
+/* work items ("spans": runs of consecutive tiles of one utterance) the fused kernel's CTAs claim dynamically */
+long long lidfe_plan_num_spans(lidfe_plan p);
 /* frames of utterance i (host copy of what the kernel will produce) */
 long long lidfe_plan_frames(lidfe_plan p, int i);
 
 /* -- the hot path --------------------------------------------------------------------------------- */
 
 /*
+ * ONE kernel for every cmvn_mode: with LIDFE_CMVN_PER_UTT / LIDFE_POST_TOPDB the CTA that completes an utterance's
+ * statistics normalises (clamps) its rows while they are still in L2 -- there is no second pass over HBM.
  * Replaces, for a whole batch in one call:
  *   wav2mel(x, use_kaildi=True)            ref: lid/audio_processor.py:8-69   (n_ceps == 0)
  *   torchaudio.compliance.kaldi.mfcc       ta: compliance/kaldi.py:669-813    (n_ceps > 0; not in the reference)
@@ -176,6 +210,16 @@ long long lidfe_plan_frames(lidfe_plan p, int i);
 int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
                     const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
                     double* stats_out_dev, void* stream);
+
+/*
+ * read_audio(normalize=True) + wav2mel in one call (ref: lid/audio_processor.py:108-122 then :8-69): same arguments as
+ * lidfe_featurize, but wav_dev holds RAW samples (int16 PCM scaled by cfg.in_scale, or float32).  A statistics pre-pass
+ * (wave_stages_kernel, mean and unbiased std per utterance) is followed by the fused kernel, which applies
+ * (x - mean) / (std + 1e-6) while it stages each tile -- the raw samples are the only waveform bytes read or written.
+ */
+int lidfe_featurize_raw(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
+                        const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
+                        double* stats_out_dev, void* stream);
 
 /*
  * Second pass of global CMVN: feats = (feats - mean) / (std + 1e-9) in place, then masks.
@@ -203,6 +247,8 @@ int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
  */
 int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,
                       float dither, const float* noise_dev, float preemph, void* stream);
+/* noise_dev == NULL with dither != 0: the noise is drawn on the device, Philox4x32-10 keyed by (cfg.seed, utterance,
+ * sample) -- no host-drawn buffer crosses PCIe.  (noise_dev != NULL keeps bit parity with the reference's RNG stream.) */
 
 /* Same stages fed with raw int16 PCM (what torchaudio.load decodes from a 16-bit wav before scaling by 1/32768,
  * ref: lid/audio_processor.py:118-122): x = (float)pcm * in_scale first.  Lets the host ship 2 bytes per sample. */
@@ -233,6 +279,10 @@ long long lidfe_resample_out_len(lidfe_resampler r, long long n_in);
 int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long long* in_off_dev, const long long* in_len_dev,
                    float* out_dev, const long long* out_off_dev, const long long* out_len_dev, long long max_out_len,
                    void* stream);
+
+/* FP32 ceiling of the device, measured: a dependent-free FFMA loop on every SM for about `ms_budget` milliseconds.
+ * Writes the achieved TFLOP/s (2 flops per FFMA) -- bench.py reports the kernel against this, not against a data sheet. */
+int lidfe_fp32_probe(float ms_budget, double* tflops_out, void* stream);
 
 const char* lidfe_strerror(int rc);
 int lidfe_abi_version(void);

@@ -17,7 +17,8 @@ IN_F32, IN_I16 = 0, 1
 CMVN_NONE, CMVN_PER_UTT, CMVN_APPLY_GLOBAL, CMVN_ACCUM_GLOBAL, POST_TOPDB = 0, 1, 2, 3, 4
 FRAMING_KALDI, FRAMING_CENTER = 0, 1
 LOG_NATURAL, LOG_DB10 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
+WINDOW_POVEY, WINDOW_HANNING, WINDOW_HAMMING, WINDOW_RECTANGULAR, WINDOW_BLACKMAN, WINDOW_HANN_PERIODIC = 0, 1, 2, 3, 4, 5
 
 EXPORTS = (
     "lidfe_create", "lidfe_destroy", "lidfe_num_frames", "lidfe_out_dim", "lidfe_plan_create",
@@ -25,6 +26,7 @@ EXPORTS = (
     "lidfe_featurize", "lidfe_cmvn_apply", "lidfe_wave_stages", "lidfe_wave_stages_i16", "lidfe_mask_apply", "lidfe_strerror",
     "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_profile_set_stride", "lidfe_mel_plan", "lidfe_mel_plan_expand",
     "lidfe_resampler_create", "lidfe_resampler_destroy", "lidfe_resample_out_len", "lidfe_resample",
+    "lidfe_plan_create_async", "lidfe_plan_num_spans", "lidfe_featurize_raw", "lidfe_fp32_probe", "lidfe_pool_stats",
 )
 
 
@@ -33,7 +35,8 @@ class LidfeConfig(C.Structure):
                 ("fft_len", C.c_int), ("n_mels", C.c_int), ("n_ceps", C.c_int), ("preemph", C.c_float),
                 ("remove_dc", C.c_int), ("log_floor", C.c_float), ("in_dtype", C.c_int),
                 ("in_scale", C.c_float), ("framing", C.c_int), ("pad", C.c_int), ("log_kind", C.c_int),
-                ("top_db", C.c_float)]
+                ("top_db", C.c_float), ("dither", C.c_float), ("window_type", C.c_int),
+                ("seed", C.c_ulonglong)]
 
 
 class LidfeError(RuntimeError):
@@ -68,15 +71,23 @@ def load_library() -> C.CDLL:
     lib.lidfe_out_dim.restype = i32
     lib.lidfe_plan_create.argtypes = [vp, C.POINTER(vp), i32, pll, pll, pll, pll]
     lib.lidfe_plan_create.restype = i32
+    lib.lidfe_plan_create_async.argtypes = [vp, C.POINTER(vp), i32, pll, pll, pll, pll, vp]
+    lib.lidfe_plan_create_async.restype = i32
     lib.lidfe_plan_destroy.argtypes = [vp]
     lib.lidfe_plan_destroy.restype = i32
-    for name in ("lidfe_plan_total_frames", "lidfe_plan_num_tiles"):
+    for name in ("lidfe_plan_total_frames", "lidfe_plan_num_tiles", "lidfe_plan_num_spans"):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = ll
     lib.lidfe_plan_frames.argtypes = [vp, i32]
     lib.lidfe_plan_frames.restype = ll
     lib.lidfe_featurize.argtypes = [vp, vp, vp, vp, ll, vp, i32, i32, vp, vp, vp]
     lib.lidfe_featurize.restype = i32
+    lib.lidfe_featurize_raw.argtypes = [vp, vp, vp, vp, ll, vp, i32, i32, vp, vp, vp]
+    lib.lidfe_featurize_raw.restype = i32
+    lib.lidfe_fp32_probe.argtypes = [f32, C.POINTER(C.c_double), vp]
+    lib.lidfe_fp32_probe.restype = i32
+    lib.lidfe_pool_stats.argtypes = [vp, pll, pll]
+    lib.lidfe_pool_stats.restype = i32
     lib.lidfe_cmvn_apply.argtypes = [vp, vp, vp, ll, vp, i32, vp, vp]
     lib.lidfe_cmvn_apply.restype = i32
     lib.lidfe_mask_apply.argtypes = [vp, vp, vp, ll, vp, i32, vp]

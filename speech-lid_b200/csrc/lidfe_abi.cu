@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -15,6 +16,27 @@
 #include "lidfe_kernels.cuh"
 
 using namespace lidfe;
+
+// One pooled allocation behind a plan: a device block, its pinned host mirror (the staging buffer of the single
+// table upload) and the event that marks the last device work that touched them.  Blocks live in the handle's pool:
+// lidfe_plan_destroy hands them back, lidfe_plan_create_async re-uses the first one that is large enough, so ragged
+// batches (a new length signature every step, ref: lid/raw_datasets.py:345-365) allocate nothing in steady state.
+//
+// Layout (sized by CAPACITY, so the at-rest state survives re-use with another batch size):
+//   workspace  sched[2] + ictl[2] int | utt_done[2][Bc] int | utt_max[2][Bc] u32 (0) | utt_min[2][Bc] u32 (~0) |
+//              utt_stats[2][Bc][2][n_out] f64 (0) | utt_wnorm[Bc] float2       ([2] = launch parity, see FbankParams::items)
+//   tables     frames[Bc] i64 | out_rows[Bc] i64 | offsets[Bc] i64 | lengths[Bc] i64 | first_tile[Bc] i64 |
+//              items[Ic] int4 | spans[Sc] | tiles[Tc] (MFCC two-kernel path only)
+struct PlanBlock {
+  unsigned char* d_base;
+  unsigned char* h_tables;      // pinned mirror of the tables section
+  size_t ws_bytes, tab_bytes;
+  int Bc;
+  long long Sc, Tc, Ic;
+  cudaEvent_t ev;               // last use on the device (kernels or the upload)
+  float* d_logmel;              // tile-blocked log-mel workspace of the two-kernel MFCC path (grown on demand)
+  long long logmel_tiles;
+};
 
 struct lidfe_ctx {
   lidfe_config cfg;
@@ -33,6 +55,17 @@ struct lidfe_ctx {
   size_t smem_bytes_dct;
   size_t smem_bytes;
   int grid_cap;   // resident CTAs of the fbank kernel on this device
+  int apply_rows; // rows per CTA of cmvn_apply_kernel (LIDFE_APPLY_ROWS, read once)
+  int span_tiles; // LIDFE_SPAN_TILES override (0 = automatic)
+  int fused_apply;  // LIDFE_FUSED_APPLY=1: per-utterance second stage inside the fbank kernel (service CTAs) instead of a second kernel
+  int service_ctas; // LIDFE_SERVICE_CTAS override (0 = automatic)
+  int dbg;         // LIDFE_DBG development switches (see FbankParams::dbg)
+  int apply_block; // rows per claimed block of the in-kernel second stage (LIDFE_APPLY_BLOCK, default 128)
+  std::vector<PlanBlock*>* pool;      // free blocks
+  std::mutex* pool_mu;
+  long long blocks_allocated;         // device/pinned block allocations made for plans so far (lidfe_pool_stats)
+  int live_plans;                     // plans that still point at this handle (guarded by pool_mu)
+  bool destroyed;                     // lidfe_destroy was called while plans were alive: the last plan frees the handle
   // optional per-launch timing of the fbank kernel (bench.py's roofline leg)
   std::vector<cudaEvent_t>* prof_events;
   int prof_used;
@@ -45,23 +78,33 @@ struct lidfe_plan_s {
   int B;
   long long total_frames;
   long long n_tiles;
+  long long n_spans;
   std::vector<long long> frames;
-  Tile* d_tiles;
+  PlanBlock* blk;
+  // views into blk->d_base
+  int* d_sched;
+  int* d_utt_done;
+  unsigned* d_utt_max;
+  unsigned* d_utt_min;
+  double* d_utt_stats;
+  float2* d_utt_wnorm;
+  int4* d_items;
+  int n_items;
+  int parity;             // per-utterance launches on this plan so far, mod 2 (host-side toggle)
   long long* d_frames;    // [B]
   long long* d_out_rows;  // [B]
-  long long max_frames;
   long long* d_offsets;   // [B]
   long long* d_lengths;   // [B]
-  double* d_utt_stats;    // [2 launches][B][2][n_out]: ping-pong, the apply kernel of launch i clears the buffer of launch i+1
-  int stats_flip;         // which half the next per-utterance-CMVN launch accumulates into (host-side toggle)
-  unsigned* d_utt_max;    // [B] (LIDFE_POST_TOPDB)
-  float* d_tile_min;      // [n_tiles][kWarps] (LIDFE_POST_TOPDB, allocated on first use)
   long long* d_utt_first_tile;   // [B]
-  float* d_logmel;        // [rows][n_mels] log-mel workspace of the two-kernel MFCC path (allocated on first use)
+  Span* d_spans;
+  Tile* d_tiles;          // MFCC two-kernel path, else NULL
+  long long max_frames;
   long long max_row;      // rows of the output matrix this plan touches
 };
 
 static std::atomic<long long> g_launches{0};
+static long long* g_dbg_buf = nullptr;
+extern "C" int lidfe_dbg_read(long long* host, int n) { return g_dbg_buf ? (int)cudaMemcpy(host, g_dbg_buf, sizeof(long long) * n, cudaMemcpyDeviceToHost) : -1; }
 
 #define CU_TRY(expr)                      \
   do {                                    \
@@ -390,7 +433,9 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
       (cfg->framing != LIDFE_FRAMING_KALDI && cfg->framing != LIDFE_FRAMING_CENTER) || cfg->pad < 0 ||
       cfg->pad > 4096 || (cfg->framing == LIDFE_FRAMING_KALDI && cfg->pad != 0) ||
       (cfg->log_kind != LIDFE_LOG_NATURAL && cfg->log_kind != LIDFE_LOG_DB10) ||
-      !(cfg->log_floor >= 1.17549435e-38f))   // a normal float: the kernel's log takes no denormals
+      !(cfg->log_floor >= 1.17549435e-38f) ||   // a normal float: the kernel's log takes no denormals
+      !(cfg->dither >= 0.f) || (cfg->dither > 0.f && cfg->framing != LIDFE_FRAMING_KALDI) ||
+      cfg->window_type < LIDFE_WINDOW_POVEY || cfg->window_type > LIDFE_WINDOW_HANN_PERIODIC)
     return LIDFE_E_CONFIG;
   if (cfg->n_ceps > 0 && !dct_host) return LIDFE_E_NULL;
 
@@ -465,9 +510,33 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   }
   c->blob_bytes = static_cast<int>(blob.size());
 
+  c->pool = new (std::nothrow) std::vector<PlanBlock*>();
+  c->pool_mu = new (std::nothrow) std::mutex();
+  if (!c->pool || !c->pool_mu) {
+    lidfe_destroy(c);
+    return LIDFE_E_NOMEM;
+  }
+  c->apply_rows = kApplyRowsDefault;
+  if (const char* env = getenv("LIDFE_APPLY_ROWS")) {      // tuning knobs are read once, here
+    const int v = atoi(env);
+    if (v >= 8 && v <= 65536) c->apply_rows = v;
+  }
+  if (const char* env = getenv("LIDFE_DBG")) c->dbg = atoi(env);
+  c->apply_block = 128;
+  if (const char* env = getenv("LIDFE_SERVICE_CTAS")) c->service_ctas = atoi(env);
+  if (const char* env = getenv("LIDFE_FUSED_APPLY")) c->fused_apply = atoi(env) != 0;
+  if (const char* env = getenv("LIDFE_APPLY_BLOCK")) {
+    const int v = atoi(env);
+    if (v >= 16 && v <= 4096) c->apply_block = v;
+  }
+  if (const char* env = getenv("LIDFE_SPAN_TILES")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= kMaxSpanTiles) c->span_tiles = v;
+  }
   cudaError_t e = cudaGetDevice(&c->device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device);
   if (e == cudaSuccess) e = upload(&c->d_blob, blob.data(), blob.size());
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the tables have landed whatever stream the caller launches on
   if (e == cudaSuccess) {
     c->smem_bytes = smem_for(*cfg, total_taps);
     if (cfg->n_ceps > 0 && cfg->n_ceps <= kDctMaxCeps) {
@@ -504,102 +573,291 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   return LIDFE_OK;
 }
 
+static void free_block(PlanBlock* b) {
+  if (!b) return;
+  cudaFree(b->d_base);
+  cudaFreeHost(b->h_tables);
+  cudaFree(b->d_logmel);
+  if (b->ev) cudaEventDestroy(b->ev);
+  delete b;
+}
+
+static void destroy_now(lidfe_ctx* h) {
+  cudaFree(h->d_blob);
+  if (h->pool) {
+    for (PlanBlock* b : *h->pool) free_block(b);
+    delete h->pool;
+  }
+  delete h->pool_mu;
+  if (h->prof_events) {
+    for (auto& ev : *h->prof_events) cudaEventDestroy(ev);
+    delete h->prof_events;
+  }
+  delete h;
+}
+
+// A handle may be destroyed before its plans (garbage-collected bindings give no order): the plans keep it alive
+// and the last one to go frees it.
 int lidfe_destroy(lidfe_handle h) {
   if (!h) return LIDFE_E_NULL;
-  cudaFree(h->d_blob);
-  delete h;
+  if (h->pool_mu) {
+    std::unique_lock<std::mutex> g(*h->pool_mu);
+    if (h->live_plans > 0) {
+      h->destroyed = true;
+      return LIDFE_OK;
+    }
+  }
+  destroy_now(h);
   return LIDFE_OK;
 }
 
-int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* wav_offsets_host,
-                      const long long* wav_lengths_host, const long long* out_rows_host,
-                      const long long* pad_rows_host) {
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+struct BlockLayout {
+  size_t sched, utt_done, utt_max, utt_min, utt_stats, utt_wnorm, ws_bytes;
+  size_t frames, out_rows, offsets, lengths, first_tile, items, spans, tiles, tab_bytes;   // tables: relative to ws_bytes
+};
+static BlockLayout block_layout(int Bc, long long Sc, long long Tc, long long Ic, int n_out) {
+  BlockLayout L;
+  size_t o = 0;
+  L.sched = o; o += 16;
+  L.utt_done = o; o = align_up(o + 2 * static_cast<size_t>(Bc) * 4, 16);          // [2 launch parities][Bc]
+  L.utt_max = o; o = align_up(o + 2 * static_cast<size_t>(Bc) * 4, 16);
+  L.utt_min = o; o = align_up(o + 2 * static_cast<size_t>(Bc) * 4, 16);
+  L.utt_stats = o; o = align_up(o + 2 * static_cast<size_t>(Bc) * 2 * n_out * 8, 16);
+  L.utt_wnorm = o; o = align_up(o + static_cast<size_t>(Bc) * 8, 256);
+  L.ws_bytes = o;
+  o = 0;
+  L.frames = o; o += static_cast<size_t>(Bc) * 8;
+  L.out_rows = o; o += static_cast<size_t>(Bc) * 8;
+  L.offsets = o; o += static_cast<size_t>(Bc) * 8;
+  L.lengths = o; o += static_cast<size_t>(Bc) * 8;
+  L.first_tile = o; o = align_up(o + static_cast<size_t>(Bc) * 8, 32);
+  L.items = o; o = align_up(o + static_cast<size_t>(Ic) * 16, 32);
+  L.spans = o; o += static_cast<size_t>(Sc) * sizeof(Span);
+  L.tiles = o; o += static_cast<size_t>(Tc) * sizeof(Tile);
+  L.tab_bytes = align_up(o, 256);
+  return L;
+}
+static long long pow2_at_least(long long v, long long lo) {
+  long long c = lo;
+  while (c < v) c <<= 1;
+  return c;
+}
+
+// a block with room for (B, spans, tiles): from the pool if one fits, else a new allocation (the only place that
+// allocates; the workspace is put to rest once, here -- the kernels leave it at rest)
+static int acquire_block(lidfe_ctx* h, int B, long long n_spans, long long n_tiles, long long n_items, PlanBlock** out) {
+  *out = nullptr;
+  {
+    std::lock_guard<std::mutex> g(*h->pool_mu);
+    for (size_t i = 0; i < h->pool->size(); ++i) {
+      PlanBlock* b = (*h->pool)[i];
+      if (b->Bc >= B && b->Sc >= n_spans && b->Tc >= n_tiles && b->Ic >= n_items) {
+        h->pool->erase(h->pool->begin() + i);
+        *out = b;
+        break;
+      }
+    }
+  }
+  if (*out) {
+    CU_TRY(cudaEventSynchronize((*out)->ev));     // its previous plan's work (normally long done)
+    return LIDFE_OK;
+  }
+  PlanBlock* b = new (std::nothrow) PlanBlock();
+  if (!b) return LIDFE_E_NOMEM;
+  memset(b, 0, sizeof(*b));
+  b->Bc = static_cast<int>(pow2_at_least(B, 64));
+  b->Sc = pow2_at_least(n_spans, 256);
+  b->Tc = n_tiles > 0 ? pow2_at_least(n_tiles, 256) : 0;
+  b->Ic = pow2_at_least(n_items, 256);
+  const BlockLayout L = block_layout(b->Bc, b->Sc, b->Tc, b->Ic, h->n_out);
+  b->ws_bytes = L.ws_bytes;
+  b->tab_bytes = L.tab_bytes;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b->d_base), L.ws_bytes + L.tab_bytes);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&b->h_tables), L.tab_bytes);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMemset(b->d_base, 0, L.ws_bytes);
+  if (e == cudaSuccess) e = cudaMemset(b->d_base + L.utt_min, 0xff, 2 * static_cast<size_t>(b->Bc) * 4);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    free_block(b);
+    return static_cast<int>(e);
+  }
+  {
+    std::lock_guard<std::mutex> g(*h->pool_mu);
+    ++h->blocks_allocated;
+  }
+  *out = b;
+  return LIDFE_OK;
+}
+
+int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long long* wav_offsets_host,
+                            const long long* wav_lengths_host, const long long* out_rows_host,
+                            const long long* pad_rows_host, void* stream) {
   if (!h || !out || !wav_offsets_host || !wav_lengths_host || !out_rows_host) return LIDFE_E_NULL;
   *out = nullptr;
   if (B <= 0) return LIDFE_E_ARG;
   const size_t in_elt = (h->cfg.in_dtype == LIDFE_IN_I16) ? 2 : 4;
-  std::vector<Tile> tiles;
+  const bool center = h->cfg.framing == LIDFE_FRAMING_CENTER;
+  const bool need_tiles = h->cfg.n_ceps > 0 && h->cfg.n_ceps <= kDctMaxCeps && h->cfg.n_mels % 4 == 0;   // mfcc_dct_kernel's table
   std::vector<long long> frames(B), utt_first_tile(B);
-  long long total = 0;
+  long long total = 0, n_tiles = 0, max_frames = 0;
   for (int i = 0; i < B; ++i) {
-    utt_first_tile[i] = static_cast<long long>(tiles.size());
     if (wav_offsets_host[i] < 0 || out_rows_host[i] < 0) return LIDFE_E_OFFSETS;
     const long long T = lidfe_num_frames(wav_lengths_host[i], &h->cfg);
     if (T <= 0) return LIDFE_E_SHORT;
     if (T > 0x7fffffffLL) return LIDFE_E_ARG;
+    if (pad_rows_host && pad_rows_host[i] < T) return LIDFE_E_OFFSETS;
     frames[i] = T;
     total += T;
-    const bool center = h->cfg.framing == LIDFE_FRAMING_CENTER;
-    const long long N = wav_lengths_host[i], cpad = h->cfg.pad;
-    for (long long f = 0; f < T; f += kTileFrames) {
-      Tile tl;
-      tl.out_row = out_rows_host[i] + f;
-      tl.nframes = static_cast<int>((T - f) < kTileFrames ? (T - f) : kTileFrames);
-      tl.utt = i;
-      tl.t0 = static_cast<int>(f);
-      // first sample of the tile relative to the utterance's first sample.  CENTER framing: frame f covers
-      // p[160 f - 200, 160 f + 200) of the constant-padded signal p (the Hann window sits at 56..455 of the 512-point
-      // buffer and |FFT|^2 does not see that shift); tiles that touch the padding / reflection are staged element-wise.
-      const long long rel = center ? f * kFrameShift - kFrameLen / 2 - cpad : f * kFrameShift;
-      const long long nsamp = static_cast<long long>(kFrameShift) * tl.nframes + (kFrameLen - kFrameShift);
-      const bool interior = rel >= 0 && rel + nsamp <= N;
-      tl.wav_off = wav_offsets_host[i] + rel;
-      const bool aligned = interior && ((static_cast<unsigned long long>(tl.wav_off) * in_elt) % 16ull) == 0ull;
-      tl.aux = aligned ? 1 : 0;
-      tiles.push_back(tl);
-    }
-    if (pad_rows_host) {
-      if (pad_rows_host[i] < T) return LIDFE_E_OFFSETS;
-      for (long long r = T; r < pad_rows_host[i]; r += 4 * kTileFrames) {
-        Tile tl;
-        tl.wav_off = 0;
-        tl.out_row = out_rows_host[i] + r;
-        tl.nframes = 0;
-        tl.utt = i;
-        tl.t0 = static_cast<int>(r);
-        const long long left = pad_rows_host[i] - r;
-        tl.aux = static_cast<int>(left < 4 * kTileFrames ? left : 4 * kTileFrames);
-        tiles.push_back(tl);
+    max_frames = T > max_frames ? T : max_frames;
+    utt_first_tile[i] = n_tiles;
+    n_tiles += (T + kTileFrames - 1) / kTileFrames;
+    if (pad_rows_host && need_tiles) n_tiles += (pad_rows_host[i] - T + 4 * kTileFrames - 1) / (4 * kTileFrames);
+  }
+  if (n_tiles > 0x7fffffffLL) return LIDFE_E_ARG;
+
+  // ---- spans: runs of <= span_tiles consecutive tiles of one utterance, utterance-major.  Enough spans per CTA that
+  //      dynamic claiming balances (>= ~10), as long as possible otherwise (a span end costs two CTA barriers, and in
+  //      the per-utterance modes a hand-over of 2 x n_out sums); the spans of the last stretch of the batch are single
+  //      tiles so that the CTAs run dry together.
+  int span_tiles = h->span_tiles;
+  if (span_tiles <= 0) {
+    const long long per_cta_tiles = n_tiles / (h->grid_cap > 0 ? h->grid_cap : 1);
+    span_tiles = static_cast<int>(per_cta_tiles / 10);
+    if (span_tiles < 1) span_tiles = 1;
+    if (span_tiles > kMaxSpanTiles) span_tiles = kMaxSpanTiles;
+  }
+  const long long tail_tiles = static_cast<long long>(h->grid_cap) * span_tiles;   // ~ one round of spans
+  std::vector<Span> spans;
+  std::vector<Tile> tiles;
+  {
+    long long tile_no = 0;
+    for (int i = 0; i < B; ++i) {
+      const long long T = frames[i], N = wav_lengths_host[i], cpad = h->cfg.pad;
+      for (long long f = 0; f < T;) {
+        const int st = (n_tiles - tile_no <= tail_tiles) ? 1 : span_tiles;
+        const long long nf = (T - f) < static_cast<long long>(st) * kTileFrames ? (T - f) : static_cast<long long>(st) * kTileFrames;
+        Span sp;
+        sp.out_row = out_rows_host[i] + f;
+        sp.nframes = static_cast<int>(nf);
+        sp.utt = i;
+        sp.t0 = static_cast<int>(f);
+        // first sample of the span relative to the utterance's first sample.  CENTER framing: frame f covers
+        // p[160 f - 200, 160 f + 200) of the constant-padded signal p (the Hann window sits at 56..455 of the 512-point
+        // buffer and |FFT|^2 does not see that shift); tiles that touch the padding / reflection are staged element-wise
+        // (the kernel decides per tile; aux only says whether the span's samples are 16-byte aligned).
+        const long long rel = center ? f * kFrameShift - kFrameLen / 2 - cpad : f * kFrameShift;
+        sp.wav_off = wav_offsets_host[i] + rel;
+        sp.aux = (sp.wav_off >= 0 && ((static_cast<unsigned long long>(sp.wav_off) * in_elt) % 16ull) == 0ull) ? 1 : 0;
+        (void)N;
+        spans.push_back(sp);
+        if (need_tiles) {
+          for (long long g = f; g < f + nf; g += kTileFrames) {
+            Tile tl = sp;
+            tl.wav_off = sp.wav_off + (g - f) * kFrameShift;
+            tl.out_row = out_rows_host[i] + g;
+            tl.nframes = static_cast<int>((T - g) < kTileFrames ? (T - g) : kTileFrames);
+            tl.t0 = static_cast<int>(g);
+            tiles.push_back(tl);
+          }
+        }
+        tile_no += (nf + kTileFrames - 1) / kTileFrames;
+        f += nf;
+      }
+      if (pad_rows_host) {
+        for (long long r = T; r < pad_rows_host[i]; r += 4 * kTileFrames) {
+          Span sp;
+          sp.wav_off = 0;
+          sp.out_row = out_rows_host[i] + r;
+          sp.nframes = 0;
+          sp.utt = i;
+          sp.t0 = static_cast<int>(r);
+          const long long left = pad_rows_host[i] - r;
+          sp.aux = static_cast<int>(left < 4 * kTileFrames ? left : 4 * kTileFrames);
+          spans.push_back(sp);
+          if (need_tiles) tiles.push_back(sp);
+        }
       }
     }
   }
-  // int16 bulk copies also need the tile's own offset 16B aligned: 160 samples * 2 B = 320 B -> ok.
-  if (tiles.size() > 0x7fffffffull) return LIDFE_E_ARG;
+  if (spans.size() > 0x7fffffffull) return LIDFE_E_ARG;
+
   lidfe_plan_s* p = new (std::nothrow) lidfe_plan_s();
   if (!p) return LIDFE_E_NOMEM;
   p->ctx = h;
   p->B = B;
   p->total_frames = total;
-  p->n_tiles = static_cast<long long>(tiles.size());
+  p->n_tiles = n_tiles;
+  p->n_spans = static_cast<long long>(spans.size());
   p->frames = frames;
-  p->d_tiles = nullptr;
-  p->d_frames = nullptr;
-  p->d_out_rows = nullptr;
-  p->max_frames = 0;
-  for (int i = 0; i < B; ++i) p->max_frames = frames[i] > p->max_frames ? frames[i] : p->max_frames;
-  p->d_offsets = nullptr;
-  p->d_lengths = nullptr;
-  p->d_utt_stats = nullptr;
-  p->stats_flip = 0;
-  p->d_utt_max = nullptr;
-  p->d_tile_min = nullptr;
-  p->d_utt_first_tile = nullptr;
-  p->d_logmel = nullptr;
+  p->max_frames = max_frames;
   p->max_row = 0;
   for (int i = 0; i < B; ++i) {
     const long long end = out_rows_host[i] + ((pad_rows_host && pad_rows_host[i] > frames[i]) ? pad_rows_host[i] : frames[i]);
     if (end > p->max_row) p->max_row = end;
   }
-  cudaError_t e = upload(&p->d_tiles, tiles.data(), tiles.size());
-  if (e == cudaSuccess) e = upload(&p->d_frames, frames.data(), frames.size());
-  if (e == cudaSuccess) e = upload(&p->d_out_rows, out_rows_host, static_cast<size_t>(B));
-  if (e == cudaSuccess) e = upload(&p->d_offsets, wav_offsets_host, static_cast<size_t>(B));
-  if (e == cudaSuccess) e = upload(&p->d_lengths, wav_lengths_host, static_cast<size_t>(B));
-  if (e == cudaSuccess) e = upload(&p->d_utt_first_tile, utt_first_tile.data(), static_cast<size_t>(B));
-  if (e == cudaSuccess)
-    e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_stats), 2 * static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemset(p->d_utt_stats, 0, 2 * static_cast<size_t>(B) * 2 * h->n_out * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->d_utt_max), static_cast<size_t>(B) * sizeof(unsigned));
+  // items of the in-kernel second stage: <= apply_block rows of one utterance each, utterance-major
+  std::vector<int4> items;
+  for (int i = 0; i < B; ++i) {
+    const long long T = frames[i];
+    for (long long r = 0; r < T; r += h->apply_block)
+      items.push_back(make_int4(i, static_cast<int>(r), static_cast<int>(T - r < h->apply_block ? T - r : h->apply_block),
+                                static_cast<int>(T)));
+  }
+  if (items.size() > 0x7fffffffull) {
+    delete p;
+    return LIDFE_E_ARG;
+  }
+  p->n_items = static_cast<int>(items.size());
+  PlanBlock* b = nullptr;
+  const int rc = acquire_block(h, B, p->n_spans, static_cast<long long>(tiles.size()), static_cast<long long>(items.size()), &b);
+  if (rc != LIDFE_OK) {
+    delete p;
+    return rc;
+  }
+  p->blk = b;
+  {
+    std::lock_guard<std::mutex> g(*h->pool_mu);
+    ++h->live_plans;
+  }
+  const BlockLayout L = block_layout(b->Bc, b->Sc, b->Tc, b->Ic, h->n_out);
+  unsigned char* ws = b->d_base;
+  unsigned char* tab = b->d_base + L.ws_bytes;
+  p->d_sched = reinterpret_cast<int*>(ws + L.sched);
+  p->d_utt_done = reinterpret_cast<int*>(ws + L.utt_done);
+  p->d_utt_max = reinterpret_cast<unsigned*>(ws + L.utt_max);
+  p->d_utt_min = reinterpret_cast<unsigned*>(ws + L.utt_min);
+  p->d_utt_stats = reinterpret_cast<double*>(ws + L.utt_stats);
+  p->d_utt_wnorm = reinterpret_cast<float2*>(ws + L.utt_wnorm);
+  p->d_items = reinterpret_cast<int4*>(tab + L.items);
+  p->d_frames = reinterpret_cast<long long*>(tab + L.frames);
+  p->d_out_rows = reinterpret_cast<long long*>(tab + L.out_rows);
+  p->d_offsets = reinterpret_cast<long long*>(tab + L.offsets);
+  p->d_lengths = reinterpret_cast<long long*>(tab + L.lengths);
+  p->d_utt_first_tile = reinterpret_cast<long long*>(tab + L.first_tile);
+  p->d_spans = reinterpret_cast<Span*>(tab + L.spans);
+  p->d_tiles = tiles.empty() ? nullptr : reinterpret_cast<Tile*>(tab + L.tiles);
+  // fill the pinned mirror, ONE asynchronous copy of what is used
+  unsigned char* ht = b->h_tables;
+  memcpy(ht + L.frames, frames.data(), static_cast<size_t>(B) * 8);
+  memcpy(ht + L.out_rows, out_rows_host, static_cast<size_t>(B) * 8);
+  memcpy(ht + L.offsets, wav_offsets_host, static_cast<size_t>(B) * 8);
+  memcpy(ht + L.lengths, wav_lengths_host, static_cast<size_t>(B) * 8);
+  memcpy(ht + L.first_tile, utt_first_tile.data(), static_cast<size_t>(B) * 8);
+  memcpy(ht + L.items, items.data(), items.size() * sizeof(int4));
+  memcpy(ht + L.spans, spans.data(), spans.size() * sizeof(Span));
+  if (!tiles.empty()) memcpy(ht + L.tiles, tiles.data(), tiles.size() * sizeof(Tile));
+  const size_t used = tiles.empty() ? L.spans + spans.size() * sizeof(Span) : L.tiles + tiles.size() * sizeof(Tile);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(tab, ht, used, cudaMemcpyHostToDevice, st);
+  // the workspace goes to rest (asynchronously, on the same stream): whatever the block's previous plan -- another
+  // batch size, an aborted launch -- left behind cannot leak into this one
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws, 0, L.ws_bytes, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws + L.utt_min, 0xff, 2 * static_cast<size_t>(b->Bc) * 4, st);
+  p->parity = 0;
+  if (e == cudaSuccess) e = cudaEventRecord(b->ev, st);
   if (e != cudaSuccess) {
     cudaGetLastError();
     lidfe_plan_destroy(p);
@@ -609,62 +867,107 @@ int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* w
   return LIDFE_OK;
 }
 
+int lidfe_plan_create(lidfe_handle h, lidfe_plan* out, int B, const long long* wav_offsets_host,
+                      const long long* wav_lengths_host, const long long* out_rows_host,
+                      const long long* pad_rows_host) {
+  const int rc = lidfe_plan_create_async(h, out, B, wav_offsets_host, wav_lengths_host, out_rows_host, pad_rows_host, nullptr);
+  if (rc != LIDFE_OK) return rc;
+  CU_TRY(cudaEventSynchronize((*out)->blk->ev));      // the tables have landed: the plan may be used on any stream
+  return LIDFE_OK;
+}
+
 int lidfe_plan_destroy(lidfe_plan p) {
   if (!p) return LIDFE_E_NULL;
-  cudaFree(p->d_tiles);
-  cudaFree(p->d_frames);
-  cudaFree(p->d_out_rows);
-  cudaFree(p->d_offsets);
-  cudaFree(p->d_lengths);
-  cudaFree(p->d_utt_stats);
-  cudaFree(p->d_utt_max);
-  cudaFree(p->d_tile_min);
-  cudaFree(p->d_utt_first_tile);
-  cudaFree(p->d_logmel);
+  lidfe_ctx* h = p->ctx;
+  bool last = false;
+  if (p->blk) {
+    std::lock_guard<std::mutex> g(*h->pool_mu);
+    h->pool->push_back(p->blk);
+    --h->live_plans;
+    last = h->destroyed && h->live_plans == 0;
+  }
   delete p;
+  if (last) destroy_now(h);
+  return LIDFE_OK;
+}
+int lidfe_pool_stats(lidfe_handle h, long long* blocks_allocated, long long* blocks_free) {
+  if (!h || !blocks_allocated || !blocks_free) return LIDFE_E_NULL;
+  std::lock_guard<std::mutex> g(*h->pool_mu);
+  *blocks_allocated = h->blocks_allocated;
+  *blocks_free = static_cast<long long>(h->pool->size());
   return LIDFE_OK;
 }
 long long lidfe_plan_total_frames(lidfe_plan p) { return p ? p->total_frames : 0; }
 long long lidfe_plan_num_tiles(lidfe_plan p) { return p ? p->n_tiles : 0; }
+long long lidfe_plan_num_spans(lidfe_plan p) { return p ? p->n_spans : 0; }
 long long lidfe_plan_frames(lidfe_plan p, int i) { return (p && i >= 0 && i < p->B) ? p->frames[i] : 0; }
 
 static int launch_apply(lidfe_ctx* h, lidfe_plan p, float* feats, long long ld, const int* masks, int n_masks,
-                        const double* utt_stats, const double* glob_stats, cudaStream_t st, int normalize,
-                        double* clear_stats) {
+                        const double* glob_stats, cudaStream_t st, int normalize, int parity = -1) {
   ApplyParams A;
+  memset(&A, 0, sizeof(A));
   A.feats = feats;
   A.ld = ld;
   A.n_out = h->n_out;
   A.masks = masks;
   A.n_masks = masks ? n_masks : 0;
-  A.utt_stats = utt_stats;
+  A.utt_stats = nullptr;
   A.utt_frames = p->d_frames;
   A.utt_out_row = p->d_out_rows;
   A.glob_stats = glob_stats;
   A.normalize = normalize;
-  A.clear_stats = clear_stats;
   A.utt_max = p->d_utt_max;
-  A.tile_min = (normalize == 2) ? p->d_tile_min : nullptr;
-  A.utt_first_tile = p->d_utt_first_tile;
   A.top_db = h->cfg.top_db;
-  int rows_per_cta = kApplyRowsDefault;
-  if (const char* env = getenv("LIDFE_APPLY_ROWS")) {
-    const int v = atoi(env);
-    if (v >= 8 && v <= 65536) rows_per_cta = v;
+  if (parity >= 0) {     // second kernel of a per-utterance mode: this launch's half in, the other half back to rest
+    const long long Bc = p->blk->Bc;
+    const int op = parity ^ 1;
+    if (normalize == 1) A.utt_stats = p->d_utt_stats + static_cast<long long>(parity) * Bc * 2 * h->n_out;
+    A.utt_max = p->d_utt_max + parity * Bc;
+    A.utt_min = p->d_utt_min + parity * Bc;
+    A.rest_stats = p->d_utt_stats + static_cast<long long>(op) * Bc * 2 * h->n_out;
+    A.rest_done = p->d_utt_done + op * Bc;
+    A.rest_max = p->d_utt_max + op * Bc;
+    A.rest_min = p->d_utt_min + op * Bc;
   }
-  A.rows_per_cta = rows_per_cta;
-  const long long chunks = (p->max_frames + rows_per_cta - 1) / rows_per_cta;
+  A.rows_per_cta = h->apply_rows;
+  const long long chunks = (p->max_frames + A.rows_per_cta - 1) / A.rows_per_cta;
   if (chunks > 65535) return LIDFE_E_ARG;
   dim3 grid(static_cast<unsigned>(p->B), static_cast<unsigned>(chunks));
   cmvn_apply_kernel<<<grid, 256, 0, st>>>(A);
   g_launches.fetch_add(1);
   CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(p->blk->ev, st));
   return LIDFE_OK;
 }
 
-int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
-                    const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
-                    double* stats_out_dev, void* stream) {
+static int launch_wave(lidfe_handle h, lidfe_plan p, const void* in, int in_i16, float in_scale, float* out, float2* norm_out,
+                       int normalize, float dither, const float* noise_dev, float preemph, void* stream) {
+  if (!h || !p || !in) return LIDFE_E_NULL;
+  if (!out && !norm_out) return LIDFE_E_NULL;
+  if (p->ctx != h || in == static_cast<const void*>(out)) return LIDFE_E_ARG;
+  WaveParams W;
+  W.in = in;
+  W.in_i16 = in_i16;
+  W.in_scale = in_scale;
+  W.out = out;
+  W.norm_out = norm_out;
+  W.offsets = p->d_offsets;
+  W.lengths = p->d_lengths;
+  W.normalize = normalize;
+  W.dither = dither;
+  W.noise = noise_dev;
+  W.seed = h->cfg.seed;
+  W.preemph = preemph;
+  wave_stages_kernel<<<static_cast<unsigned>(p->B) * kWaveCluster, kWaveThreads, 0, static_cast<cudaStream_t>(stream)>>>(W);
+  g_launches.fetch_add(1);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(p->blk->ev, static_cast<cudaStream_t>(stream)));
+  return LIDFE_OK;
+}
+
+static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
+                          const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
+                          double* stats_out_dev, void* stream, bool raw) {
   if (!h || !p || !wav_dev || !out_dev) return LIDFE_E_NULL;
   if (p->ctx != h) return LIDFE_E_ARG;
   if (out_ld < h->n_out || cmvn_mode < 0 || cmvn_mode > 4 || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
@@ -672,13 +975,38 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   if (cmvn_mode == LIDFE_CMVN_ACCUM_GLOBAL && !stats_out_dev) return LIDFE_E_NULL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
+  if (raw) {   // statistics pre-pass of normalize_wav: (mean, std + 1e-6) per utterance; the fused kernel applies them
+    const int rc = launch_wave(h, p, wav_dev, h->cfg.in_dtype == LIDFE_IN_I16 ? 1 : 0, h->cfg.in_scale, nullptr, p->d_utt_wnorm, 1,
+                               0.f, nullptr, 0.f, stream);
+    if (rc != LIDFE_OK) return rc;
+  }
+
   FbankParams P;
   memset(&P, 0, sizeof(P));
   P.wav = wav_dev;
   P.out = out_dev;
   P.out_ld = out_ld;
-  P.tiles = p->d_tiles;
-  P.n_tiles = static_cast<int>(p->n_tiles);
+  P.spans = p->d_spans;
+  P.n_spans = static_cast<int>(p->n_spans);
+  P.sched = p->d_sched;
+  P.utt_done = p->d_utt_done;
+  P.ictl = p->d_sched + 2;
+  P.items = p->d_items;
+  P.n_items = p->n_items;
+  P.parity = p->parity;
+  P.b_cap = p->blk->Bc;
+  P.n_utts = p->B;
+  if (cmvn_mode == LIDFE_CMVN_PER_UTT || cmvn_mode == LIDFE_POST_TOPDB) p->parity ^= 1;
+  P.dbg = h->dbg;
+  if (h->dbg & 16) {
+    static long long* g_dbg = nullptr;
+    if (!g_dbg) cudaMalloc(reinterpret_cast<void**>(&g_dbg), 8 * 8 * 4096);
+    P.dbg_buf = g_dbg;
+    g_dbg_buf = g_dbg;
+  }
+  P.utt_frames = p->d_frames;
+  P.utt_out_row = p->d_out_rows;
+  P.utt_first_tile = p->d_utt_first_tile;
   P.const_blob = h->d_blob;
   P.const_bytes = h->blob_bytes;
   for (int b = 0; b < kBands; ++b) P.band_taps[b] = h->band_taps[b];
@@ -699,8 +1027,13 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   P.utt_offsets = p->d_offsets;
   P.utt_lengths = p->d_lengths;
   P.utt_max = p->d_utt_max;
+  P.utt_min = p->d_utt_min;
+  P.top_db = h->cfg.top_db;
   P.in_scale = h->cfg.in_scale;
   P.remove_dc = h->cfg.remove_dc;
+  P.utt_wnorm = raw ? p->d_utt_wnorm : nullptr;
+  P.dither = h->cfg.dither;
+  P.seed = h->cfg.seed;
   P.masks = masks_dev;
   P.n_masks = masks_dev ? n_masks : 0;
   P.mode = cmvn_mode;
@@ -708,31 +1041,23 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
   P.stats_out = stats_out_dev;
   P.utt_stats = p->d_utt_stats;
 
-  // per-utterance CMVN: no memset -- the statistics workspace is double buffered and the apply kernel of one launch
-  // clears the half the next launch accumulates into (a plan is in flight on one stream at a time)
-  const size_t stats_half = static_cast<size_t>(p->B) * 2 * h->n_out;
-  double* stats_cur = p->d_utt_stats + (p->stats_flip ? stats_half : 0);
-  double* stats_nxt = p->d_utt_stats + (p->stats_flip ? 0 : stats_half);
-  if (cmvn_mode == LIDFE_CMVN_PER_UTT) {
-    P.utt_stats = stats_cur;
-    p->stats_flip ^= 1;
-  }
-  if (cmvn_mode == LIDFE_POST_TOPDB) {
-    CU_TRY(cudaMemsetAsync(p->d_utt_max, 0, static_cast<size_t>(p->B) * sizeof(unsigned), st));
-    if (!p->d_tile_min)
-      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&p->d_tile_min), static_cast<size_t>(p->n_tiles) * kWarps * sizeof(float)));
-    P.tile_min = p->d_tile_min;
-  }
-
-  const bool mfcc2 = h->cfg.n_ceps > 0 && h->cfg.n_ceps <= kDctMaxCeps && h->cfg.n_mels % 4 == 0 &&
-                     (cmvn_mode == LIDFE_CMVN_NONE || cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL);
+  const bool mfcc2 = p->d_tiles && (cmvn_mode == LIDFE_CMVN_NONE || cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL);
+  long long grid = p->n_spans < h->grid_cap ? p->n_spans : h->grid_cap;
+  if (grid < 1) grid = 1;
   if (mfcc2) {
     // MFCC without statistics: fbank-only kernel into the log-mel workspace, then the register-tiled DCT kernel
-    if (!p->d_logmel)
-      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&p->d_logmel),
-                        static_cast<size_t>(p->n_tiles) * kTileFrames * h->cfg.n_mels * sizeof(float)));   // tile-blocked
+    PlanBlock* b = p->blk;
+    if (b->logmel_tiles < p->n_tiles) {      // grown on demand, kept with the pooled block
+      CU_TRY(cudaStreamSynchronize(st));
+      cudaFree(b->d_logmel);
+      b->d_logmel = nullptr;
+      b->logmel_tiles = 0;
+      const long long cap = pow2_at_least(p->n_tiles, 256);
+      CU_TRY(cudaMalloc(reinterpret_cast<void**>(&b->d_logmel), static_cast<size_t>(cap) * kTileFrames * h->cfg.n_mels * sizeof(float)));
+      b->logmel_tiles = cap;
+    }
     FbankParams F = P;
-    F.out = p->d_logmel;
+    F.out = b->d_logmel;
     F.out_ld = h->cfg.n_mels;
     F.n_ceps = 0;
     F.n_out = h->cfg.n_mels;
@@ -741,9 +1066,13 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     F.mode = LIDFE_CMVN_NONE;
     F.ws_blocked = 1;
     F.const_bytes = h->blob_bytes_fbank;
+    F.n_compute = static_cast<int>(p->n_spans < static_cast<long long>(h->num_sms) * 4 ? p->n_spans : static_cast<long long>(h->num_sms) * 4);
+    if (F.n_compute < 1) F.n_compute = 1;
+    F.k_static = static_cast<int>((p->n_spans / F.n_compute) * 85 / 100);
+    if (F.k_static < 1) F.k_static = 1;
     fbank_fn f2 = (h->cfg.in_dtype == LIDFE_IN_I16) ? pick_kernel_t<short>(false, h->std_mel)
                                                      : pick_kernel_t<float>(false, h->std_mel);
-    long long g2 = p->n_tiles < static_cast<long long>(h->num_sms) * 4 ? p->n_tiles : static_cast<long long>(h->num_sms) * 4;
+    long long g2 = p->n_spans < static_cast<long long>(h->num_sms) * 4 ? p->n_spans : static_cast<long long>(h->num_sms) * 4;
     if (g2 < 1) g2 = 1;
     const bool prof2 = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
     if (prof2) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
@@ -755,7 +1084,7 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
       h->prof_used += 2;
     }
     DctParams D;
-    D.logmel = p->d_logmel;
+    D.logmel = b->d_logmel;
     D.out = out_dev;
     D.out_ld = out_ld;
     D.tiles = p->d_tiles;
@@ -775,11 +1104,32 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     mfcc_dct_kernel<<<static_cast<unsigned>(gd), kDctThreads, h->smem_bytes_dct, st>>>(D);
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(p->blk->ev, st));
     return LIDFE_OK;
   }
 
-  long long grid = p->n_tiles < h->grid_cap ? p->n_tiles : h->grid_cap;
-  if (grid < 1) grid = 1;
+  // per-utterance modes: some of the resident CTAs are SERVICE CTAs (the second stage, see FbankParams::items)
+  P.n_compute = static_cast<int>(grid);
+  const bool per_utt = (cmvn_mode == LIDFE_CMVN_PER_UTT || cmvn_mode == LIDFE_POST_TOPDB);
+  const int launch_parity = P.parity;
+  if (per_utt && !h->fused_apply) P.n_items = 0;       // second stage as its own kernel (default)
+  if (per_utt && h->fused_apply) {
+    long long service = h->service_ctas > 0 ? h->service_ctas : h->num_sms / 8;
+    if (service > grid / 4) service = grid / 4;
+    if (service < 1) service = 1;
+    long long compute = p->n_spans < h->grid_cap - service ? p->n_spans : h->grid_cap - service;
+    if (compute < 1) compute = 1;
+    P.n_compute = static_cast<int>(compute);
+    grid = compute + service;
+  }
+  // static head of the schedule: ~85 % of the spans are dealt out as consecutive runs (fused second stage: none, the
+  // utterances have to complete progressively)
+  {
+    const long long per = p->n_spans / (P.n_compute > 0 ? P.n_compute : 1);
+    long long ks = (per * 85) / 100;
+    if (ks < 1 || (per_utt && h->fused_apply)) ks = 1;
+    P.k_static = static_cast<int>(ks);
+  }
   fbank_fn fn = pick_kernel(h);
   bool prof = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
   if (prof) prof = (h->prof_calls++ % (h->prof_stride > 0 ? h->prof_stride : 1)) == 0;
@@ -791,19 +1141,29 @@ int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* ou
     CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used + 1], st));
     h->prof_used += 2;
   }
-
-  if (cmvn_mode == LIDFE_CMVN_PER_UTT)
-    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, stats_cur, nullptr, st, 1, stats_nxt);
-  if (cmvn_mode == LIDFE_POST_TOPDB)
-    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, nullptr, st, 2, nullptr);
+  if (per_utt && !h->fused_apply)
+    return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, cmvn_mode == LIDFE_CMVN_PER_UTT ? 1 : 2, launch_parity);
+  CU_TRY(cudaEventRecord(p->blk->ev, st));
   return LIDFE_OK;
+}
+
+int lidfe_featurize(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
+                    const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
+                    double* stats_out_dev, void* stream) {
+  return featurize_impl(h, p, wav_dev, out_dev, out_ld, masks_dev, n_masks, cmvn_mode, stats_in_dev, stats_out_dev, stream, false);
+}
+
+int lidfe_featurize_raw(lidfe_handle h, lidfe_plan p, const void* wav_dev, float* out_dev, long long out_ld,
+                        const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
+                        double* stats_out_dev, void* stream) {
+  return featurize_impl(h, p, wav_dev, out_dev, out_ld, masks_dev, n_masks, cmvn_mode, stats_in_dev, stats_out_dev, stream, true);
 }
 
 int lidfe_cmvn_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long ld, const int* masks_dev, int n_masks,
                      const double* stats_dev, void* stream) {
   if (!h || !p || !feats_dev || !stats_dev) return LIDFE_E_NULL;
   if (p->ctx != h || ld < h->n_out || n_masks < 0 || n_masks > kMaxMasks) return LIDFE_E_ARG;
-  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, stats_dev, static_cast<cudaStream_t>(stream), 1, nullptr);
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, stats_dev, static_cast<cudaStream_t>(stream), 1);
 }
 
 int lidfe_profile_begin(lidfe_handle h, int max_launches) {
@@ -849,39 +1209,76 @@ int lidfe_mask_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long l
                      void* stream) {
   if (!h || !p || !feats_dev || !masks_dev) return LIDFE_E_NULL;
   if (p->ctx != h || ld < h->n_out || n_masks < 1 || n_masks > kMaxMasks) return LIDFE_E_ARG;
-  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, nullptr, static_cast<cudaStream_t>(stream), 0, nullptr);
-}
-
-static int launch_wave(lidfe_handle h, lidfe_plan p, const void* in, int in_i16, float in_scale, float* out, int normalize,
-                       float dither, const float* noise_dev, float preemph, void* stream) {
-  if (!h || !p || !in || !out) return LIDFE_E_NULL;
-  if (p->ctx != h || in == static_cast<const void*>(out)) return LIDFE_E_ARG;
-  if (dither != 0.f && !noise_dev) return LIDFE_E_NULL;
-  WaveParams W;
-  W.in = in;
-  W.in_i16 = in_i16;
-  W.in_scale = in_scale;
-  W.out = out;
-  W.offsets = p->d_offsets;
-  W.lengths = p->d_lengths;
-  W.normalize = normalize;
-  W.dither = dither;
-  W.noise = noise_dev;
-  W.preemph = preemph;
-  wave_stages_kernel<<<static_cast<unsigned>(p->B) * kWaveCluster, kWaveThreads, 0, static_cast<cudaStream_t>(stream)>>>(W);
-  g_launches.fetch_add(1);
-  CU_TRY(cudaGetLastError());
-  return LIDFE_OK;
+  return launch_apply(h, p, feats_dev, ld, masks_dev, n_masks, nullptr, static_cast<cudaStream_t>(stream), 0);
 }
 
 int lidfe_wave_stages(lidfe_handle h, lidfe_plan p, const float* wav_in_dev, float* wav_out_dev, int normalize,
                       float dither, const float* noise_dev, float preemph, void* stream) {
-  return launch_wave(h, p, wav_in_dev, 0, 1.f, wav_out_dev, normalize, dither, noise_dev, preemph, stream);
+  if (!wav_out_dev) return LIDFE_E_NULL;
+  return launch_wave(h, p, wav_in_dev, 0, 1.f, wav_out_dev, nullptr, normalize, dither, noise_dev, preemph, stream);
 }
 
 int lidfe_wave_stages_i16(lidfe_handle h, lidfe_plan p, const short* pcm_in_dev, float in_scale, float* wav_out_dev,
                           int normalize, float dither, const float* noise_dev, float preemph, void* stream) {
-  return launch_wave(h, p, pcm_in_dev, 1, in_scale, wav_out_dev, normalize, dither, noise_dev, preemph, stream);
+  if (!wav_out_dev) return LIDFE_E_NULL;
+  return launch_wave(h, p, pcm_in_dev, 1, in_scale, wav_out_dev, nullptr, normalize, dither, noise_dev, preemph, stream);
+}
+
+// ---- FP32 ceiling, measured (bench.py's roofline denominator) -----------------------------------------------------
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, float seed, int iters) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed + i + threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], seed, 0.5f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int lidfe_fp32_probe(float ms_budget, double* tflops_out, void* stream) {
+  if (!tflops_out) return LIDFE_E_NULL;
+  if (!(ms_budget > 0.f)) return LIDFE_E_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int threads = 256, blocks = sms * 8, iters = 4096;
+  float* out = nullptr;
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(&out), sizeof(float) * threads * blocks));
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  fp32_probe_kernel<<<blocks, threads, 0, st>>>(out, 1.0001f, iters);     // warm-up
+  double best = 0.0;
+  float spent = 0.f;
+  cudaError_t e = cudaSuccess;
+  for (int r = 0; r < 64 && spent < ms_budget && e == cudaSuccess; ++r) {
+    cudaEventRecord(e0, st);
+    fp32_probe_kernel<<<blocks, threads, 0, st>>>(out, 1.0001f, iters);
+    cudaEventRecord(e1, st);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    g_launches.fetch_add(1);
+    spent += ms;
+    if (ms > 0.f) {
+      const double tf = 2.0 * 8.0 * iters * static_cast<double>(threads) * blocks / (ms * 1e-3) / 1e12;
+      best = tf > best ? tf : best;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  *tflops_out = best;
+  return LIDFE_OK;
 }
 
 // ---- polyphase sinc resampler (row f4) ---------------------------------------------------------------------------

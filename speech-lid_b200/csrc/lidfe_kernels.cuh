@@ -46,7 +46,6 @@ constexpr int kLogmelOff = 520;                   // MFCC log-mel staging (80 pa
 __host__ __device__ constexpr int vals_off(bool mfcc) { return mfcc ? 688 : 520; }         // parked feature pairs (80 pairs)
 __host__ __device__ constexpr int scratch_floats(bool mfcc) { return mfcc ? 864 : 704; }
 constexpr int kMaxMasks = 8;
-constexpr int kTileCache = 16;                     // tile descriptors a CTA keeps in shared memory (refilled if its range is longer)
 // mel steps per band of the two banks the reference uses, for the fully unrolled kernel variants:
 // kind 1 = Kaldi 80 x 257 (20 Hz .. 8 kHz, mel = 1127 ln(1 + f/700)), kind 2 = HTK 80 x 257 (0 .. 8 kHz, 2595 log10)
 __host__ __device__ constexpr int std_taps(int kind, int b) {
@@ -62,13 +61,42 @@ struct Tile {
   int t0;               // index of the first frame inside its utterance (time masks)
   int aux;              // zero-fill tiles: number of rows to clear.  else: 1 if TMA-eligible (16B aligned)
 };
+// A SPAN is the unit of work a CTA claims: up to kMaxSpanTiles consecutive tiles of ONE utterance, described like a
+// tile whose nframes may exceed kTileFrames (the kernel cuts it into tiles itself: tile i starts 16 i frames / 2560 i
+// samples / 16 i rows further), or a run of zero-fill rows (nframes == 0, aux = rows).  Spans are listed utterance-
+// major and claimed in that order, so utterances complete progressively and the CTA that completes one can normalise
+// it while its rows are still in L2 (per-utterance CMVN / top_db in ONE kernel).
+typedef Tile Span;
+constexpr int kMaxSpanTiles = 8;
 
 struct FbankParams {
   const void* wav;
   float* out;
   long long out_ld;
-  const Tile* tiles;
-  int n_tiles;
+  const Span* spans;
+  int n_spans;
+  // dynamic schedule + per-utterance completion (all self-cleaning: the kernel leaves them as it found them)
+  int* sched;               // [0] span claim counter, [1] CTA exit counter
+  int* utt_done;            // [2][B_cap] frames of utterance i whose statistics have been handed over
+  // per-utterance second stage (CMVN / top_db).  The rows of every utterance are cut into ITEMS of <= apply_rows rows,
+  // listed utterance-major.  Every WARP of a service CTA (blockIdx.x >= n_compute; they do nothing else) and, once the
+  // spans have run out, every warp of the compute CTAs claims items one after the other (one atomic each), waits until
+  // the item's utterance has all its frames handed over, finalises the utterance's constants and rewrites the rows in
+  // place from L2.  The per-utterance bookkeeping is double buffered by launch parity: launch e works on half e & 1 and
+  // puts the other half (launch e - 1's, fully consumed) back to rest, so nothing is reset behind a reader's back.
+  int* ictl;                // [0] next item to claim
+  const int4* items;        // [n_items] (utt, first row, rows, frames of the utterance)
+  int n_items;
+  int n_compute;            // CTAs [0, n_compute) process spans; the rest are service CTAs (per-utterance modes only)
+  int k_static;             // every compute CTA starts with k_static CONSECUTIVE spans (CTA b: b * k_static ...), the rest are claimed
+  int parity;               // launch parity of this plan; B_cap = stride between the halves of the per-utterance arrays
+  int b_cap;
+  int n_utts;
+  long long* dbg_buf;       // [grid][8] per-CTA timeline (LIDFE_DBG & 16), else NULL
+  int dbg;                  // development switches (LIDFE_DBG): 1 skip apply_rows, 2 skip the stats atomics, 4 skip fences, 8 no help at span ends
+  const long long* utt_frames;      // [B]
+  const long long* utt_out_row;     // [B]
+  const long long* utt_first_tile;  // [B] (tile-blocked log-mel workspace of the two-kernel MFCC path)
   // constant tables: ONE device blob laid out exactly like the kernel's shared-memory table area, so a single TMA
   // bulk copy stages it:  window[416] | tw1[16][16] float2 = W256^(K1*t) | tw2[8][16] float2 = W512^(t+16i) |
   // mel_k0[80] int | mel (wa, wb) pairs per band [steps_b][16] (x 0.25: the power bins are left scaled by 4) |
@@ -82,17 +110,21 @@ struct FbankParams {
   int center, pad;          // LIDFE_FRAMING_CENTER: frames centred at 160 f over the constant-padded, reflect-extended signal
   const long long* utt_offsets;  // [B] first sample of each utterance (edge tiles of CENTER framing)
   const long long* utt_lengths;  // [B]
-  unsigned* utt_max;        // [B] order-preserving encoding of the utterance's max feature (LIDFE_POST_TOPDB)
-  float* tile_min;          // [n_tiles][kWarps] smallest live feature each warp saw in a tile (LIDFE_POST_TOPDB): lets the
-                            // clamp pass skip every block of rows that has nothing below max - top_db
+  unsigned* utt_max;        // [2][B_cap] order-preserving encoding of the utterance's max feature (LIDFE_POST_TOPDB); 0 at rest
+  unsigned* utt_min;        // [2][B_cap] same for its min (lets the clamp pass be skipped); 0xffffffff at rest
+  float top_db;
   int remove_dc;
+  // normalize_wav fused into the sample load (row f2): (x * in_scale - mean) / div per utterance, or NULL
+  const float2* utt_wnorm;  // [B] (mean, std + 1e-6) from wave_stats
+  float dither;             // > 0: x += dither * U[0,1), Philox keyed by (seed, utterance, sample) (ref: lid/audio_processor.py:129), KALDI framing
+  unsigned long long seed;
   // epilogue
   const int* masks;         // [B][n_masks][4]
   int n_masks;
   int mode;                 // LIDFE_CMVN_*
   const double* stats_in;   // [2*n_out+1]
   double* stats_out;        // [2*n_out+1]
-  double* utt_stats;        // [B][2][n_out]
+  double* utt_stats;        // [2][B_cap][2][n_out], zero at rest
   // two-kernel MFCC path: `out` is the log-mel workspace in the tile-blocked layout mfcc_dct_kernel reads,
   // [tile][n_out / 4][16 frames][4 dims] (a 16-byte chunk = 4 consecutive dims of one frame; the 16 frames of a tile
   // sit next to each other so that a half-warp of the DCT kernel loads 256 contiguous bytes)
@@ -279,17 +311,179 @@ struct SmemLayout {
   static constexpr int off_in0 = 0;                                                // ONE input buffer (see the tile loop)
   static constexpr int off_scratch = kInBytes;                                     // [2*kWarps][scratch_floats] floats
   static constexpr int off_norm = off_scratch + 2 * kWarps * scratch_floats(kMfcc) * 4;   // [80] float2 (mean, inv_std)
-  static constexpr int off_acc = off_norm + kMaxMels * 8;                          // fp64: [kWarps][2][80] per-warp sums + frame count
-  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 4) * 8;      // [1 staged + kWarps private][kMaxMasks][4] int
-  static constexpr int off_bar = off_masks + (1 + kWarps) * kMaxMasks * 16;        // mbarriers: full, tables; then the arrival counter
-  static constexpr int off_tiles = off_bar + 48;                                   // [kTileCache] Tile descriptors
+  static constexpr int off_lo = off_norm + kMaxMels * 8;                           // [80] float: -(mean - (float)mean) * inv_std
+  static constexpr int off_acc = off_lo + kMaxMels * 4;                            // fp64: [kWarps][2][80] per-warp sums + frame count + wmax/wmin
+  static constexpr int off_masks = off_acc + (kWarps * 2 * kMaxMels + 6) * 8;      // [kMaxMasks][4] int: the current span's utterance
+  static constexpr int off_bar = off_masks + kMaxMasks * 16;                       // mbarriers: full @0, tables @16; arrival counter @32; ctl ints @36..
+  static constexpr int off_span = off_bar + 64;                                    // [2] Span descriptors: current, next (prefetched by cp.async)
   // constant tables, one contiguous block = the device blob (see FbankParams::const_blob)
-  static constexpr int off_window = off_tiles + kTileCache * 32;                   // [416]
+  static constexpr int off_window = off_span + 2 * 32;                             // [416]
   static constexpr int off_tw1 = off_window + 416 * 4;                             // [16][16] float2
   static constexpr int off_tw2 = off_tw1 + 256 * 8;                                // [8][16] float2
   static constexpr int off_k0 = off_tw2 + 128 * 8;                                 // [80] int
   static constexpr int off_melw = off_k0 + kMaxMels * 4;                           // sum(band_taps)*16 float2, then dct, lifter
 };
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {   // L2 load: the rows were written by other SMs
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_cg_f(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+// x / d with r = 1 / d rounded to nearest: quotient, residual, correction (the division sequence without its scaling
+// fix-ups; samples and 1/std are far from the exponent limits).  Shared by wave_stages_kernel and the fused load, so
+// the two normalize_wav paths produce the same bits.
+__device__ __forceinline__ float div_by(float x, float d, float r) {
+  const float q = __fmul_rn(x, r);
+  return __fmaf_rn(__fmaf_rn(-d, q, x), r, q);
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so the dither of sample i of utterance u is a pure function of
+// (seed, u, i) -- no state, no host-drawn noise buffer crossing PCIe, the same value whichever thread asks for it.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// U[0,1) with torch.rand's float32 resolution (24 random bits * 2^-24), keyed by (seed, utterance, sample)
+__device__ __forceinline__ float dither_uniform(unsigned long long seed, int utt, long long i) {
+  const unsigned long long blk = static_cast<unsigned long long>(i) >> 2;
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), static_cast<uint32_t>(utt), 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const int e = static_cast<int>(i & 3);
+  const uint32_t v = e == 0 ? r.x : e == 1 ? r.y : e == 2 ? r.z : r.w;
+  return static_cast<float>(v >> 8) * 5.9604644775390625e-08f;
+}
+
+// the same stream for the even/odd pair (i, i + 1), i even: one Philox block covers both
+__device__ __forceinline__ float2 dither_pair(unsigned long long seed, int utt, long long i) {
+  const unsigned long long blk = static_cast<unsigned long long>(i) >> 2;
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), static_cast<uint32_t>(utt), 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const bool hi = (i & 2) != 0;
+  return make_float2(static_cast<float>((hi ? r.z : r.x) >> 8) * 5.9604644775390625e-08f,
+                     static_cast<float>((hi ? r.w : r.y) >> 8) * 5.9604644775390625e-08f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-utterance second stage, run by the CTA that completed the utterance's statistics, on rows that are still in L2:
+// per-utterance CMVN (x - mean) / (std + 1e-9) or AmplitudeToDB's clamp at max - top_db, then the SpecAugment zero-fill.
+// kind: 1 = CMVN, 2 = top_db clamp.  Fast path (80 dims, 16-byte aligned rows): thread i owns float4 i, i + 128, ... of
+// a 32-row block; 32 rows x 20 float4 = 640 = 5 x 128, so the five columns a thread meets repeat block after block and
+// their constants live in registers.
+// ------------------------------------------------------------------------------------------------
+// Rewrites rows [r0, r0 + rows) of utterance utt in place, ONE WARP.  kind 1: (x - mean) * inv + lo per dim (constants
+// in shared memory, float4 triples per 4 dims), kind 2: max(x, db_floor); then the SpecAugment zero-fill.  Fast path (80
+// dims, 16-byte aligned rows): lane l owns float4 l, l + 32, ... of the block, 8 loads in flight per lane.
+__device__ __forceinline__ void apply_rows_warp(float* __restrict__ base, long long out_ld, int n_out, int nm, bool fast, int r0, int rows,
+                                             int kind, float db_floor, const float4* __restrict__ sm_c4, const int* __restrict__ sm_masks) {
+  // (everything by value: through a reference to the kernel's parameter block every store was preceded by a generic
+  //  re-load of out_ld -- the stores might alias it -- and a round of 8 stores cost 8 dependent memory latencies)
+  const int lane = threadIdx.x & 31;
+  if (fast) {
+    // Groups of 8 rows = 160 float4 = 5 per lane: lane l owns float4 l + 32 m (m = 0..4) of every group, i.e. five FIXED
+    // (row offset, column) pairs -- no division in the loop, the frequency-mask verdicts are five 4-bit constants, the
+    // normalisation constants five fixed shared-memory addresses.  Two groups (10 loads) are in flight per lane.
+    int roff[5], col[5];
+    unsigned fz = 0u;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const int i = lane + 32 * m;
+      roff[m] = i / 20;
+      col[m] = i - roff[m] * 20;
+      for (int q = 0; q < nm; ++q) {
+        const int f0 = sm_masks[4 * q + 2], f1 = sm_masks[4 * q + 3];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fz |= (4 * col[m] + e >= f0 && 4 * col[m] + e < f1) ? (1u << (4 * m + e)) : 0u;
+      }
+    }
+    // time masks as (start, end) rows relative to this block; at most 4 are kept in registers
+    int t0[4], t1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      t0[q] = (q < nm) ? sm_masks[4 * q] - r0 : 0;
+      t1[q] = (q < nm) ? sm_masks[4 * q + 1] - r0 : 0;
+    }
+    const long long ld4 = out_ld >> 2;
+    float4* g = reinterpret_cast<float4*>(base);
+    for (int rb = 0; rb < rows; rb += 16) {
+      float4 x[10];
+#pragma unroll
+      for (int u = 0; u < 10; ++u) {
+        const int row = rb + (u / 5) * 8 + roff[u % 5];
+        if (row < rows) x[u] = g[row * ld4 + col[u % 5]];
+      }
+#pragma unroll
+      for (int u = 0; u < 10; ++u) {
+        const int m = u % 5;
+        const int row = rb + (u / 5) * 8 + roff[m];
+        if (row >= rows) continue;
+        float4 v = x[u];
+        if (kind == 1) {
+          const float4 mean = sm_c4[col[m]], inv = sm_c4[20 + col[m]], lo = sm_c4[40 + col[m]];
+          v.x = fmaf(v.x - mean.x, inv.x, lo.x);      // (x - mean_hi) * inv - mean_lo * inv
+          v.y = fmaf(v.y - mean.y, inv.y, lo.y);
+          v.z = fmaf(v.z - mean.z, inv.z, lo.z);
+          v.w = fmaf(v.w - mean.w, inv.w, lo.w);
+        } else {
+          v.x = fmaxf(v.x, db_floor);
+          v.y = fmaxf(v.y, db_floor);
+          v.z = fmaxf(v.z, db_floor);
+          v.w = fmaxf(v.w, db_floor);
+        }
+        bool zr = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) zr |= (row >= t0[q] && row < t1[q]);
+        for (int q = 4; q < nm; ++q) zr |= (r0 + row >= sm_masks[4 * q] && r0 + row < sm_masks[4 * q + 1]);
+        const unsigned z = zr ? 0xfu : ((fz >> (4 * m)) & 0xfu);
+        v.x = (z & 1u) ? 0.f : v.x;
+        v.y = (z & 2u) ? 0.f : v.y;
+        v.z = (z & 4u) ? 0.f : v.z;
+        v.w = (z & 8u) ? 0.f : v.w;
+        g[row * ld4 + col[m]] = v;
+      }
+    }
+  } else {
+    const float* sm_c = reinterpret_cast<const float*>(sm_c4);     // mean[80] | inv[80] | lo[80]
+    const int total = rows * n_out;
+    for (int i = lane; i < total; i += 32) {
+      const int rw = i / n_out;
+      const int d = i - rw * n_out;
+      float* p = base + static_cast<long long>(rw) * out_ld + d;
+      float xv = *p;
+      if (kind == 1) xv = fmaf(xv - sm_c[d], sm_c[kMaxMels + d], sm_c[2 * kMaxMels + d]);
+      else xv = fmaxf(xv, db_floor);
+      const int tf = r0 + rw;
+      bool z = false;
+      for (int q = 0; q < nm; ++q)
+        z |= (tf >= sm_masks[4 * q] && tf < sm_masks[4 * q + 1]) || (d >= sm_masks[4 * q + 2] && d < sm_masks[4 * q + 3]);
+      *p = z ? 0.f : xv;
+    }
+  }
+}
+__device__ __forceinline__ int ld_volatile_i(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // the fused front-end kernel
@@ -307,11 +501,14 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
   const float2* const sm_tw2 = reinterpret_cast<const float2*>(smem + L::off_tw2);
   const int* const sm_k0 = reinterpret_cast<const int*>(smem + L::off_k0);
   float2* const sm_norm = reinterpret_cast<float2*>(smem + L::off_norm);
+  float* const sm_lo = reinterpret_cast<float*>(smem + L::off_lo);
   double* const sm_acc = reinterpret_cast<double*>(smem + L::off_acc);
+  float* const sm_wmax = reinterpret_cast<float*>(sm_acc + kWarps * 2 * kMaxMels + 2);   // [kWarps] max, then [kWarps] min
   int* const sm_masks = reinterpret_cast<int*>(smem + L::off_masks);
   uint64_t* const sm_bar = reinterpret_cast<uint64_t*>(smem + L::off_bar);
-  int* const sm_arrivals = reinterpret_cast<int*>(smem + L::off_bar + 40);   // warps that have consumed the current tile's samples (running count)
-  Tile* const sm_tiles = reinterpret_cast<Tile*>(smem + L::off_tiles);
+  int* const sm_arrivals = reinterpret_cast<int*>(smem + L::off_bar + 32);   // warps that have consumed the current tile's samples (running count)
+  volatile int* const sm_ctl = reinterpret_cast<volatile int*>(smem + L::off_bar + 36);   // [0], [1] next span (ping-pong with the span slots), [2..6] service_item scratch, [5] also the exit flag
+  Span* const sm_span = reinterpret_cast<Span*>(smem + L::off_span);
   float* const sm_melw = reinterpret_cast<float*>(smem + L::off_melw);
 
   const int tid = threadIdx.x;
@@ -335,53 +532,50 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
   float* const sm_dct = sm_melw + tap_off[kBands] * 32;
   float* const sm_lifter = sm_dct + (kMfcc ? ((P.n_mels * P.n_ceps + 3) & ~3) : 0);   // sections padded to 16 B
 
-  // this CTA's contiguous tile range (neighbouring tiles share their halo in L2 and their utterance's statistics)
-  const long long nt = P.n_tiles;
-  const int tile_begin = static_cast<int>((nt * blockIdx.x) / gridDim.x);
-  const int tile_end = static_cast<int>((nt * (blockIdx.x + 1)) / gridDim.x);
-
   // ---- one-time staging: all constant tables arrive with ONE TMA bulk copy while the CTA sets up the rest ------
   if (tid == 0) {
-    mbar_init(&sm_bar[0], 1);            // full: samples (and mask table) of the staged tile have landed
+    mbar_init(&sm_bar[0], 1);            // full: samples of the staged tile have landed
     mbar_init(&sm_bar[2], 1);            // constant tables have landed
     *sm_arrivals = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&sm_bar[2], static_cast<uint32_t>(P.const_bytes));
     tma_bulk_g2s_plain(smem + L::off_window, P.const_blob, static_cast<uint32_t>(P.const_bytes), &sm_bar[2]);
   }
-  {
-    {   // descriptors of the first kTileCache tiles of the range (4 x 8-byte words each)
-      const int n = min(tile_end - tile_begin, kTileCache);
-      const long long* src = reinterpret_cast<const long long*>(P.tiles + tile_begin);
-      long long* dst = reinterpret_cast<long long*>(sm_tiles);
-      for (int i = tid; i < n * 4; i += kThreads) dst[i] = src[i];
-    }
-    for (int i = tid; i < kWarps * 2 * kMaxMels + 2; i += kThreads) sm_acc[i] = 0.0;
-    if (tid < kWarps) reinterpret_cast<float*>(sm_acc + kWarps * 2 * kMaxMels + 2)[tid] = -INFINITY;
-    if (mode == 2 && tid < n_out) {
-      // finalise the all-reduced sums: mean, 1/(std + 1e-9) (unbiased)
-      const double n = P.stats_in[2 * n_out];
-      const double mean = P.stats_in[tid] / n;
-      double var = (P.stats_in[n_out + tid] - P.stats_in[tid] * mean) / (n - 1.0);
-      var = var > 0.0 ? var : 0.0;
-      sm_norm[tid] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / (sqrt(var) + 1e-9)));
-    }
+  // Work is claimed span by span in utterance-major order: the first span is this CTA's index, every later one comes
+  // from a global counter (claimed one span ahead by thread 0, so the atomic's latency hides behind a whole span; the
+  // claimed span's descriptor is fetched into the spare slot by cp.async).  Dynamic claims keep the CTAs balanced
+  // when some of them stop to normalise an utterance.
+  long long t_start = 0, n_sp = 0, n_blk = 0;
+  if (P.dbg_buf && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+  int span_idx = blockIdx.x * P.k_static;
+  int pend = 0;                                                                   // thread 0: the span after this one
+  if (tid < 2 && span_idx < P.n_spans) reinterpret_cast<int4*>(&sm_span[0])[tid] = __ldg(reinterpret_cast<const int4*>(P.spans + span_idx) + tid);
+  // Every compute CTA first walks k_static consecutive spans of its own (neighbouring spans share their utterance, so
+  // per-utterance sums leave the CTA about twice, and no atomics are spent), then claims the remaining ~15 % of the
+  // spans one by one from a global counter, which keeps the CTAs balanced to the end.  (Service CTAs take none.)
+  const int n_compute = (P.mode == 1 || P.mode == 4) ? P.n_compute : static_cast<int>(gridDim.x);
+  const int n_static = n_compute * P.k_static;
+  int k_mine = 1;                                                                 // thread 0: spans taken so far
+  if (tid == 0 && static_cast<int>(blockIdx.x) < n_compute) pend = (P.k_static > 1) ? span_idx + 1 : n_static + atomicAdd(&P.sched[0], 1);
+  for (int i = tid; i < kWarps * 2 * kMaxMels + 2; i += kThreads) sm_acc[i] = 0.0;
+  if (tid < kWarps) { sm_wmax[tid] = -INFINITY; sm_wmax[kWarps + tid] = INFINITY; }
+  if (mode == 2 && tid < n_out) {
+    // finalise the all-reduced sums: mean, 1/(std + 1e-9) (unbiased)
+    const double n = P.stats_in[2 * n_out];
+    const double mean = P.stats_in[tid] / n;
+    double var = (P.stats_in[n_out + tid] - P.stats_in[tid] * mean) / (n - 1.0);
+    var = var > 0.0 ? var : 0.0;
+    sm_norm[tid] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / (sqrt(var) + 1e-9)));
   }
-  __syncthreads();   // mbarriers initialised, descriptors cached
+  __syncthreads();   // mbarriers initialised, first span descriptor in place
 
-  // Producer side.  There is ONE input buffer and no CTA-wide barrier per tile: every warp bumps a shared arrival counter
-  // once it has consumed its samples (right after the framing stage, ~15 % into a tile); the warp that arrives last
-  // knows the buffer -- and the staged mask table -- is free and immediately stages the next tile (TMA bulk copy), so
-  // the copy overlaps the remaining ~85 % of the current tile.  Consumers wait on the "full" mbarrier.
+  // Producer side of the sample staging.  There is ONE input buffer and no CTA-wide barrier per tile: every warp bumps a
+  // shared arrival counter once it has consumed its samples (right after the framing stage, ~15 % into a tile); the
+  // warp that arrives last knows the buffer is free and immediately stages the span's next tile (TMA bulk copy), so the
+  // copy overlaps the remaining ~85 % of the current tile.  Consumers wait on the "full" mbarrier.  Every tile of a span
+  // takes exactly kWarps arrivals (zero-fill rows are spans of their own, handled between two CTA barriers).
   const bool stage_masks = (mode == 0 || mode == 2) && P.n_masks > 0;
-  auto stage_tile = [&](int tile_idx) {          // called by exactly one warp per tile
-    if (tile_idx >= tile_end) return;
-    const Tile tl = sm_tiles[(tile_idx - tile_begin) % kTileCache];
-    if (tl.nframes == 0) return;
-    if (stage_masks) {
-      if (lane < P.n_masks * 4) sm_masks[lane] = P.masks[static_cast<long long>(tl.utt) * P.n_masks * 4 + lane];
-      __syncwarp();
-    }
+  auto stage_tile = [&](const Tile& tl) {          // called by exactly one warp per tile
     const int nsamp = kFrameShift * tl.nframes + (kFrameLen - kFrameShift);
     const TIn* src = reinterpret_cast<const TIn*>(P.wav) + tl.wav_off;
     TIn* dst = sm_in;
@@ -400,11 +594,11 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
         // once at either end like torch.stft(center=True, pad_mode="reflect"); zeros inside the constant padding
         const long long N = P.utt_lengths[tl.utt];
         const TIn* x = reinterpret_cast<const TIn*>(P.wav) + P.utt_offsets[tl.utt];
-        const long long L = N + 2 * P.pad;
+        const long long Lp = N + 2 * P.pad;
         const long long u0 = static_cast<long long>(kFrameShift) * tl.t0 - (kFrameLen / 2);
         for (int i = lane; i < nsamp; i += 32) {
           long long u = u0 + i;
-          u = u < 0 ? -u : (u >= L ? 2 * (L - 1) - u : u);
+          u = u < 0 ? -u : (u >= Lp ? 2 * (Lp - 1) - u : u);
           const long long r = u - P.pad;
           dst[i] = (r >= 0 && r < N) ? x[r] : static_cast<TIn>(0);
         }
@@ -427,404 +621,521 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
   const int partner = (lane & 16) | ((16 - t) & 15);
   const int up_lane = (lane & 16) | ((t - 1) & 15);
 
-  if (warp == 0) stage_tile(tile_begin);   // first tile's samples are in flight while the tables land
   mbar_wait(&sm_bar[2], 0u);
   int k0[kBands];
 #pragma unroll
   for (int b = 0; b < kBands; ++b) k0[b] = sm_k0[t + 16 * b];
 
-  int cur_utt = -1;
-  unsigned dim_masked = 0u;   // bit b: output dim t+16b is inside a frequency mask of the current utterance
+  double frames_acc = 0.0;    // mode 3: frames this CTA has added to its sums (thread kThreads - 1)
+  int frames_held = 0, held_utt = -1;   // per-utterance modes: frames in the CTA's accumulators, and whose they are
+  int cur = 0;                // which sm_span slot holds the current span
 
-  int it = 0;
-  for (int tile_idx = tile_begin; tile_idx < tile_end; ++tile_idx, ++it) {
-    const Tile tl = sm_tiles[it % kTileCache];
-    if (__builtin_expect((it + 1) % kTileCache == 0 && tile_idx + 1 < tile_end, 0)) {
-      // descriptor cache exhausted (ranges longer than kTileCache tiles): refill.  Everyone has its copy of `tl`.
-      __syncthreads();
-      const int n = min(tile_end - (tile_idx + 1), kTileCache);
-      const long long* src = reinterpret_cast<const long long*>(P.tiles + tile_idx + 1);
-      long long* dst = reinterpret_cast<long long*>(sm_tiles);
-      for (int i = tid; i < n * 4; i += kThreads) dst[i] = src[i];
-      __syncthreads();
+  // Second stage of the per-utterance modes (see FbankParams::items), one warp at a time, no CTA barrier anywhere: the
+  // warp takes the item it claimed one item ago (and claims the next right away, so that the atomic's and the
+  // descriptor's round trips hide behind the rows), waits for the utterance, finalises its constants from the
+  // handed-over sums (fp64) into its own scratch, and rewrites the rows.  The warp that meets an utterance's FIRST item
+  // also puts the other launch parity's bookkeeping of that utterance back to rest.
+  const int par = P.parity & 1;
+  int* const done_cur = P.utt_done + par * P.b_cap;
+  unsigned* const max_cur = P.utt_max + par * P.b_cap;
+  unsigned* const min_cur = P.utt_min + par * P.b_cap;
+  double* const stats_cur = P.utt_stats + static_cast<long long>(par) * P.b_cap * 2 * n_out;
+  auto service_warp = [&]() {
+    float4* const c4 = reinterpret_cast<float4*>(sm_scratch + warp * 2 * kScratchFloats);   // [60] float4: mean | inv | lo
+    float* const cf = reinterpret_cast<float*>(c4);
+    int* const wmasks = reinterpret_cast<int*>(cf + 3 * kMaxMels);                            // [kMaxMasks][4]
+    int nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&P.ictl[0], 1);
+    for (;;) {
+      int4 item = make_int4(-1, 0, 0, 0);
+      if (lane == 0) {
+        const int it = nxt;
+        if (it < P.n_items) {
+          nxt = atomicAdd(&P.ictl[0], 1);                        // the item after this one: in flight during the rows
+          item = __ldg(&P.items[it]);
+          while (ld_volatile_i(&done_cur[item.x]) != item.w) __nanosleep(100);
+          __threadfence();                                       // acquire: the utterance's sums and rows
+        }
+      }
+      item.x = __shfl_sync(0xffffffffu, item.x, 0);
+      item.y = __shfl_sync(0xffffffffu, item.y, 0);
+      item.z = __shfl_sync(0xffffffffu, item.z, 0);
+      item.w = __shfl_sync(0xffffffffu, item.w, 0);
+      if (item.x < 0) break;
+      const int utt = item.x;
+      float db_floor = 0.f;
+      bool skip = false;
+      if (mode == 1) {
+        for (int d = lane; d < n_out; d += 32) {
+          const double n = static_cast<double>(item.w);
+          const double sm = __ldcg(stats_cur + (static_cast<long long>(utt) * 2 + 0) * n_out + d);
+          const double ss = __ldcg(stats_cur + (static_cast<long long>(utt) * 2 + 1) * n_out + d);
+          const double mu = sm / n;
+          double var = (ss - sm * mu) / (n - 1.0);   // n == 1 -> NaN, as torch.std of one sample
+          var = var > 0.0 ? var : (var == var ? 0.0 : var);
+          const float mean = static_cast<float>(mu);
+          cf[d] = mean;
+          cf[kMaxMels + d] = static_cast<float>(1.0 / (sqrt(var) + 1e-9));
+          cf[2 * kMaxMels + d] = static_cast<float>(-(mu - static_cast<double>(mean)) / (sqrt(var) + 1e-9));   // keeps x - mean accurate when std << |mean|
+        }
+      } else {
+        const float mx = ord2f(__ldcg(&max_cur[utt])), mn = ord2f(__ldcg(&min_cur[utt]));
+        db_floor = mx - P.top_db;
+        skip = (mn >= db_floor) && P.n_masks == 0;      // nothing below max - top_db: the clamp is the identity
+      }
+      if (P.n_masks > 0 && lane < P.n_masks * 4) wmasks[lane] = P.masks[static_cast<long long>(utt) * P.n_masks * 4 + lane];
+      if (item.y == 0) {   // first item of the utterance: the previous launch's half goes back to rest
+        const int op = par ^ 1;
+        double* os = P.utt_stats + (static_cast<long long>(op) * P.b_cap + utt) * 2 * n_out;
+        for (int e = lane; e < 2 * n_out; e += 32) os[e] = 0.0;
+        if (lane == 0) {
+          P.utt_done[op * P.b_cap + utt] = 0;
+          P.utt_max[op * P.b_cap + utt] = 0u;
+          P.utt_min[op * P.b_cap + utt] = 0xffffffffu;
+        }
+      }
+      __syncwarp();
+      if (!skip && !(P.dbg & 1)) {
+        const bool fast = (n_out == 80) && (P.out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
+        apply_rows_warp(P.out + (P.utt_out_row[utt] + item.y) * P.out_ld, P.out_ld, n_out, P.n_masks, fast, item.y, item.z,
+                        mode == 1 ? 1 : 2, db_floor, c4, wmasks);
+      }
+      __syncwarp();                                              // the constants are free again
+      ++n_blk;
     }
+  };
+  const bool per_utt_mode = (mode == 1 || mode == 4);
+  const bool service = per_utt_mode && static_cast<int>(blockIdx.x) >= P.n_compute;
+  if (service || static_cast<int>(blockIdx.x) >= n_compute) span_idx = P.n_spans;
+  while (span_idx < P.n_spans) {
+    const Span sp = sm_span[cur];
+    bool fetched = false;     // thread 0: the next span's descriptor copy has been issued
+    auto fetch_next = [&]() {
+      if (tid == 0 && !fetched) {
+        fetched = true;
+        if (pend < P.n_spans) {
+          cp_async16(reinterpret_cast<int4*>(&sm_span[cur ^ 1]), reinterpret_cast<const int4*>(P.spans + pend));
+          cp_async16(reinterpret_cast<int4*>(&sm_span[cur ^ 1]) + 1, reinterpret_cast<const int4*>(P.spans + pend) + 1);
+        }
+        cp_async_commit();
+      }
+    };
 
-    if (__builtin_expect(tl.nframes == 0, 0)) {
-      // zero-fill tile: pad_sequence's zeros (ref: lid/raw_datasets.py:347-350)
-      const long long total = P.ws_blocked ? 0 : static_cast<long long>(tl.aux) * n_out;   // (the DCT kernel fills them)
+    if (__builtin_expect(sp.nframes == 0, 0)) {
+      // zero-fill span: pad_sequence's zeros (ref: lid/raw_datasets.py:347-350)
+      fetch_next();
+      const long long total = P.ws_blocked ? 0 : static_cast<long long>(sp.aux) * n_out;   // (the DCT kernel fills them)
       for (long long i = tid; i < total; i += kThreads) {
         const long long r = i / n_out;
         const int d = static_cast<int>(i - r * n_out);
-        P.out[(tl.out_row + r) * P.out_ld + d] = 0.f;
+        P.out[(sp.out_row + r) * P.out_ld + d] = 0.f;
       }
-      if (arrive_is_last()) stage_tile(tile_idx + 1);
-      continue;
-    }
-
-    // consumer side: wait for this tile's samples (and mask table), take a private copy of the masks
-    mbar_wait(&sm_bar[0], phase);
-    phase ^= 1u;
-    const TIn* in = sm_in;
-    int* const wm = sm_masks + (1 + warp) * kMaxMasks * 4;
-    if (stage_masks) {
-      __syncwarp();                                  // previous tile's readers of this warp's copy are done
-      if (lane < P.n_masks * 4) wm[lane] = sm_masks[lane];
-      __syncwarp();
-      if (__builtin_expect(tl.utt != cur_utt, 0)) {
-        cur_utt = tl.utt;
-        dim_masked = 0u;
+    } else {
+      // ---- per-span set-up: the utterance's mask table, normalize_wav constants, edge-tile geometry ----------
+      unsigned dim_masked = 0u;   // bit b: output dim t+16b is inside a frequency mask of the span's utterance
+      if (stage_masks) {
+        if (tid < P.n_masks * 4) sm_masks[tid] = P.masks[static_cast<long long>(sp.utt) * P.n_masks * 4 + tid];
+        __syncthreads();
         for (int q = 0; q < P.n_masks; ++q) {
-          const int f0 = wm[4 * q + 2], f1 = wm[4 * q + 3];
+          const int f0 = sm_masks[4 * q + 2], f1 = sm_masks[4 * q + 3];
 #pragma unroll
           for (int b = 0; b < kBands; ++b) dim_masked |= (t + 16 * b >= f0 && t + 16 * b < f1) ? (1u << b) : 0u;
         }
       }
-    }
-
-    f2 val[kBands];
-    const int flA = warp * 4 + half * 2;          // frame A inside the tile; B = A + 1
-    const bool actA = flA < tl.nframes, actB = flA + 1 < tl.nframes;
-    {
-      // Frame B starts 160 samples = 5 x 32 after frame A, so lane t's element j of B is its element j+5 of A:
-      // 18 loads cover both frames.  A pair whose frame B lies beyond the utterance (odd tail) still reads valid
-      // shared memory; an entirely dead pair recomputes frame 0.  Neither is stored nor counted.
-      const TIn* fr = in + kFrameShift * (actA ? flA : 0);
-
-      // ---- load, DC removal, pre-emphasis, window (ta: compliance/kaldi.py:183-204) ---------------
-      f2 R[16], I[16];     // R[j] = (re_A, re_B), I[j] = (im_A, im_B) of z[t + 16 j]
-      {
-        float2 x[18];
-#pragma unroll
-        for (int j = 0; j < 18; ++j) {
-          const int n = t + 16 * j;
-          x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
+      const int* const wm = sm_masks;
+      const bool wnorm = P.utt_wnorm != nullptr;
+      float wn_mean = 0.f, wn_div = 1.f, wn_rcp = 1.f;
+      if (wnorm) {
+        const float2 wn = P.utt_wnorm[sp.utt];
+        wn_mean = wn.x;
+        wn_div = wn.y;
+        wn_rcp = __frcp_rn(wn.y);
+      }
+      const long long utt_len = P.center ? P.utt_lengths[sp.utt] : 0;
+      const long long tile0 = P.ws_blocked ? P.utt_first_tile[sp.utt] + sp.t0 / kTileFrames : 0;
+      const int n_tiles = (sp.nframes + kTileFrames - 1) / kTileFrames;
+      auto tile_of = [&](int ti) {
+        Tile tl;
+        tl.wav_off = sp.wav_off + static_cast<long long>(ti) * (kTileFrames * kFrameShift);
+        tl.out_row = sp.out_row + ti * kTileFrames;
+        tl.nframes = min(kTileFrames, sp.nframes - ti * kTileFrames);
+        tl.utt = sp.utt;
+        tl.t0 = sp.t0 + ti * kTileFrames;
+        tl.aux = sp.aux;
+        if (P.center) {    // tiles that touch the constant padding / the reflection are staged element-wise
+          const long long rel = static_cast<long long>(tl.t0) * kFrameShift - kFrameLen / 2 - P.pad;
+          const long long nsamp = static_cast<long long>(kFrameShift) * tl.nframes + (kFrameLen - kFrameShift);
+          if (!(rel >= 0 && rel + nsamp <= utt_len)) tl.aux = 0;
         }
-        float mA = 0.f, mB = 0.f;
-        if (kStdMel == 1 || (kStdMel == 0 && P.remove_dc)) {
-          f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
+        return tl;
+      };
+      if (warp == 0) stage_tile(tile_of(0));
+
+      for (int ti = 0; ti < n_tiles; ++ti) {
+        const Tile tl = tile_of(ti);
+        const long long tile_idx = tile0 + ti;
+        // consumer side: wait for this tile's samples
+        mbar_wait(&sm_bar[0], phase);
+        phase ^= 1u;
+        const TIn* in = sm_in;
+
+        f2 val[kBands];
+        const int flA = warp * 4 + half * 2;          // frame A inside the tile; B = A + 1
+        const bool actA = flA < tl.nframes, actB = flA + 1 < tl.nframes;
+        {
+          // Frame B starts 160 samples = 5 x 32 after frame A, so lane t's element j of B is its element j+5 of A:
+          // 18 loads cover both frames.  A pair whose frame B lies beyond the utterance (odd tail) still reads valid
+          // shared memory; an entirely dead pair recomputes frame 0.  Neither is stored nor counted.
+          const TIn* fr = in + kFrameShift * (actA ? flA : 0);
+
+          // ---- load, DC removal, pre-emphasis, window (ta: compliance/kaldi.py:183-204) ---------------
+          f2 R[16], I[16];     // R[j] = (re_A, re_B), I[j] = (im_A, im_B) of z[t + 16 j]
+          {
+            float2 x[18];
+    #pragma unroll
+            for (int j = 0; j < 18; ++j) {
+              const int n = t + 16 * j;
+              x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
+            }
+            if (wnorm) {   // normalize_wav while loading (row f2): (x - mean) / (std + 1e-6), the division as in wave_stages_kernel
 #pragma unroll
-          for (int j = 0; j < 13; ++j) {
-            if (j < 12 || t < 8) {
-              sA = add2(sA, x[j]);
-              sB = add2(sB, x[j + 5]);
+              for (int j = 0; j < 18; ++j) {
+                x[j].x = div_by(__fsub_rn(x[j].x, wn_mean), wn_div, wn_rcp);
+                x[j].y = div_by(__fsub_rn(x[j].y, wn_mean), wn_div, wn_rcp);
+              }
+            }
+            if (P.dither != 0.f) {   // in-kernel dither: every frame that loads sample i adds the same noise to it
+              const long long s0 = static_cast<long long>(kFrameShift) * (tl.t0 + (actA ? flA : 0));
+#pragma unroll
+              for (int j = 0; j < 18; ++j) {
+                const float2 u = dither_pair(P.seed, tl.utt, s0 + 2 * (t + 16 * j));
+                x[j].x = __fadd_rn(x[j].x, __fmul_rn(P.dither, u.x));
+                x[j].y = __fadd_rn(x[j].y, __fmul_rn(P.dither, u.y));
+              }
+            }
+            float mA = 0.f, mB = 0.f;
+            if (kStdMel == 1 || (kStdMel == 0 && P.remove_dc)) {
+              f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
+    #pragma unroll
+              for (int j = 0; j < 13; ++j) {
+                if (j < 12 || t < 8) {
+                  sA = add2(sA, x[j]);
+                  sB = add2(sB, x[j + 5]);
+                }
+              }
+              f2 sum = make_float2(sA.x + sA.y, sB.x + sB.y);
+    #pragma unroll
+              for (int o = 8; o >= 1; o >>= 1) {
+                sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+                sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+              }
+              mA = __fdiv_rn(sum.x, static_cast<float>(kFrameLen));
+              mB = __fdiv_rn(sum.y, static_cast<float>(kFrameLen));
+            }
+            const float c = P.preemph;
+            // One pass over the 13 sample pairs: (A,B) pairs are formed by the mean subtraction itself (scalar FADDs write
+            // straight into the pair halves); x[2n-1] - mean lives in lane t-1 (same j), lane 0 takes lane 15's value of
+            // step j-1, and the very first sample of the frame replicates itself (ta: compliance/kaldi.py:193-198).
+            // x[j] - c * x[j-1]: product and difference rounded separately, as the reference's two tensor ops; with the
+            // reference's c == 1.0 the product is exact, so that (warp-uniform) variant skips the multiplies.
+            auto frame_pass = [&](auto unit_tag) {
+              constexpr bool kUnit = decltype(unit_tag)::value;
+              f2 to_prev = make_float2(0.f, 0.f);
+    #pragma unroll
+              for (int j = 0; j < 13; ++j) {
+                const int n = t + 16 * j;
+                const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
+                const f2 te = make_float2(__fsub_rn(x[j].x, mA), __fsub_rn(x[j + 5].x, mB));   // x[2n]   - mean
+                const f2 to = make_float2(__fsub_rn(x[j].y, mA), __fsub_rn(x[j + 5].y, mB));   // x[2n+1] - mean
+                const f2 send = (t == 15) ? to_prev : to;
+                f2 tp;
+                tp.x = __shfl_sync(0xffffffffu, send.x, up_lane);
+                tp.y = __shfl_sync(0xffffffffu, send.y, up_lane);
+                if (j == 0 && t == 0) tp = te;
+                to_prev = to;
+                const f2 se = kUnit ? sub2(te, tp) : sub2(te, mul2(tp, bc(c)));
+                const f2 so = kUnit ? sub2(to, te) : sub2(to, mul2(te, bc(c)));
+                R[j] = mul2(se, bc(w.x));
+                I[j] = mul2(so, bc(w.y));
+              }
+            };
+            // The framing flavour is fixed per kernel variant (kStdMel: 1 = the reference's Kaldi call, DC removal +
+            // coefficient 1.0; 2 = its torch.stft call, window only; 0 = anything else), so that every instantiation
+            // carries one copy of this loop: the tile body has to stay inside the 32 KB instruction cache.
+            if (kStdMel == 2) {
+              // window only; the (A,B) pairs are formed by the scalar multiplies themselves
+    #pragma unroll
+              for (int j = 0; j < 13; ++j) {
+                const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * (t + 16 * j));
+                R[j] = make_float2(__fmul_rn(x[j].x, w.x), __fmul_rn(x[j + 5].x, w.x));
+                I[j] = make_float2(__fmul_rn(x[j].y, w.y), __fmul_rn(x[j + 5].y, w.y));
+              }
+            } else if (kStdMel == 1) {
+              frame_pass(std::true_type{});
+            } else {
+              frame_pass(std::false_type{});
+            }
+            if (t >= 8) R[12] = I[12] = make_float2(0.f, 0.f);
+            R[13] = R[14] = R[15] = I[13] = I[14] = I[15] = make_float2(0.f, 0.f);
+          }
+
+          // ---- stage 1: 16-point DFT over j, twiddle W256^(K1*t), transpose through shared ------------
+          fft16<true>(R, I);
+          __syncwarp();   // previous tile's readers of this scratch are done; every lane has consumed its samples
+          if (arrive_is_last() && ti + 1 < n_tiles) stage_tile(tile_of(ti + 1));   // the input buffer is free: next tile's TMA overlaps the rest
+          if (ti == 0) fetch_next();
+    #pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const int K1 = rev4(p);
+            if (K1 != 0) {
+              const float2 w = sm_tw1[K1 * 16 + t];
+              cmul2(R[p], I[p], w.x, w.y);
+            }
+            T_pl[K1 * kRowStride + t] = R[p];
+          }
+          __syncwarp();
+    #pragma unroll
+          for (int q = 0; q < 8; ++q) {                      // real parts back, transposed
+            const float4 a = *reinterpret_cast<const float4*>(T_pl + t * kRowStride + 2 * q);
+            R[2 * q] = make_float2(a.x, a.y);
+            R[2 * q + 1] = make_float2(a.z, a.w);
+          }
+          __syncwarp();   // one plane: the imaginary parts go through it after the real parts have been read back
+    #pragma unroll
+          for (int p = 0; p < 16; ++p) T_pl[rev4(p) * kRowStride + t] = I[p];
+          __syncwarp();
+    #pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(T_pl + t * kRowStride + 2 * q);
+            I[2 * q] = make_float2(b.x, b.y);
+            I[2 * q + 1] = make_float2(b.z, b.w);
+          }
+          // ---- stage 2: position p holds Z[t + 16*rev4(p)] ----------------------------------------------
+          fft16<false>(R, I);
+          __syncwarp();   // all lanes finished reading the transpose planes before the power bins overwrite them
+
+          // ---- real-FFT split + power; lane t pairs with lane 16-t ------------------------------------
+          if (t == 0) my_P[128] = mul2(fma2(R[2], R[2], mul2(I[2], I[2])), bc(4.f));   // 4|Z[128]|^2, Z[128] at rev4(8)
+    #pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // partner's Z[(16-t) + 16 (15-i)]; lane 0 pairs k=16i with 256-16i = its own Z[16 (16-i)], k=0 with itself
+            const int ps = rev4(15 - i);
+            f2 br, bi;
+            br.x = __shfl_sync(0xffffffffu, R[ps].x, partner);
+            br.y = __shfl_sync(0xffffffffu, R[ps].y, partner);
+            bi.x = __shfl_sync(0xffffffffu, I[ps].x, partner);
+            bi.y = __shfl_sync(0xffffffffu, I[ps].y, partner);
+            if (t == 0) {
+              const int own = (i == 0) ? 0 : rev4(16 - i);
+              br = R[own];
+              bi = I[own];
+            }
+            const f2 ar = R[rev4(i)], ai = I[rev4(i)];
+            const f2 e2r = add2(ar, br), e2i = sub2(ai, bi);          // 2E = a + conj(b)
+            f2 o2r = add2(ai, bi), o2i = sub2(br, ar);                // 2O = -i (a - conj(b))
+            const float2 w = sm_tw2[i * 16 + t];
+            cmul2(o2r, o2i, w.x, w.y);                                // W512^k * 2O
+            const f2 xar = add2(e2r, o2r), xai = add2(e2i, o2i);      // 2 X[k]
+            const f2 xbr = sub2(e2r, o2r), xbi = sub2(e2i, o2i);      // 2 conj(X[256-k])
+            const int k = t + 16 * i;
+            my_P[k] = fma2(xar, xar, mul2(xai, xai));                 // 4 |X[k]|^2   (the 1/4 lives in the mel weights)
+            my_P[256 - k] = fma2(xbr, xbr, mul2(xbi, xbi));
+          }
+          __syncwarp();
+
+          // ---- sparse triangular mel + log (ta: compliance/kaldi.py:621-633) ---------------------------
+          // Segment form: this lane walks the bins between the centres of filters d = t + 16 b and d + 1 once, with the
+          // down-slope weight of its own filter (wa) and the up-slope weight of the next one (wb); the wb sum travels one
+          // lane up (lane 15's goes to lane 0 of the next band).
+          {
+            f2 carry15 = make_float2(0.f, 0.f);                   // lane 0: what lane 15 accumulated for it in the last band
+            const int src = (lane & 16) | ((t - 1) & 15);
+    #pragma unroll
+            for (int b = 0; b < kBands; ++b) {
+              f2 own = make_float2(0.f, 0.f), nxt = make_float2(0.f, 0.f);
+              const f2* pp = my_P + k0[b];
+              const float2* wp = reinterpret_cast<const float2*>(sm_melw) + tap_off[b] * 16 + t;
+              if (kStdMel) {
+    #pragma unroll
+                for (int i = 0; i < std_taps(kStdMel, b); ++i) {
+                  const f2 p = pp[i];
+                  const float2 w = wp[i * 16];
+                  own = fma2(p, bc(w.x), own);
+                  nxt = fma2(p, bc(w.y), nxt);
+                }
+              } else {
+    #pragma unroll 2
+                for (int i = 0; i < taps[b]; ++i) {
+                  const f2 p = pp[i];
+                  const float2 w = wp[i * 16];
+                  own = fma2(p, bc(w.x), own);
+                  nxt = fma2(p, bc(w.y), nxt);
+                }
+              }
+              f2 got;
+              got.x = __shfl_sync(0xffffffffu, nxt.x, src);
+              got.y = __shfl_sync(0xffffffffu, nxt.y, src);
+              const f2 acc = add2(own, t == 0 ? carry15 : got);
+              carry15 = got;
+              // lg2.approx (abs. error ~1e-7 in the log) except at the floor, where the reference's log(eps) is returned exactly
+              val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.x) * P.log_scale,
+                                   acc.y <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.y) * P.log_scale);
             }
           }
-          f2 sum = make_float2(sA.x + sA.y, sB.x + sB.y);
-#pragma unroll
-          for (int o = 8; o >= 1; o >>= 1) {
-            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
-            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
-          }
-          mA = __fdiv_rn(sum.x, static_cast<float>(kFrameLen));
-          mB = __fdiv_rn(sum.y, static_cast<float>(kFrameLen));
-        }
-        const float c = P.preemph;
-        // One pass over the 13 sample pairs: (A,B) pairs are formed by the mean subtraction itself (scalar FADDs write
-        // straight into the pair halves); x[2n-1] - mean lives in lane t-1 (same j), lane 0 takes lane 15's value of
-        // step j-1, and the very first sample of the frame replicates itself (ta: compliance/kaldi.py:193-198).
-        // x[j] - c * x[j-1]: product and difference rounded separately, as the reference's two tensor ops; with the
-        // reference's c == 1.0 the product is exact, so that (warp-uniform) variant skips the multiplies.
-        auto frame_pass = [&](auto unit_tag) {
-          constexpr bool kUnit = decltype(unit_tag)::value;
-          f2 to_prev = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < 13; ++j) {
-            const int n = t + 16 * j;
-            const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
-            const f2 te = make_float2(__fsub_rn(x[j].x, mA), __fsub_rn(x[j + 5].x, mB));   // x[2n]   - mean
-            const f2 to = make_float2(__fsub_rn(x[j].y, mA), __fsub_rn(x[j + 5].y, mB));   // x[2n+1] - mean
-            const f2 send = (t == 15) ? to_prev : to;
-            f2 tp;
-            tp.x = __shfl_sync(0xffffffffu, send.x, up_lane);
-            tp.y = __shfl_sync(0xffffffffu, send.y, up_lane);
-            if (j == 0 && t == 0) tp = te;
-            to_prev = to;
-            const f2 se = kUnit ? sub2(te, tp) : sub2(te, mul2(tp, bc(c)));
-            const f2 so = kUnit ? sub2(to, te) : sub2(to, mul2(te, bc(c)));
-            R[j] = mul2(se, bc(w.x));
-            I[j] = mul2(so, bc(w.y));
-          }
-        };
-        // The framing flavour is fixed per kernel variant (kStdMel: 1 = the reference's Kaldi call, DC removal +
-        // coefficient 1.0; 2 = its torch.stft call, window only; 0 = anything else), so that every instantiation
-        // carries one copy of this loop: the tile body has to stay inside the 32 KB instruction cache.
-        if (kStdMel == 2) {
-          // window only; the (A,B) pairs are formed by the scalar multiplies themselves
-#pragma unroll
-          for (int j = 0; j < 13; ++j) {
-            const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * (t + 16 * j));
-            R[j] = make_float2(__fmul_rn(x[j].x, w.x), __fmul_rn(x[j + 5].x, w.x));
-            I[j] = make_float2(__fmul_rn(x[j].y, w.y), __fmul_rn(x[j + 5].y, w.y));
-          }
-        } else if (kStdMel == 1) {
-          frame_pass(std::true_type{});
-        } else {
-          frame_pass(std::false_type{});
-        }
-        if (t >= 8) R[12] = I[12] = make_float2(0.f, 0.f);
-        R[13] = R[14] = R[15] = I[13] = I[14] = I[15] = make_float2(0.f, 0.f);
-      }
 
-      // ---- stage 1: 16-point DFT over j, twiddle W256^(K1*t), transpose through shared ------------
-      fft16<true>(R, I);
-      __syncwarp();   // previous tile's readers of this scratch are done; every lane has consumed its samples
-      if (arrive_is_last()) stage_tile(tile_idx + 1);   // the input buffer is free: next tile's TMA overlaps the rest
-#pragma unroll
-      for (int p = 0; p < 16; ++p) {
-        const int K1 = rev4(p);
-        if (K1 != 0) {
-          const float2 w = sm_tw1[K1 * 16 + t];
-          cmul2(R[p], I[p], w.x, w.y);
-        }
-        T_pl[K1 * kRowStride + t] = R[p];
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {                      // real parts back, transposed
-        const float4 a = *reinterpret_cast<const float4*>(T_pl + t * kRowStride + 2 * q);
-        R[2 * q] = make_float2(a.x, a.y);
-        R[2 * q + 1] = make_float2(a.z, a.w);
-      }
-      __syncwarp();   // one plane: the imaginary parts go through it after the real parts have been read back
-#pragma unroll
-      for (int p = 0; p < 16; ++p) T_pl[rev4(p) * kRowStride + t] = I[p];
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 b = *reinterpret_cast<const float4*>(T_pl + t * kRowStride + 2 * q);
-        I[2 * q] = make_float2(b.x, b.y);
-        I[2 * q + 1] = make_float2(b.z, b.w);
-      }
-      // ---- stage 2: position p holds Z[t + 16*rev4(p)] ----------------------------------------------
-      fft16<false>(R, I);
-      __syncwarp();   // all lanes finished reading the transpose planes before the power bins overwrite them
-
-      // ---- real-FFT split + power; lane t pairs with lane 16-t ------------------------------------
-      if (t == 0) my_P[128] = mul2(fma2(R[2], R[2], mul2(I[2], I[2])), bc(4.f));   // 4|Z[128]|^2, Z[128] at rev4(8)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // partner's Z[(16-t) + 16 (15-i)]; lane 0 pairs k=16i with 256-16i = its own Z[16 (16-i)], k=0 with itself
-        const int ps = rev4(15 - i);
-        f2 br, bi;
-        br.x = __shfl_sync(0xffffffffu, R[ps].x, partner);
-        br.y = __shfl_sync(0xffffffffu, R[ps].y, partner);
-        bi.x = __shfl_sync(0xffffffffu, I[ps].x, partner);
-        bi.y = __shfl_sync(0xffffffffu, I[ps].y, partner);
-        if (t == 0) {
-          const int own = (i == 0) ? 0 : rev4(16 - i);
-          br = R[own];
-          bi = I[own];
-        }
-        const f2 ar = R[rev4(i)], ai = I[rev4(i)];
-        const f2 e2r = add2(ar, br), e2i = sub2(ai, bi);          // 2E = a + conj(b)
-        f2 o2r = add2(ai, bi), o2i = sub2(br, ar);                // 2O = -i (a - conj(b))
-        const float2 w = sm_tw2[i * 16 + t];
-        cmul2(o2r, o2i, w.x, w.y);                                // W512^k * 2O
-        const f2 xar = add2(e2r, o2r), xai = add2(e2i, o2i);      // 2 X[k]
-        const f2 xbr = sub2(e2r, o2r), xbi = sub2(e2i, o2i);      // 2 conj(X[256-k])
-        const int k = t + 16 * i;
-        my_P[k] = fma2(xar, xar, mul2(xai, xai));                 // 4 |X[k]|^2   (the 1/4 lives in the mel weights)
-        my_P[256 - k] = fma2(xbr, xbr, mul2(xbi, xbi));
-      }
-      __syncwarp();
-
-      // ---- sparse triangular mel + log (ta: compliance/kaldi.py:621-633) ---------------------------
-      // Segment form: this lane walks the bins between the centres of filters d = t + 16 b and d + 1 once, with the
-      // down-slope weight of its own filter (wa) and the up-slope weight of the next one (wb); the wb sum travels one
-      // lane up (lane 15's goes to lane 0 of the next band).
-      {
-        f2 carry15 = make_float2(0.f, 0.f);                   // lane 0: what lane 15 accumulated for it in the last band
-        const int src = (lane & 16) | ((t - 1) & 15);
-#pragma unroll
-        for (int b = 0; b < kBands; ++b) {
-          f2 own = make_float2(0.f, 0.f), nxt = make_float2(0.f, 0.f);
-          const f2* pp = my_P + k0[b];
-          const float2* wp = reinterpret_cast<const float2*>(sm_melw) + tap_off[b] * 16 + t;
-          if (kStdMel) {
-#pragma unroll
-            for (int i = 0; i < std_taps(kStdMel, b); ++i) {
-              const f2 p = pp[i];
-              const float2 w = wp[i * 16];
-              own = fma2(p, bc(w.x), own);
-              nxt = fma2(p, bc(w.y), nxt);
+          // ---- MFCC: DCT-II + lifter (ta: compliance/kaldi.py:648-666,786-796) --------------------------
+          if (kMfcc) {
+            f2* my_L = reinterpret_cast<f2*>(my_scratch + kLogmelOff);
+    #pragma unroll
+            for (int b = 0; b < kBands; ++b)
+              if (t + 16 * b < P.n_mels) my_L[t + 16 * b] = val[b];
+            __syncwarp();
+            f2 acc[kBands];
+    #pragma unroll
+            for (int b = 0; b < kBands; ++b) acc[b] = make_float2(0.f, 0.f);
+            const int nc = P.n_ceps;
+    #pragma unroll 4
+            for (int m = 0; m < P.n_mels; ++m) {
+              const f2 l = my_L[m];
+              const float* drow = sm_dct + m * nc + t;
+    #pragma unroll
+              for (int b = 0; b < kBands; ++b)
+                if (16 * b < nc) acc[b] = fma2(l, bc((t + 16 * b < nc) ? drow[16 * b] : 0.f), acc[b]);
             }
-          } else {
-#pragma unroll 2
-            for (int i = 0; i < taps[b]; ++i) {
-              const f2 p = pp[i];
-              const float2 w = wp[i * 16];
-              own = fma2(p, bc(w.x), own);
-              nxt = fma2(p, bc(w.y), nxt);
+    #pragma unroll
+            for (int b = 0; b < kBands; ++b) val[b] = mul2(acc[b], bc((t + 16 * b < nc) ? sm_lifter[t + 16 * b] : 0.f));
+          }
+
+          // ---- epilogue: global CMVN, SpecAugment zero-fill, store ---------------------------------------
+          {
+            const int tfA = tl.t0 + flA;   // frame index inside the utterance
+            bool rowA = false, rowB = false;
+            unsigned dm = 0u;
+            if (mode == 0 || mode == 2) {
+              dm = dim_masked;
+              for (int q = 0; q < P.n_masks; ++q) {
+                const int m0 = wm[4 * q], m1 = wm[4 * q + 1];
+                rowA |= (tfA >= m0 && tfA < m1);
+                rowB |= (tfA + 1 >= m0 && tfA + 1 < m1);
+              }
+            }
+            if (P.ws_blocked) {
+              // tile-blocked log-mel workspace: dim d = t + 16 b of frame r lives at ((d / 4) * 16 + r) * 4 + d % 4 inside
+              // the tile's block (no masks / normalisation on this path: they belong to the DCT kernel's epilogue)
+              float* o = P.out + static_cast<long long>(tile_idx) * (kTileFrames * n_out) + (t >> 2) * 64 + (t & 3) + flA * 4;
+    #pragma unroll
+              for (int b = 0; b < kBands; ++b) {
+                if (t + 16 * b < n_out) {
+                  if (actA) o[256 * b] = val[b].x;
+                  if (actB) o[256 * b + 4] = val[b].y;
+                }
+              }
+            } else if (mode != 2 && !(mode == 0 && P.n_masks > 0) && tl.nframes == kTileFrames) {
+              // full tile, nothing to apply here (no masks given, or a statistics mode: masks and normalisation happen in
+              // the second pass)
+              float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
+    #pragma unroll
+              for (int b = 0; b < kBands; ++b) {
+                if (t + 16 * b < n_out) {
+                  orow[16 * b] = val[b].x;
+                  orow[P.out_ld + 16 * b] = val[b].y;
+                }
+              }
+            } else {
+              float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
+    #pragma unroll
+              for (int b = 0; b < kBands; ++b) {
+                const int d = t + 16 * b;
+                if (d < n_out) {
+                  f2 x = val[b];
+                  if (mode == 2) {
+                    const float2 nm = sm_norm[d];
+                    x = mul2(sub2(x, bc(nm.x)), bc(nm.y));
+                  }
+                  const bool dz = (dm >> b) & 1u;
+                  if (actA) orow[16 * b] = (dz || rowA) ? 0.f : x.x;
+                  if (actB) orow[P.out_ld + 16 * b] = (dz || rowB) ? 0.f : x.y;
+                }
+              }
             }
           }
-          f2 got;
-          got.x = __shfl_sync(0xffffffffu, nxt.x, src);
-          got.y = __shfl_sync(0xffffffffu, nxt.y, src);
-          const f2 acc = add2(own, t == 0 ? carry15 : got);
-          carry15 = got;
-          // lg2.approx (abs. error ~1e-7 in the log) except at the floor, where the reference's log(eps) is returned exactly
-          val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.x) * P.log_scale,
-                               acc.y <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.y) * P.log_scale);
         }
-      }
 
-      // ---- MFCC: DCT-II + lifter (ta: compliance/kaldi.py:648-666,786-796) --------------------------
-      if (kMfcc) {
-        f2* my_L = reinterpret_cast<f2*>(my_scratch + kLogmelOff);
-#pragma unroll
-        for (int b = 0; b < kBands; ++b)
-          if (t + 16 * b < P.n_mels) my_L[t + 16 * b] = val[b];
-        __syncwarp();
-        f2 acc[kBands];
-#pragma unroll
-        for (int b = 0; b < kBands; ++b) acc[b] = make_float2(0.f, 0.f);
-        const int nc = P.n_ceps;
-#pragma unroll 4
-        for (int m = 0; m < P.n_mels; ++m) {
-          const f2 l = my_L[m];
-          const float* drow = sm_dct + m * nc + t;
+        // ---- statistics.  Each warp parks the (A,B) feature pairs of its 4 frames in its own scratch, re-reads them
+        //      dim-major and adds sum and sum of squares, in fp64 (x*x is exact there), to ITS OWN accumulators in
+        //      shared memory (lane-owned dims: no atomics, no cross-warp traffic per tile).  The 4 warps' accumulators
+        //      are combined when the span ends (per-utterance CMVN) or when the CTA runs out of work (global sums).
+        if (want_stats) {
+          f2* my_V = reinterpret_cast<f2*>(my_scratch + kValsOff);
 #pragma unroll
           for (int b = 0; b < kBands; ++b)
-            if (16 * b < nc) acc[b] = fma2(l, bc((t + 16 * b < nc) ? drow[16 * b] : 0.f), acc[b]);
-        }
-#pragma unroll
-        for (int b = 0; b < kBands; ++b) val[b] = mul2(acc[b], bc((t + 16 * b < nc) ? sm_lifter[t + 16 * b] : 0.f));
-      }
-
-      // ---- epilogue: global CMVN, SpecAugment zero-fill, store ---------------------------------------
-      {
-        const int tfA = tl.t0 + flA;   // frame index inside the utterance
-        bool rowA = false, rowB = false;
-        unsigned dm = 0u;
-        if (mode == 0 || mode == 2) {
-          dm = dim_masked;
-          for (int q = 0; q < P.n_masks; ++q) {
-            const int m0 = wm[4 * q], m1 = wm[4 * q + 1];
-            rowA |= (tfA >= m0 && tfA < m1);
-            rowB |= (tfA + 1 >= m0 && tfA + 1 < m1);
+            if (t + 16 * b < n_out) my_V[t + 16 * b] = val[b];
+          __syncwarp();
+          double* wacc = sm_acc + warp * 2 * kMaxMels;
+          const float* v0 = sm_scratch + (warp * 2 + 0) * kScratchFloats + kValsOff;
+          const float* v1 = v0 + kScratchFloats;
+          const int f0 = warp * 4;
+          for (int d = lane; d < n_out; d += 32) {
+            const f2 p0 = *reinterpret_cast<const f2*>(v0 + 2 * d), p1 = *reinterpret_cast<const f2*>(v1 + 2 * d);
+            double a1 = wacc[d], a2 = wacc[kMaxMels + d];
+            if (f0 + 3 < tl.nframes) {   // all four frames live (every tile but an utterance's last): no predicates
+              const double x0 = p0.x, x1 = p0.y, x2 = p1.x, x3 = p1.y;       // short dependency chains: a tree per tile
+              a1 += (x0 + x1) + (x2 + x3);
+              a2 += fma(x1, x1, x0 * x0) + fma(x3, x3, x2 * x2);
+            } else {
+              if (f0 + 0 < tl.nframes) { const double x = p0.x; a1 += x; a2 = fma(x, x, a2); }
+              if (f0 + 1 < tl.nframes) { const double x = p0.y; a1 += x; a2 = fma(x, x, a2); }
+              if (f0 + 2 < tl.nframes) { const double x = p1.x; a1 += x; a2 = fma(x, x, a2); }
+            }
+            wacc[d] = a1;
+            wacc[kMaxMels + d] = a2;
           }
         }
-        if (P.ws_blocked) {
-          // tile-blocked log-mel workspace: dim d = t + 16 b of frame r lives at ((d / 4) * 16 + r) * 4 + d % 4 inside
-          // the tile's block (no masks / normalisation on this path: they belong to the DCT kernel's epilogue)
-          float* o = P.out + static_cast<long long>(tile_idx) * (kTileFrames * n_out) + (t >> 2) * 64 + (t & 3) + flA * 4;
+        if (mode == 4) {   // AmplitudeToDB(top_db): running max / min of this warp's live features (ta: functional/functional.py:391-403)
+          float m = -INFINITY, mn = INFINITY;
 #pragma unroll
-          for (int b = 0; b < kBands; ++b) {
+          for (int b = 0; b < kBands; ++b)
             if (t + 16 * b < n_out) {
-              if (actA) o[256 * b] = val[b].x;
-              if (actB) o[256 * b + 4] = val[b].y;
+              if (actA) { m = fmaxf(m, val[b].x); mn = fminf(mn, val[b].x); }
+              if (actB) { m = fmaxf(m, val[b].y); mn = fminf(mn, val[b].y); }
             }
-          }
-        } else if (mode != 2 && !(mode == 0 && P.n_masks > 0) && tl.nframes == kTileFrames) {
-          // full tile, nothing to apply here (no masks given, or a statistics mode: masks and normalisation happen in
-          // the second pass)
-          float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
 #pragma unroll
-          for (int b = 0; b < kBands; ++b) {
-            if (t + 16 * b < n_out) {
-              orow[16 * b] = val[b].x;
-              orow[P.out_ld + 16 * b] = val[b].y;
-            }
+          for (int o = 16; o >= 1; o >>= 1) {
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
           }
-        } else {
-          float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
-#pragma unroll
-          for (int b = 0; b < kBands; ++b) {
-            const int d = t + 16 * b;
-            if (d < n_out) {
-              f2 x = val[b];
-              if (mode == 2) {
-                const float2 nm = sm_norm[d];
-                x = mul2(sub2(x, bc(nm.x)), bc(nm.y));
-              }
-              const bool dz = (dm >> b) & 1u;
-              if (actA) orow[16 * b] = (dz || rowA) ? 0.f : x.x;
-              if (actB) orow[P.out_ld + 16 * b] = (dz || rowB) ? 0.f : x.y;
-            }
+          if (lane == 0) {
+            sm_wmax[warp] = fmaxf(sm_wmax[warp], m);
+            sm_wmax[kWarps + warp] = fminf(sm_wmax[kWarps + warp], mn);
           }
         }
-      }
+      }   // tiles of the span
+      if (mode == 3 && tid == kThreads - 1) frames_acc += static_cast<double>(sp.nframes);
     }
 
-    // ---- statistics.  Each warp parks the (A,B) feature pairs of its 4 frames in its own scratch, re-reads them
-    //      dim-major and adds sum and sum of squares, in fp64 (x*x is exact there), to ITS OWN accumulators in shared
-    //      memory (lane-owned dims: no atomics, no cross-warp traffic per tile).  The 4 warps' accumulators are only
-    //      combined when the utterance changes or the CTA's range ends (about twice per CTA). ------------------------
-    if (want_stats) {
-      f2* my_V = reinterpret_cast<f2*>(my_scratch + kValsOff);
-#pragma unroll
-      for (int b = 0; b < kBands; ++b)
-        if (t + 16 * b < n_out) my_V[t + 16 * b] = val[b];
-      __syncwarp();
-      double* wacc = sm_acc + warp * 2 * kMaxMels;
-      const float* v0 = sm_scratch + (warp * 2 + 0) * kScratchFloats + kValsOff;
-      const float* v1 = v0 + kScratchFloats;
-      const int f0 = warp * 4;
-      for (int d = lane; d < n_out; d += 32) {
-        const f2 p0 = *reinterpret_cast<const f2*>(v0 + 2 * d), p1 = *reinterpret_cast<const f2*>(v1 + 2 * d);
-        double a1 = wacc[d], a2 = wacc[kMaxMels + d];
-        if (f0 + 3 < tl.nframes) {   // all four frames live (every tile but an utterance's last): no predicates
-          const double x0 = p0.x, x1 = p0.y, x2 = p1.x, x3 = p1.y;       // short dependency chains: a tree per tile
-          a1 += (x0 + x1) + (x2 + x3);
-          a2 += fma(x1, x1, x0 * x0) + fma(x3, x3, x2 * x2);
-        } else {
-          if (f0 + 0 < tl.nframes) { const double x = p0.x; a1 += x; a2 = fma(x, x, a2); }
-          if (f0 + 1 < tl.nframes) { const double x = p0.y; a1 += x; a2 = fma(x, x, a2); }
-          if (f0 + 2 < tl.nframes) { const double x = p1.x; a1 += x; a2 = fma(x, x, a2); }
-        }
-        wacc[d] = a1;
-        wacc[kMaxMels + d] = a2;
+    // ---- end of span.  Thread 0 publishes the next span (claimed one span ago; its descriptor sits in the spare
+    //      slot) and claims the one after.  For per-utterance CMVN / top_db the span's statistics are handed over to
+    //      global memory; the CTA whose hand-over completes the utterance normalises it on the spot. ------------------
+    if (tid == 0) {
+      cp_async_wait<0>();
+      sm_ctl[cur] = pend;
+    }
+    __syncthreads();   // every warp is done with the span: statistics complete, descriptor + claim visible
+    // per-utterance modes: sums / extrema leave the CTA when its next span belongs to another utterance (or is a
+    // zero-fill span, or there is none)
+    if (sp.nframes != 0) frames_held += sp.nframes;
+    bool hand_over = false;
+    if ((mode == 1 || mode == 4) && frames_held > 0) {
+      const int nxt_idx = sm_ctl[cur];
+      hand_over = nxt_idx >= P.n_spans;
+      if (!hand_over) {
+        const Span nx = sm_span[cur ^ 1];
+        hand_over = (nx.nframes == 0) || (nx.utt != held_utt);
       }
     }
-    float* const sm_wmax = reinterpret_cast<float*>(sm_acc + kWarps * 2 * kMaxMels + 2);
-    if (mode == 4) {   // AmplitudeToDB(top_db): running max of this warp's live features (ta: functional/functional.py:391-403)
-      float m = -INFINITY, mn = INFINITY;
-#pragma unroll
-      for (int b = 0; b < kBands; ++b)
-        if (t + 16 * b < n_out) {
-          if (actA) { m = fmaxf(m, val[b].x); mn = fminf(mn, val[b].x); }
-          if (actB) { m = fmaxf(m, val[b].y); mn = fminf(mn, val[b].y); }
-        }
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      }
-      if (lane == 0) {
-        sm_wmax[warp] = fmaxf(sm_wmax[warp], m);
-        if (P.tile_min) P.tile_min[static_cast<long long>(tile_idx) * kWarps + warp] = mn;   // every warp writes: no reset needed
-      }
-    }
-    // No per-tile CTA barrier.  Cross-warp state is only touched when sums / maxima are handed over (utterance change,
-    // zero-fill ahead, end of the CTA's range): a CTA-uniform, rare event bracketed by two barriers.
-    if (mode == 4) {
-      bool flush = (tile_idx + 1 == tile_end);
-      if (!flush) {
-        const Tile nx = sm_tiles[(it + 1) % kTileCache];
-        flush = (nx.nframes == 0) || (nx.utt != tl.utt);
-      }
-      if (__builtin_expect(flush, 0)) {
-        __syncthreads();   // every warp's running maximum covers this tile
-        if (tid == 0) {
-          float m = sm_wmax[0];
-#pragma unroll
-          for (int w = 1; w < kWarps; ++w) m = fmaxf(m, sm_wmax[w]);
-          atomicMax(&P.utt_max[tl.utt], f2ord(m));
-#pragma unroll
-          for (int w = 0; w < kWarps; ++w) sm_wmax[w] = -INFINITY;
-        }
-        __syncthreads();
-      }
-    }
-    if (want_stats) {
-      bool flush = (tile_idx + 1 == tile_end);
-      if (!flush) {    // zero-fill tiles skip this block, so sums are also handed over before one
-        const Tile nx = sm_tiles[(it + 1) % kTileCache];
-        flush = (nx.nframes == 0) || (mode == 1 && nx.utt != tl.utt);
-      }
-      if (mode == 3 && tid == kThreads - 1) sm_acc[kWarps * 2 * kMaxMels] += static_cast<double>(tl.nframes);
-      if (__builtin_expect(flush, 0)) {     // combine the warps' accumulators
-        __syncthreads();   // every warp has added this tile
+    if (sp.nframes != 0) held_utt = sp.utt;
+    if (hand_over) {
+      if (mode == 1) {
         for (int e = tid; e < 2 * kMaxMels; e += kThreads) {
           const int which = e / kMaxMels, d = e - which * kMaxMels;
           double a = 0.0;
@@ -833,18 +1144,70 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
             a += sm_acc[w * 2 * kMaxMels + e];
             sm_acc[w * 2 * kMaxMels + e] = 0.0;
           }
-          if (d < n_out && a != 0.0) {
-            if (mode == 1) atomicAdd(&P.utt_stats[(static_cast<long long>(tl.utt) * 2 + which) * n_out + d], a);
-            else atomicAdd(&P.stats_out[which * n_out + d], a);
-          }
+          if (d < n_out && a != 0.0 && !(P.dbg & 2)) atomicAdd(&stats_cur[(static_cast<long long>(held_utt) * 2 + which) * n_out + d], a);
         }
-        if (mode == 3 && tid == kThreads - 1) {
-          atomicAdd(&P.stats_out[2 * n_out], sm_acc[kWarps * 2 * kMaxMels]);
-          sm_acc[kWarps * 2 * kMaxMels] = 0.0;
-        }
-        __syncthreads();   // accumulators are zero again before any warp adds the next tile
+      } else if (tid == 0) {
+        float m = sm_wmax[0], mn = sm_wmax[kWarps];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) { m = fmaxf(m, sm_wmax[w]); mn = fminf(mn, sm_wmax[kWarps + w]); }
+        atomicMax(&max_cur[held_utt], f2ord(m));
+        atomicMin(&min_cur[held_utt], f2ord(mn));
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) { sm_wmax[w] = -INFINITY; sm_wmax[kWarps + w] = INFINITY; }
       }
+      if (P.n_items > 0) {   // in-kernel second stage: announce the frames (a separate second kernel needs no count)
+        __syncthreads();     // every thread's feature rows and sums are issued: thread 0's fence covers them (bar.sync + cumulativity)
+        if (tid == 0) {
+          if (!(P.dbg & 4)) __threadfence();
+          atomicAdd(&done_cur[held_utt], frames_held);     // no return value needed: the service warps watch the count
+        }
+      } else {
+        __syncthreads();     // the accumulators are zero again before any warp adds the next span
+      }
+      frames_held = 0;
     }
+    ++n_sp;
+    span_idx = sm_ctl[cur];
+    if (tid == 0 && span_idx < P.n_spans) {
+      ++k_mine;
+      pend = (k_mine < P.k_static) ? span_idx + 1 : n_static + atomicAdd(&P.sched[0], 1);
+    }
+    cur ^= 1;
+  }
+
+  long long t_spans = 0, n_iter = 0;
+  if (P.dbg_buf && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_spans));
+  // ---- out of spans (or a service CTA from the start): every warp takes items until all of them have been claimed ----
+  if (per_utt_mode) {
+    service_warp();
+    __syncthreads();   // every warp of the CTA has made its last claim before the CTA counts itself out
+  }
+
+  // ---- out of work: global sums (mode 3) leave the CTA once; the last CTA to get here puts the claim counter back ----
+  if (mode == 3) {
+    __syncthreads();
+    for (int e = tid; e < 2 * kMaxMels; e += kThreads) {
+      const int which = e / kMaxMels, d = e - which * kMaxMels;
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) a += sm_acc[w * 2 * kMaxMels + e];
+      if (d < n_out && a != 0.0) atomicAdd(&P.stats_out[which * n_out + d], a);
+    }
+    if (tid == kThreads - 1 && frames_acc != 0.0) atomicAdd(&P.stats_out[2 * n_out], frames_acc);
+  }
+  if (P.dbg_buf && tid == 0) {
+    long long t_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+    long long* o = P.dbg_buf + 8 * blockIdx.x;
+    o[0] = t_start; o[1] = t_spans; o[2] = t_end; o[3] = n_sp; o[4] = n_blk; o[5] = n_iter;
+  }
+  // the last CTA to get here puts the schedule (and the per-utterance bookkeeping) back to rest for the next launch
+  if (tid == 0) sm_ctl[5] = (atomicAdd(&P.sched[1], 1) == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
+  __syncthreads();
+  if (sm_ctl[5] && tid == 0) {
+    P.ictl[0] = 0;
+    P.sched[0] = 0;
+    P.sched[1] = 0;
   }
 }
 
@@ -868,10 +1231,14 @@ struct ApplyParams {
   int normalize;                 // 0 -> masks only, 1 -> (x - mean) * inv_std, 2 -> max(x, utt_max - top_db)
   int rows_per_cta;
   const unsigned* utt_max;       // [B] (normalize == 2)
+  const unsigned* utt_min;       // [B] or NULL (normalize == 2): lets blocks of an utterance with nothing below the floor return at once
   float top_db;
-  double* clear_stats;           // [B][2][n_out] or NULL: the other half of the ping-pong workspace, zeroed here
-  const float* tile_min;         // [n_tiles][kWarps] or NULL (normalize == 2): per-tile minima written by fbank_kernel
-  const long long* utt_first_tile;   // [B] index of each utterance's first tile
+  // the OTHER launch parity's bookkeeping of every utterance, put back to rest here (the two-kernel flavour of the
+  // per-utterance modes; see FbankParams::items), or NULL
+  double* rest_stats;            // [B][2][n_out]
+  int* rest_done;                // [B]
+  unsigned* rest_max;            // [B]
+  unsigned* rest_min;            // [B]
 };
 
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__ ApplyParams P) {
@@ -884,15 +1251,6 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   const long long r0 = static_cast<long long>(blockIdx.y) * P.rows_per_cta;
   if (r0 >= T) return;
   const int rows = static_cast<int>(T - r0 < P.rows_per_cta ? T - r0 : P.rows_per_cta);
-  if (P.normalize == 2 && P.n_masks == 0 && P.tile_min) {
-    // AmplitudeToDB's clamp only moves values below max - top_db: if no tile of this block of rows holds one, there
-    // is nothing to do here (the per-tile minima come from fbank_kernel; the block never touches the features)
-    const float floor_db = ord2f(P.utt_max[utt]) - P.top_db;
-    const long long t_lo = P.utt_first_tile[utt] + r0 / kTileFrames, t_hi = P.utt_first_tile[utt] + (r0 + rows - 1) / kTileFrames;
-    int below = 0;
-    for (long long i = t_lo * kWarps + tid; i < (t_hi + 1) * kWarps; i += 256) below |= (P.tile_min[i] < floor_db) ? 1 : 0;
-    if (!__syncthreads_or(below)) return;
-  }
   float* base = P.feats + (P.utt_out_row[utt] + r0) * P.ld;
   const bool vec = (P.n_out % 4 == 0) && (P.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.feats) & 15) == 0);
 
@@ -914,8 +1272,16 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const __grid_constant__
   }
 
   const float db_floor = (P.normalize == 2) ? ord2f(P.utt_max[utt]) - P.top_db : 0.f;
-  if (P.clear_stats && blockIdx.y == 0 && tid < 2 * P.n_out)
-    P.clear_stats[static_cast<long long>(utt) * 2 * P.n_out + tid] = 0.0;   // next launch's accumulators
+  if (blockIdx.y == 0) {
+    if (P.rest_stats && tid < 2 * P.n_out) P.rest_stats[static_cast<long long>(utt) * 2 * P.n_out + tid] = 0.0;
+    if (P.rest_done && tid == 0) {
+      P.rest_done[utt] = 0;
+      P.rest_max[utt] = 0u;
+      P.rest_min[utt] = 0xffffffffu;
+    }
+  }
+  // AmplitudeToDB's clamp only moves values below max - top_db: an utterance that holds none needs no pass at all
+  if (P.normalize == 2 && P.n_masks == 0 && P.utt_min && ord2f(P.utt_min[utt]) >= db_floor) return;
   if (tid < P.n_out) {
     float mean = 0.f, inv = 1.f, lo = 0.f;
     if (P.normalize == 1) {
@@ -1057,14 +1423,6 @@ struct DctParams {
   const double* stats_in;   // [2*n_ceps+1] (mode 2)
 };
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // One pass: this thread's frame (row g) of TM consecutive tiles, columns c0 .. c0+19.  `ring` is the thread's slot of
 // stage 0 / row 0; stage s, row i lives at ring[(s * kDctMaxTiles + i) * kDctThreads].
@@ -1229,12 +1587,14 @@ struct WaveParams {
   const void* in;             // float32 or int16 samples
   int in_i16;                 // 1 -> int16 PCM, converted as (float)s * in_scale before anything else
   float in_scale;
-  float* out;
+  float* out;                 // NULL: statistics only (the fused load of fbank_kernel applies them, row f2)
+  float2* norm_out;           // [B] (mean, std + 1e-6) of every utterance, or NULL
   const long long* offsets;   // [B]
   const long long* lengths;   // [B]
   int normalize;
   float dither;
-  const float* noise;
+  const float* noise;         // the U[0,1) draw (parity with the reference's torch.rand_like), or NULL: Philox below
+  unsigned long long seed;
   float preemph;
 };
 
@@ -1259,7 +1619,7 @@ __global__ void __cluster_dims__(kWaveCluster, 1, 1) __launch_bounds__(kWaveThre
   const short* xs = reinterpret_cast<const short*>(P.in) + off;
   auto ld = [&](long long i) -> float { return P.in_i16 ? static_cast<float>(xs[i]) * P.in_scale : xf[i]; };
   const float* nz = P.noise ? P.noise + off : nullptr;
-  float* y = P.out + off;
+  float* y = P.out ? P.out + off : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long per = (n + kWaveCluster - 1) / kWaveCluster;
   const long long lo = per * rank < n ? per * rank : n, hi = lo + per < n ? lo + per : n;
@@ -1282,7 +1642,7 @@ __global__ void __cluster_dims__(kWaveCluster, 1, 1) __launch_bounds__(kWaveThre
     return t;
   };
 
-  float mean = 0.f, div = 1.f;
+  float mean = 0.f, div = 1.f, rcp = 1.f;
   if (P.normalize) {
     // two-pass mean / unbiased variance in fp64 (torch.std_mean accumulates in fp32 with a cascade)
     double s = 0.0;
@@ -1298,17 +1658,21 @@ __global__ void __cluster_dims__(kWaveCluster, 1, 1) __launch_bounds__(kWaveThre
     const double qt = cluster_total(1);
     mean = static_cast<float>(m);
     div = static_cast<float>(sqrt(qt / static_cast<double>(n - 1))) + 1e-6f;
+    rcp = __frcp_rn(div);
+    if (P.norm_out && rank == 0 && tid == 0) P.norm_out[u] = make_float2(mean, div);
   }
-  auto stage1 = [&](long long i) -> float {
-    float v = ld(i);
-    if (P.normalize) v = __fdiv_rn(__fsub_rn(v, mean), div);
-    if (P.dither != 0.f) v = __fadd_rn(v, __fmul_rn(P.dither, nz[i]));
-    return v;
-  };
-  for (long long i = lo + tid; i < hi; i += kWaveThreads) {
-    float v = stage1(i);
-    if (P.preemph != 0.f && i > 0) v = __fsub_rn(v, __fmul_rn(P.preemph, stage1(i - 1)));
-    y[i] = v;
+  if (y) {
+    auto stage1 = [&](long long i) -> float {
+      float v = ld(i);
+      if (P.normalize) v = div_by(__fsub_rn(v, mean), div, rcp);
+      if (P.dither != 0.f) v = __fadd_rn(v, __fmul_rn(P.dither, nz ? nz[i] : dither_uniform(P.seed, u, i)));
+      return v;
+    };
+    for (long long i = lo + tid; i < hi; i += kWaveThreads) {
+      float v = stage1(i);
+      if (P.preemph != 0.f && i > 0) v = __fsub_rn(v, __fmul_rn(P.preemph, stage1(i - 1)));
+      y[i] = v;
+    }
   }
   cluster.sync();                                        // no CTA exits while a peer may still read its partials
 }

@@ -82,16 +82,26 @@ class FrontEnd:
                  hop_length: float = 0.01, preemph: float = 1.0, cepstral_lifter: float = 22.0,
                  remove_dc: bool = True, in_dtype: torch.dtype = torch.float32, in_scale: float = 1.0,
                  device: Union[str, torch.device, None] = None, kind: str = "kaldi", pad: int = 0,
-                 top_db: float = 80.0):
+                 top_db: float = 80.0, window: str = "povey", dither: float = 0.0, seed: int = 0):
         """``kind="kaldi"``: the ``use_kaildi=True`` branch (ref: lid/audio_processor.py:41-69).
         ``kind="melspec_db"``: the reference's default branch, MelSpectrogram(n_fft=512, win 400, hop 160, pad,
         center, reflect, power 2, HTK mel 0-8 kHz) + AmplitudeToDB(top_db=80) (ref: lid/audio_processor.py:72-105);
-        ``preemph`` / ``remove_dc`` / ``n_ceps`` do not apply to it."""
+        ``preemph`` / ``remove_dc`` / ``n_ceps`` do not apply to it.
+        ``window``: one of torchaudio.compliance.kaldi's window types -- "povey" (the reference's), "hanning", "hamming",
+        "rectangular", "blackman" (ta: compliance/kaldi.py:86-113); kaldi branch only.
+        ``dither`` > 0: ``wav += dither * U[0,1)`` (ref: lid/audio_processor.py:129) inside the fused kernel, Philox keyed
+        by (seed, utterance, sample); 0 is the reference's ``wav2mel`` (its kaldi call passes dither=0.0, :57)."""
         if kind not in ("kaldi", "melspec_db"):
             raise ValueError("kind must be 'kaldi' or 'melspec_db'")
         self.kind = kind
         if kind == "melspec_db":
             preemph, remove_dc, n_ceps = 0.0, False, 0
+            if window != "povey" or dither != 0.0:
+                raise ValueError("window / dither belong to kind='kaldi'")
+        wtypes = {"povey": _lib.WINDOW_POVEY, "hanning": _lib.WINDOW_HANNING, "hamming": _lib.WINDOW_HAMMING,
+                  "rectangular": _lib.WINDOW_RECTANGULAR, "blackman": _lib.WINDOW_BLACKMAN}
+        if window not in wtypes:
+            raise ValueError("Invalid window type " + str(window))      # ta: compliance/kaldi.py:113
         self.lib = _lib.load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("speech_lid_b200.FrontEnd needs a CUDA device (sm_100a); there is no CPU path")
@@ -116,7 +126,9 @@ class FrontEnd:
                                     framing=_lib.FRAMING_KALDI if kind == "kaldi" else _lib.FRAMING_CENTER,
                                     pad=int(pad) if kind == "melspec_db" else 0,
                                     log_kind=_lib.LOG_NATURAL if kind == "kaldi" else _lib.LOG_DB10,
-                                    top_db=float(top_db))
+                                    top_db=float(top_db), dither=float(dither),
+                                    window_type=wtypes[window] if kind == "kaldi" else _lib.WINDOW_HANN_PERIODIC,
+                                    seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
         self.in_dtype = in_dtype
         self.n_mels, self.n_ceps = int(n_mels), int(n_ceps)
         self.n_out = self.n_ceps if self.n_ceps > 0 else self.n_mels
@@ -125,7 +137,7 @@ class FrontEnd:
         if frame_len != 400 or frame_shift != 160 or int(sr) != 16000:
             _lib.check(_lib.E_CONFIG)
         if kind == "kaldi":
-            window = tables.povey_window(frame_len).contiguous()
+            window = tables.kaldi_window(window, frame_len).contiguous()
             banks = tables.mel_banks(self.n_mels, fft_len, float(sr)).contiguous()
         else:
             window = tables.hann_window(frame_len).contiguous()
@@ -141,7 +153,15 @@ class FrontEnd:
 
     def close(self) -> None:
         if getattr(self, "handle", None):
-            self.lib.lidfe_destroy(self.handle)
+            for cache in (self.__dict__.get("_plan_cache", {}), ):
+                for plan in list(cache.values()):
+                    plan.close()
+                cache.clear()
+            for st in self.__dict__.get("_host_cache", {}).values():
+                for c in st:
+                    c["plan"].close()
+            self.__dict__.get("_host_cache", {}).clear()
+            self.lib.lidfe_destroy(self.handle)      # plans still alive elsewhere keep the native handle until they go
             self.handle = None
 
     def __del__(self):
@@ -164,6 +184,12 @@ class FrontEnd:
         _lib.check(self.lib.lidfe_profile_end(self.handle, buf, cap, C.byref(n)))
         return [float(buf[i]) for i in range(min(n.value, cap))]
 
+    def pool_stats(self) -> Tuple[int, int]:
+        """(plan-memory blocks allocated since creation, blocks currently free in the pool)."""
+        a, f = C.c_longlong(0), C.c_longlong(0)
+        _lib.check(self.lib.lidfe_pool_stats(self.handle, C.byref(a), C.byref(f)))
+        return int(a.value), int(f.value)
+
     # ------------------------------------------------------------------ frame arithmetic
     def num_frames(self, n_samples: int) -> int:
         """kaldi: 1 + (N - 400) // 160 (0 if N < 400), ta: compliance/kaldi.py:63-67;
@@ -172,7 +198,8 @@ class FrontEnd:
 
     # ------------------------------------------------------------------ planning / packing
     def make_plan(self, lengths: Sequence[int], padded: bool = True,
-                  offsets: Optional[Sequence[int]] = None, t_max: Optional[int] = None) -> Plan:
+                  offsets: Optional[Sequence[int]] = None, t_max: Optional[int] = None,
+                  stream: Optional[torch.cuda.Stream] = None) -> Plan:
         """Build the segment-offset table for utterances of ``lengths`` samples.  ``offsets`` default to a
         packing that starts every utterance on a 16-byte boundary (so each tile is one TMA bulk copy)."""
         lengths = [int(n) for n in lengths]
@@ -206,8 +233,12 @@ class FrontEnd:
             pad_rows = None
         ph = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.lidfe_plan_create(self.handle, C.byref(ph), len(lengths), _ll_array(offsets),
-                                                  _ll_array(lengths), _ll_array(out_rows), pad_rows))
+            # one pinned-buffer fill + one async copy on the current stream; the memory comes from the handle's pool, so
+            # a new length signature every step costs no cudaMalloc / synchronisation (include/lidfe.h, Conventions)
+            st = stream if stream is not None else torch.cuda.current_stream(self.device)
+            _lib.check(self.lib.lidfe_plan_create_async(self.handle, C.byref(ph), len(lengths), _ll_array(offsets),
+                                                        _ll_array(lengths), _ll_array(out_rows), pad_rows,
+                                                        st.cuda_stream))
         return Plan(handle=ph.value, lengths=lengths, offsets=offsets, frames=frames, out_rows=out_rows,
                     rows=rows, t_max=t_max, padded=padded, total_samples=total, _owner=self)
 
@@ -234,6 +265,9 @@ class FrontEnd:
             if w.dim() == 2:
                 w = w[0]        # channel=-1 -> first channel     ta: compliance/kaldi.py:135-137
             flat.append(w)
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                return self.pack(flat, plan, pinned=pinned)
         if all(w.is_cuda for w in flat):
             packed = torch.zeros(plan.total_samples, dtype=self.in_dtype, device=self.device)
             for w, o, n in zip(flat, plan.offsets, plan.lengths):
@@ -249,9 +283,12 @@ class FrontEnd:
     def featurize_packed(self, packed: torch.Tensor, plan: Plan, out: Optional[torch.Tensor] = None,
                          masks: Optional[torch.Tensor] = None, cmvn: str = "none",
                          stats_in: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
-                         stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
-        """Launch the fused kernel(s) on device-resident packed samples.  Returns ``out``:
-        (B, T_max, n_out) if the plan is padded, (sum T_i, n_out) otherwise."""
+                         stream: Optional[torch.cuda.Stream] = None, raw: bool = False) -> torch.Tensor:
+        """Launch the fused kernel on device-resident packed samples.  Returns ``out``:
+        (B, T_max, n_out) if the plan is padded, (sum T_i, n_out) otherwise.
+        ``raw=True``: ``packed`` holds raw samples (int16 PCM scaled by ``in_scale``, or float32) and
+        ``read_audio``'s ``normalize_wav`` (ref: lid/audio_processor.py:108-122) is fused in: a statistics pre-pass, then
+        (x - mean) / (std + 1e-6) applied while the kernel stages each tile."""
         if self.kind == "melspec_db":
             # the reference's default branch always ends in AmplitudeToDB(top_db=80); it has no CMVN
             if cmvn not in ("none", "topdb"):
@@ -280,21 +317,39 @@ class FrontEnd:
             if s is not None and (s.dtype != torch.float64 or s.numel() != 2 * self.n_out + 1 or not s.is_cuda):
                 raise ValueError("stats tensors must be float64 CUDA tensors of 2*n_out+1 elements")
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        fn = self.lib.lidfe_featurize_raw if raw else self.lib.lidfe_featurize
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.lidfe_featurize(self.handle, plan.handle, packed.data_ptr(), out.data_ptr(),
-                                                self.n_out, _ptr(masks), n_masks, CMVN_MODES[cmvn],
-                                                _ptr(stats_in), _ptr(stats_out), st.cuda_stream))
+            _lib.check(fn(self.handle, plan.handle, packed.data_ptr(), out.data_ptr(), self.n_out, _ptr(masks), n_masks,
+                          CMVN_MODES[cmvn], _ptr(stats_in), _ptr(stats_out), st.cuda_stream))
         return out
+
+    # ------------------------------------------------------------------ argument checks shared by the entry points
+    def _check_feats(self, feats: torch.Tensor, plan: Plan) -> None:
+        if (feats.dtype != torch.float32 or not feats.is_cuda or not feats.is_contiguous()
+                or feats.numel() < plan.rows * self.n_out or feats.device != self.device):
+            raise ValueError("feats must be a contiguous float32 tensor on %s with rows*n_out elements" % self.device)
+
+    def _check_masks(self, masks: Optional[torch.Tensor], plan: Plan):
+        if masks is None:
+            return None, 0
+        if masks.dtype != torch.int32 or masks.dim() != 3 or masks.shape[0] != plan.batch or masks.shape[2] != 4:
+            raise ValueError("masks must be int32 [B, n_masks, 4]")
+        if masks.shape[1] == 0:
+            return None, 0
+        return masks.to(self.device).contiguous(), int(masks.shape[1])
+
+    def _check_stats(self, stats: torch.Tensor) -> None:
+        if (stats.dtype != torch.float64 or stats.numel() != 2 * self.n_out + 1 or not stats.is_cuda
+                or not stats.is_contiguous() or stats.device != self.device):
+            raise ValueError("stats must be a contiguous float64 tensor of 2*n_out+1 elements on %s "
+                             "(move the all-reduced vector back to the GPU)" % self.device)
 
     def cmvn_apply(self, feats: torch.Tensor, plan: Plan, stats: torch.Tensor,
                    masks: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """Second pass of global CMVN, in place: (x - mean) / (std + 1e-9) from the all-reduced sums, then masks."""
-        n_masks = 0
-        if masks is not None:
-            masks = masks.to(self.device).contiguous()
-            n_masks = masks.shape[1]
-            if n_masks == 0:
-                masks = None
+        self._check_feats(feats, plan)
+        self._check_stats(stats)
+        masks, n_masks = self._check_masks(masks, plan)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.lidfe_cmvn_apply(self.handle, plan.handle, feats.data_ptr(), self.n_out, _ptr(masks),
@@ -304,11 +359,14 @@ class FrontEnd:
     def mask_apply(self, feats: torch.Tensor, plan: Plan, masks: torch.Tensor,
                    stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """Zero-fill [t0,t1) x [f0,f1) bands in place (SpecAugment application, ref: lid/audio_processor.py:225-227)."""
-        masks = masks.to(self.device).contiguous()
+        self._check_feats(feats, plan)
+        masks, n_masks = self._check_masks(masks, plan)
+        if masks is None:
+            return feats
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.lidfe_mask_apply(self.handle, plan.handle, feats.data_ptr(), self.n_out,
-                                                 masks.data_ptr(), masks.shape[1], st.cuda_stream))
+                                                 masks.data_ptr(), n_masks, st.cuda_stream))
         return feats
 
     def wave_stages(self, packed: torch.Tensor, plan: Plan, normalize: bool = False, dither: float = 0.0,
@@ -316,10 +374,19 @@ class FrontEnd:
                     stream: Optional[torch.cuda.Stream] = None, out: Optional[torch.Tensor] = None,
                     pcm_scale: float = 1.0 / 32768.0) -> torch.Tensor:
         """normalize_wav / dither / 0.97 pre-emphasis over every utterance of a packed float32 buffer
-        (ref: lid/audio_processor.py:108-115,129-134).  ``packed`` may be int16 PCM (scaled by ``pcm_scale`` first, as
+        (ref: lid/audio_processor.py:108-115,129-134).  ``dither`` without ``noise``: the U[0,1) draw happens on the
+        device (Philox keyed by (seed, utterance, sample)); with ``noise`` (the reference's ``torch.rand_like`` draw) the
+        result is bit-identical to the reference.  ``packed`` may be int16 PCM (scaled by ``pcm_scale`` first, as
         torchaudio.load does).  Returns a new packed float32 buffer (or fills ``out``)."""
         if packed.dtype not in (torch.float32, torch.int16):
             raise ValueError("wave_stages works on float32 samples or int16 PCM")
+        if not packed.is_cuda or not packed.is_contiguous() or packed.numel() < plan.total_samples:
+            raise ValueError("packed must be a contiguous CUDA buffer covering the plan's extent")
+        if noise is not None and (noise.dtype != torch.float32 or not noise.is_cuda or not noise.is_contiguous()
+                                  or noise.numel() < plan.total_samples):
+            raise ValueError("noise must be a contiguous float32 CUDA buffer laid out like `packed`")
+        if out is not None and (out.dtype != torch.float32 or not out.is_cuda or out.numel() < plan.total_samples):
+            raise ValueError("out must be a float32 CUDA buffer covering the plan's extent")
         if out is None:
             out = torch.zeros(packed.numel(), dtype=torch.float32, device=packed.device)
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
@@ -345,14 +412,19 @@ class FrontEnd:
         ``host_in`` may also hold raw int16 PCM (what a 16-bit wav file decodes to): each group is then shipped at
         2 bytes per sample and ``read_audio``'s scaling + ``normalize_wav`` (ref: lid/audio_processor.py:108-122) run on
         the device before framing."""
-        pcm = host_in.dtype == torch.int16 and self.in_dtype == torch.float32
+        pcm = host_in.dtype == torch.int16
+        # int16 PCM into an int16 FrontEnd(in_scale=1/32768): ONE fused pass (statistics pre-pass + normalise-at-load);
+        # into a float32 FrontEnd: the two-kernel path (wave_stages writes a float32 copy the fbank kernel re-reads)
+        fused = pcm and self.in_dtype == torch.int16
         if not plan.padded:
             raise ValueError("featurize_host needs a padded plan")
         if cmvn not in ("none", "utt", "topdb"):
             raise ValueError("featurize_host supports cmvn 'none' or 'utt' (global CMVN needs the all-reduce in between)")
         B = plan.batch
         chunks = max(1, min(chunks, B))
-        key = (plan.handle, chunks, pcm)
+        # the pipeline (sub-plans, device buffers, streams) is keyed by the batch's CONTENT, not by the plan's address:
+        # a freed plan's handle is routinely handed out again by the allocator for a different batch
+        key = (tuple(plan.lengths), tuple(plan.offsets), plan.t_max, chunks, pcm)
         cache = self.__dict__.setdefault("_host_cache", {})
         st = cache.get(key)
         if st is None:
@@ -366,9 +438,10 @@ class FrontEnd:
                                      t_max=plan.t_max)
                 st.append(dict(a=a, b=b, base=base, end=end, plan=sub, stream=torch.cuda.Stream(self.device),
                                dev_in=torch.empty(end - base, dtype=host_in.dtype, device=self.device),
-                               dev_f32=torch.zeros(end - base, dtype=torch.float32, device=self.device) if pcm else None,
-                               dev_out=torch.empty((b - a, plan.t_max, self.n_out), dtype=torch.float32, device=self.device),
-                               dev_masks=None))
+                               dev_f32=(torch.zeros(end - base, dtype=torch.float32, device=self.device)
+                                        if pcm and not fused else None),
+                               dev_out=torch.empty((b - a, plan.t_max, self.n_out), dtype=torch.float32, device=self.device)))
+            torch.cuda.current_stream(self.device).synchronize()      # sub-plan tables were uploaded on this stream
             cache.clear()          # one cached pipeline at a time
             cache[key] = st
         cur = torch.cuda.current_stream(self.device)
@@ -381,9 +454,9 @@ class FrontEnd:
                 if masks is not None and masks.shape[1] > 0:
                     m = masks[c["a"]:c["b"]].to(self.device, non_blocking=True)
                 src = c["dev_in"]
-                if pcm:
+                if pcm and not fused:
                     src = self.wave_stages(c["dev_in"], c["plan"], normalize=True, stream=s, out=c["dev_f32"])
-                self.featurize_packed(src, c["plan"], out=c["dev_out"], masks=m, cmvn=cmvn, stream=s)
+                self.featurize_packed(src, c["plan"], out=c["dev_out"], masks=m, cmvn=cmvn, stream=s, raw=fused)
                 host_out[c["a"]:c["b"]].copy_(c["dev_out"], non_blocking=True)
         for c in st:
             c["stream"].synchronize()

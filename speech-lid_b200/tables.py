@@ -16,6 +16,23 @@ def povey_window(frame_len: int) -> torch.Tensor:
     return torch.hann_window(frame_len, periodic=False, dtype=torch.float32).pow(0.85)
 
 
+def kaldi_window(window_type: str, frame_len: int, blackman_coeff: float = 0.42) -> torch.Tensor:
+    """The five windows of ``_feature_window_function`` with its fp32 torch expressions.   ta: compliance/kaldi.py:86-113"""
+    if window_type == "povey":
+        return povey_window(frame_len)
+    if window_type == "hanning":
+        return torch.hann_window(frame_len, periodic=False, dtype=torch.float32)
+    if window_type == "hamming":
+        return torch.hamming_window(frame_len, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32)
+    if window_type == "rectangular":
+        return torch.ones(frame_len, dtype=torch.float32)
+    if window_type == "blackman":
+        a = 2 * math.pi / (frame_len - 1)
+        n = torch.arange(frame_len, dtype=torch.float32)
+        return (blackman_coeff - 0.5 * torch.cos(a * n) + (0.5 - blackman_coeff) * torch.cos(2 * a * n)).to(torch.float32)
+    raise ValueError("Invalid window type " + window_type)
+
+
 def _mel(freq):
     return 1127.0 * math.log(1.0 + freq / 700.0)
 
