@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblidfe.so")
+# LIDFE_LIB_PATH: development only (kernel variants built next to the product library by tools/build_variants.py)
+LIB_PATH = os.environ.get("LIDFE_LIB_PATH") or os.path.join(_HERE, "liblidfe.so")
 
 # include/lidfe.h
 E_NULL, E_CONFIG, E_SHORT, E_OFFSETS, E_ARG, E_MELBANK, E_NOMEM = -1, -2, -3, -4, -5, -6, -7

@@ -14,6 +14,7 @@
 
 #include "../../include/lidfe.h"
 #include "lidfe_kernels.cuh"
+#include "lidfe_fbank_warp.cuh"
 
 using namespace lidfe;
 
@@ -32,7 +33,7 @@ struct PlanBlock {
   unsigned char* h_tables;      // pinned mirror of the tables section
   size_t ws_bytes, tab_bytes;
   int Bc;
-  long long Sc, Tc, Ic;
+  long long Sc, Tc, Ic, Wc;     // capacities: spans, tiles, items, warp spans
   cudaEvent_t ev;               // last use on the device (kernels or the upload)
   float* d_logmel;              // tile-blocked log-mel workspace of the two-kernel MFCC path (grown on demand)
   long long logmel_tiles;
@@ -55,6 +56,13 @@ struct lidfe_ctx {
   size_t smem_bytes_dct;
   size_t smem_bytes;
   int grid_cap;   // resident CTAs of the fbank kernel on this device
+  // warp-autonomous kernel (lidfe_fbank_warp.cuh): used whenever the configuration and the call are inside its scope
+  int warp_ok;        // configuration inside its scope (KALDI framing, no in-kernel dither, std_mel 0/1)
+  int w_grid;         // resident CTAs of that kernel
+  int w_tab_bytes;    // shared-memory bytes in front of the per-warp areas
+  int w_static_pct;       // share of the quads dealt out as static per-warp runs (LIDFE_WSTATIC, default 90)
+  int w_pool_quads;       // quads per span of the dynamically claimed pool (LIDFE_WPOOL, default 1)
+  size_t w_smem;      // dynamic shared memory per CTA
   int apply_rows; // rows per CTA of cmvn_apply_kernel (LIDFE_APPLY_ROWS, read once)
   int span_tiles; // LIDFE_SPAN_TILES override (0 = automatic)
   int fused_apply;  // LIDFE_FUSED_APPLY=1: per-utterance second stage inside the fbank kernel (service CTAs) instead of a second kernel
@@ -97,6 +105,11 @@ struct lidfe_plan_s {
   long long* d_lengths;   // [B]
   long long* d_utt_first_tile;   // [B]
   Span* d_spans;
+  Span* d_wspans;         // warp spans (NULL when the handle cannot use the warp kernel)
+  long long n_wspans;
+  int n_wstatic;          // spans [0, n_wstatic) are the warps' static runs, the rest is the pool
+  int* d_w_first;         // [W + 1] first static span of every warp
+  bool all_aligned;       // every utterance starts on a 16-byte boundary (TMA-eligible)
   Tile* d_tiles;          // MFCC two-kernel path, else NULL
   long long max_frames;
   long long max_row;      // rows of the output matrix this plan touches
@@ -123,6 +136,14 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 }
 
 typedef void (*fbank_fn)(const FbankParams);
+static fbank_fn pick_warp_kernel(int in_dtype, int std_mel, bool stats) {
+  if (in_dtype == LIDFE_IN_I16) {
+    if (stats) return std_mel == 1 ? fbank_warp_kernel<short, 1, true> : fbank_warp_kernel<short, 0, true>;
+    return std_mel == 1 ? fbank_warp_kernel<short, 1, false> : fbank_warp_kernel<short, 0, false>;
+  }
+  if (stats) return std_mel == 1 ? fbank_warp_kernel<float, 1, true> : fbank_warp_kernel<float, 0, true>;
+  return std_mel == 1 ? fbank_warp_kernel<float, 1, false> : fbank_warp_kernel<float, 0, false>;
+}
 template <typename TIn>
 static fbank_fn pick_kernel_t(bool mfcc, int std_mel) {
   if (mfcc) return std_mel == 1 ? fbank_kernel<TIn, true, 1> : std_mel == 2 ? fbank_kernel<TIn, true, 2> : fbank_kernel<TIn, true, 0>;
@@ -564,6 +585,28 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
       }
     }
   }
+  // warp-autonomous kernel: KALDI framing without in-kernel dither; the HTK / CENTER variant (std_mel 2) stays with fbank_kernel
+  c->warp_ok = (cfg->framing == LIDFE_FRAMING_KALDI && cfg->dither == 0.f && c->std_mel != 2) ? 1 : 0;
+  if (const char* env = getenv("LIDFE_WARP_KERNEL")) c->warp_ok = c->warp_ok && atoi(env) != 0;
+  c->w_static_pct = 90;
+  c->w_pool_quads = 1;
+  if (const char* env = getenv("LIDFE_WSTATIC")) { const int v = atoi(env); if (v >= 0 && v <= 100) c->w_static_pct = v; }
+  if (const char* env = getenv("LIDFE_WPOOL")) { const int v = atoi(env); if (v >= 1 && v <= 64) c->w_pool_quads = v; }
+  if (e == cudaSuccess && c->warp_ok) {
+    c->w_tab_bytes = static_cast<int>((kWTabOff + c->blob_bytes_fbank + kMaxMels * 8 + 127) / 128 * 128);
+    const size_t per_warp = (cfg->in_dtype == LIDFE_IN_I16) ? WarpLayout<short>::kWarpBytes : WarpLayout<float>::kWarpBytes;
+    c->w_smem = static_cast<size_t>(c->w_tab_bytes) + kWWarps * per_warp;
+    fbank_fn wf = pick_warp_kernel(cfg->in_dtype, c->std_mel, true);
+    e = cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->w_smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(pick_warp_kernel(cfg->in_dtype, c->std_mel, false), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(c->w_smem));
+    if (e == cudaSuccess) {
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf, kWThreads, c->w_smem);
+      if (e == cudaSuccess) c->w_grid = (per_sm < 1 ? 1 : per_sm) * c->num_sms;
+    }
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     lidfe_destroy(c);
@@ -614,9 +657,9 @@ int lidfe_destroy(lidfe_handle h) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct BlockLayout {
   size_t sched, utt_done, utt_max, utt_min, utt_stats, utt_wnorm, ws_bytes;
-  size_t frames, out_rows, offsets, lengths, first_tile, items, spans, tiles, tab_bytes;   // tables: relative to ws_bytes
+  size_t frames, out_rows, offsets, lengths, first_tile, items, spans, wfirst, wspans, tiles, tab_bytes;   // tables: relative to ws_bytes
 };
-static BlockLayout block_layout(int Bc, long long Sc, long long Tc, long long Ic, int n_out) {
+static BlockLayout block_layout(int Bc, long long Sc, long long Tc, long long Ic, long long Wc, int n_out, long long n_warps) {
   BlockLayout L;
   size_t o = 0;
   L.sched = o; o += 16;
@@ -634,6 +677,8 @@ static BlockLayout block_layout(int Bc, long long Sc, long long Tc, long long Ic
   L.first_tile = o; o = align_up(o + static_cast<size_t>(Bc) * 8, 32);
   L.items = o; o = align_up(o + static_cast<size_t>(Ic) * 16, 32);
   L.spans = o; o += static_cast<size_t>(Sc) * sizeof(Span);
+  L.wfirst = o; o = align_up(o + (Wc > 0 ? static_cast<size_t>(n_warps) + 1 : 0) * 4, 32);
+  L.wspans = o; o += static_cast<size_t>(Wc) * sizeof(Span);
   L.tiles = o; o += static_cast<size_t>(Tc) * sizeof(Tile);
   L.tab_bytes = align_up(o, 256);
   return L;
@@ -646,13 +691,13 @@ static long long pow2_at_least(long long v, long long lo) {
 
 // a block with room for (B, spans, tiles): from the pool if one fits, else a new allocation (the only place that
 // allocates; the workspace is put to rest once, here -- the kernels leave it at rest)
-static int acquire_block(lidfe_ctx* h, int B, long long n_spans, long long n_tiles, long long n_items, PlanBlock** out) {
+static int acquire_block(lidfe_ctx* h, int B, long long n_spans, long long n_tiles, long long n_items, long long n_wspans, PlanBlock** out) {
   *out = nullptr;
   {
     std::lock_guard<std::mutex> g(*h->pool_mu);
     for (size_t i = 0; i < h->pool->size(); ++i) {
       PlanBlock* b = (*h->pool)[i];
-      if (b->Bc >= B && b->Sc >= n_spans && b->Tc >= n_tiles && b->Ic >= n_items) {
+      if (b->Bc >= B && b->Sc >= n_spans && b->Tc >= n_tiles && b->Ic >= n_items && b->Wc >= n_wspans) {
         h->pool->erase(h->pool->begin() + i);
         *out = b;
         break;
@@ -670,7 +715,8 @@ static int acquire_block(lidfe_ctx* h, int B, long long n_spans, long long n_til
   b->Sc = pow2_at_least(n_spans, 256);
   b->Tc = n_tiles > 0 ? pow2_at_least(n_tiles, 256) : 0;
   b->Ic = pow2_at_least(n_items, 256);
-  const BlockLayout L = block_layout(b->Bc, b->Sc, b->Tc, b->Ic, h->n_out);
+  b->Wc = n_wspans > 0 ? pow2_at_least(n_wspans, 256) : 0;
+  const BlockLayout L = block_layout(b->Bc, b->Sc, b->Tc, b->Ic, b->Wc, h->n_out, static_cast<long long>(h->w_grid) * kWWarps);
   b->ws_bytes = L.ws_bytes;
   b->tab_bytes = L.tab_bytes;
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b->d_base), L.ws_bytes + L.tab_bytes);
@@ -811,8 +857,83 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
     return LIDFE_E_ARG;
   }
   p->n_items = static_cast<int>(items.size());
+  // ---- warp spans (lidfe_fbank_warp.cuh).  The quads (4 frames) of the batch, utterance-major, are dealt out as
+  //      W contiguous STATIC runs of s = floor(f Q / W) quads, one per warp (cut into spans where the utterance changes),
+  //      followed by a POOL of short spans (zero-fill runs first, then the last Q - W s quads) that the warps claim one at
+  //      a time when their own run is done.  w_first[w] .. w_first[w + 1] are warp w's static spans.
+  std::vector<Span> wspans;
+  std::vector<int> w_first;
+  bool all_aligned = true;
+  for (int i = 0; i < B; ++i) all_aligned = all_aligned && ((static_cast<unsigned long long>(wav_offsets_host[i]) * in_elt) % 16ull) == 0ull;
+  if (h->warp_ok && all_aligned) {
+    long long n_quads = 0;
+    for (int i = 0; i < B; ++i) n_quads += (frames[i] + kQuadFrames - 1) / kQuadFrames;
+    const long long W = static_cast<long long>(h->w_grid) * kWWarps;
+    const long long s_run = (n_quads * h->w_static_pct) / (100 * W);          // static quads per warp
+    const long long static_quads = s_run * W;
+    std::vector<Span> pool;
+    auto push_frames = [&](std::vector<Span>& dst, int i, long long f, long long nf) {
+      Span sp;
+      sp.wav_off = wav_offsets_host[i] + f * kFrameShift;
+      sp.out_row = out_rows_host[i] + f;
+      sp.nframes = static_cast<int>(nf);
+      sp.utt = i;
+      sp.t0 = static_cast<int>(f);
+      sp.aux = 1;
+      dst.push_back(sp);
+    };
+    if (pad_rows_host) {
+      for (int i = 0; i < B; ++i) {
+        for (long long r = frames[i]; r < pad_rows_host[i]; r += 64) {
+          Span sp;
+          sp.wav_off = 0;
+          sp.out_row = out_rows_host[i] + r;
+          sp.nframes = 0;
+          sp.utt = i;
+          sp.t0 = static_cast<int>(r);
+          const long long left = pad_rows_host[i] - r;
+          sp.aux = static_cast<int>(left < 64 ? left : 64);
+          pool.push_back(sp);
+        }
+      }
+    }
+    w_first.assign(static_cast<size_t>(W) + 1, 0);
+    long long quad_no = 0;      // quads dealt out so far
+    long long w_cur = 0;        // warp whose run is being filled
+    for (int i = 0; i < B; ++i) {
+      const long long T = frames[i];
+      for (long long f = 0; f < T;) {
+        const long long left_q = (T - f + kQuadFrames - 1) / kQuadFrames;      // quads left in this utterance
+        if (quad_no < static_quads) {
+          while (quad_no >= (w_cur + 1) * s_run) w_first[static_cast<size_t>(++w_cur)] = static_cast<int>(wspans.size());
+          long long q = (w_cur + 1) * s_run - quad_no;                         // quads left in this warp's run
+          if (q > left_q) q = left_q;
+          const long long nf = (T - f) < q * kQuadFrames ? (T - f) : q * kQuadFrames;
+          push_frames(wspans, i, f, nf);
+          quad_no += q;
+          f += nf;
+        } else {
+          long long q = h->w_pool_quads < left_q ? h->w_pool_quads : left_q;
+          const long long nf = (T - f) < q * kQuadFrames ? (T - f) : q * kQuadFrames;
+          push_frames(pool, i, f, nf);
+          quad_no += q;
+          f += nf;
+        }
+      }
+    }
+    while (w_cur < W) w_first[static_cast<size_t>(++w_cur)] = static_cast<int>(wspans.size());
+    p->n_wstatic = static_cast<int>(wspans.size());
+    wspans.insert(wspans.end(), pool.begin(), pool.end());
+    if (wspans.size() > 0x7fffffffull) {
+      delete p;
+      return LIDFE_E_ARG;
+    }
+  }
+  p->n_wspans = static_cast<long long>(wspans.size());
+  p->all_aligned = all_aligned;
   PlanBlock* b = nullptr;
-  const int rc = acquire_block(h, B, p->n_spans, static_cast<long long>(tiles.size()), static_cast<long long>(items.size()), &b);
+  const int rc = acquire_block(h, B, p->n_spans, static_cast<long long>(tiles.size()), static_cast<long long>(items.size()),
+                               p->n_wspans, &b);
   if (rc != LIDFE_OK) {
     delete p;
     return rc;
@@ -822,7 +943,7 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
     std::lock_guard<std::mutex> g(*h->pool_mu);
     ++h->live_plans;
   }
-  const BlockLayout L = block_layout(b->Bc, b->Sc, b->Tc, b->Ic, h->n_out);
+  const BlockLayout L = block_layout(b->Bc, b->Sc, b->Tc, b->Ic, b->Wc, h->n_out, static_cast<long long>(h->w_grid) * kWWarps);
   unsigned char* ws = b->d_base;
   unsigned char* tab = b->d_base + L.ws_bytes;
   p->d_sched = reinterpret_cast<int*>(ws + L.sched);
@@ -838,6 +959,8 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
   p->d_lengths = reinterpret_cast<long long*>(tab + L.lengths);
   p->d_utt_first_tile = reinterpret_cast<long long*>(tab + L.first_tile);
   p->d_spans = reinterpret_cast<Span*>(tab + L.spans);
+  p->d_wspans = wspans.empty() ? nullptr : reinterpret_cast<Span*>(tab + L.wspans);
+  p->d_w_first = wspans.empty() ? nullptr : reinterpret_cast<int*>(tab + L.wfirst);
   p->d_tiles = tiles.empty() ? nullptr : reinterpret_cast<Tile*>(tab + L.tiles);
   // fill the pinned mirror, ONE asynchronous copy of what is used
   unsigned char* ht = b->h_tables;
@@ -848,8 +971,13 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
   memcpy(ht + L.first_tile, utt_first_tile.data(), static_cast<size_t>(B) * 8);
   memcpy(ht + L.items, items.data(), items.size() * sizeof(int4));
   memcpy(ht + L.spans, spans.data(), spans.size() * sizeof(Span));
+  if (!wspans.empty()) {
+    memcpy(ht + L.wspans, wspans.data(), wspans.size() * sizeof(Span));
+    memcpy(ht + L.wfirst, w_first.data(), w_first.size() * sizeof(int));
+  }
   if (!tiles.empty()) memcpy(ht + L.tiles, tiles.data(), tiles.size() * sizeof(Tile));
-  const size_t used = tiles.empty() ? L.spans + spans.size() * sizeof(Span) : L.tiles + tiles.size() * sizeof(Tile);
+  const size_t used = !tiles.empty() ? L.tiles + tiles.size() * sizeof(Tile)
+                      : !wspans.empty() ? L.wspans + wspans.size() * sizeof(Span) : L.spans + spans.size() * sizeof(Span);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemcpyAsync(tab, ht, used, cudaMemcpyHostToDevice, st);
   // the workspace goes to rest (asynchronously, on the same stream): whatever the block's previous plan -- another
@@ -1041,6 +1169,32 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
   P.stats_out = stats_out_dev;
   P.utt_stats = p->d_utt_stats;
 
+  // the warp-autonomous kernel takes every call inside its scope (see lidfe_fbank_warp.cuh)
+  const bool use_warp = h->warp_ok && !raw && p->d_wspans != nullptr && !h->fused_apply && cmvn_mode != LIDFE_POST_TOPDB;
+  auto launch_warp = [&](FbankParams& F, bool profile) -> int {
+    F.wspans = p->d_wspans;
+    F.n_wspans = static_cast<int>(p->n_wspans);
+    F.w_tab_bytes = h->w_tab_bytes;
+    F.const_bytes = h->blob_bytes_fbank;
+    long long grid_w = (p->n_wspans + kWWarps - 1) / kWWarps;      // (never more warps than spans)
+    if (grid_w > h->w_grid || p->n_wstatic > 0) grid_w = h->w_grid;
+    if (grid_w < 1) grid_w = 1;
+    F.w_first = p->d_w_first;
+    F.n_wstatic = p->n_wstatic;
+    fbank_fn wf = pick_warp_kernel(h->cfg.in_dtype, h->std_mel, F.mode == LIDFE_CMVN_PER_UTT || F.mode == LIDFE_CMVN_ACCUM_GLOBAL);
+    bool prof = profile && h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
+    if (prof) prof = (h->prof_calls++ % (h->prof_stride > 0 ? h->prof_stride : 1)) == 0;
+    if (prof) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
+    wf<<<static_cast<unsigned>(grid_w), kWThreads, h->w_smem, st>>>(F);
+    g_launches.fetch_add(1);
+    CU_TRY(cudaGetLastError());
+    if (prof) {
+      CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used + 1], st));
+      h->prof_used += 2;
+    }
+    return LIDFE_OK;
+  };
+
   const bool mfcc2 = p->d_tiles && (cmvn_mode == LIDFE_CMVN_NONE || cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL);
   long long grid = p->n_spans < h->grid_cap ? p->n_spans : h->grid_cap;
   if (grid < 1) grid = 1;
@@ -1074,14 +1228,19 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
                                                      : pick_kernel_t<float>(false, h->std_mel);
     long long g2 = p->n_spans < static_cast<long long>(h->num_sms) * 4 ? p->n_spans : static_cast<long long>(h->num_sms) * 4;
     if (g2 < 1) g2 = 1;
-    const bool prof2 = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
-    if (prof2) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
-    f2<<<static_cast<unsigned>(g2), kThreads, h->smem_bytes_fbank, st>>>(F);
-    g_launches.fetch_add(1);
-    CU_TRY(cudaGetLastError());
-    if (prof2) {
-      CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used + 1], st));
-      h->prof_used += 2;
+    if (use_warp) {
+      const int rcw = launch_warp(F, true);
+      if (rcw != LIDFE_OK) return rcw;
+    } else {
+      const bool prof2 = h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
+      if (prof2) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
+      f2<<<static_cast<unsigned>(g2), kThreads, h->smem_bytes_fbank, st>>>(F);
+      g_launches.fetch_add(1);
+      CU_TRY(cudaGetLastError());
+      if (prof2) {
+        CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used + 1], st));
+        h->prof_used += 2;
+      }
     }
     DctParams D;
     D.logmel = b->d_logmel;
@@ -1104,6 +1263,17 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     mfcc_dct_kernel<<<static_cast<unsigned>(gd), kDctThreads, h->smem_bytes_dct, st>>>(D);
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(p->blk->ev, st));
+    return LIDFE_OK;
+  }
+
+  if (use_warp && h->cfg.n_ceps == 0) {
+    const int launch_parity_w = P.parity;
+    P.n_items = 0;
+    const int rcw = launch_warp(P, true);
+    if (rcw != LIDFE_OK) return rcw;
+    if (cmvn_mode == LIDFE_CMVN_PER_UTT)
+      return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 1, launch_parity_w);
     CU_TRY(cudaEventRecord(p->blk->ev, st));
     return LIDFE_OK;
   }

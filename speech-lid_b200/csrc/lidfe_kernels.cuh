@@ -24,6 +24,12 @@
 #include <type_traits>
 #include <stdint.h>
 
+// Development only: -DLIDFE_ABL=<bits> builds ABLATED variants of fbank_kernel (wrong results) that tools/ablate.py times
+// against the full kernel to price each stage inside the real pipeline.  The product is always built with 0.
+#ifndef LIDFE_ABL
+#define LIDFE_ABL 0
+#endif
+
 namespace lidfe {
 
 constexpr int kFrameLen = 400;
@@ -75,6 +81,12 @@ struct FbankParams {
   long long out_ld;
   const Span* spans;
   int n_spans;
+  // warp-autonomous kernel (lidfe_fbank_warp.cuh): spans = runs of consecutive frames of one utterance
+  const Span* wspans;
+  int n_wspans;
+  const int* w_first;       // [warps + 1]: warp g's static spans are [w_first[g], w_first[g + 1])
+  int n_wstatic;            // spans [n_wstatic, n_wspans) are the pool, claimed one at a time (sched[0])
+  int w_tab_bytes;          // shared-memory bytes in front of the per-warp areas (tables' mbarrier, tables, global-CMVN constants)
   // dynamic schedule + per-utterance completion (all self-cleaning: the kernel leaves them as it found them)
   int* sched;               // [0] span claim counter, [1] CTA exit counter
   int* utt_done;            // [2][B_cap] frames of utterance i whose statistics have been handed over
@@ -520,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
   // compile-time constant there (no per-band bound checks, immediate store offsets)
   const int n_out = (kStdMel != 0 && !kMfcc) ? 80 : P.n_out;
   const int mode = P.mode;
-  const bool want_stats = (mode == 1) || (mode == 3);
+  const bool want_stats = !(LIDFE_ABL & 1024) && ((mode == 1) || (mode == 3));
 
   int taps[kBands], tap_off[kBands + 1];
   tap_off[0] = 0;
@@ -769,14 +781,16 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
         }
         return tl;
       };
-      if (warp == 0) stage_tile(tile_of(0));
+      if (warp == 0 && (!(LIDFE_ABL & 1) || n_sp == 0)) stage_tile(tile_of(0));
 
       for (int ti = 0; ti < n_tiles; ++ti) {
         const Tile tl = tile_of(ti);
         const long long tile_idx = tile0 + ti;
         // consumer side: wait for this tile's samples
-        mbar_wait(&sm_bar[0], phase);
-        phase ^= 1u;
+        if (!(LIDFE_ABL & 1) || (n_sp == 0 && ti == 0)) {
+          mbar_wait(&sm_bar[0], phase);
+          phase ^= 1u;
+        }
         const TIn* in = sm_in;
 
         f2 val[kBands];
@@ -795,7 +809,8 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
     #pragma unroll
             for (int j = 0; j < 18; ++j) {
               const int n = t + 16 * j;
-              x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
+              if (LIDFE_ABL & 8) x[j] = make_float2(__int_as_float(0x3f000000 + ((tl.t0 + n) << 8)), __int_as_float(0x3f800000 - ((tl.t0 + j) << 9)));
+              else x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
             }
             if (wnorm) {   // normalize_wav while loading (row f2): (x - mean) / (std + 1e-6), the division as in wave_stages_kernel
 #pragma unroll
@@ -814,7 +829,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
               }
             }
             float mA = 0.f, mB = 0.f;
-            if (kStdMel == 1 || (kStdMel == 0 && P.remove_dc)) {
+            if (!(LIDFE_ABL & 2048) && (kStdMel == 1 || (kStdMel == 0 && P.remove_dc))) {
               f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
     #pragma unroll
               for (int j = 0; j < 13; ++j) {
@@ -844,13 +859,16 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
     #pragma unroll
               for (int j = 0; j < 13; ++j) {
                 const int n = t + 16 * j;
-                const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
+                const float2 w = (LIDFE_ABL & 256) ? make_float2(0.5f, 0.25f) : *reinterpret_cast<const float2*>(sm_window + 2 * n);
                 const f2 te = make_float2(__fsub_rn(x[j].x, mA), __fsub_rn(x[j + 5].x, mB));   // x[2n]   - mean
                 const f2 to = make_float2(__fsub_rn(x[j].y, mA), __fsub_rn(x[j + 5].y, mB));   // x[2n+1] - mean
                 const f2 send = (t == 15) ? to_prev : to;
                 f2 tp;
-                tp.x = __shfl_sync(0xffffffffu, send.x, up_lane);
-                tp.y = __shfl_sync(0xffffffffu, send.y, up_lane);
+                if (LIDFE_ABL & 128) tp = send;
+                else {
+                  tp.x = __shfl_sync(0xffffffffu, send.x, up_lane);
+                  tp.y = __shfl_sync(0xffffffffu, send.y, up_lane);
+                }
                 if (j == 0 && t == 0) tp = te;
                 to_prev = to;
                 const f2 se = kUnit ? sub2(te, tp) : sub2(te, mul2(tp, bc(c)));
@@ -880,19 +898,20 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
           }
 
           // ---- stage 1: 16-point DFT over j, twiddle W256^(K1*t), transpose through shared ------------
-          fft16<true>(R, I);
+          if (!(LIDFE_ABL & 64)) fft16<true>(R, I);
           __syncwarp();   // previous tile's readers of this scratch are done; every lane has consumed its samples
-          if (arrive_is_last() && ti + 1 < n_tiles) stage_tile(tile_of(ti + 1));   // the input buffer is free: next tile's TMA overlaps the rest
+          if (!(LIDFE_ABL & 1) && arrive_is_last() && ti + 1 < n_tiles) stage_tile(tile_of(ti + 1));   // the input buffer is free: next tile's TMA overlaps the rest
           if (ti == 0) fetch_next();
     #pragma unroll
           for (int p = 0; p < 16; ++p) {
             const int K1 = rev4(p);
             if (K1 != 0) {
-              const float2 w = sm_tw1[K1 * 16 + t];
+              const float2 w = (LIDFE_ABL & 512) ? make_float2(0.6f, 0.8f) : sm_tw1[K1 * 16 + t];
               cmul2(R[p], I[p], w.x, w.y);
             }
-            T_pl[K1 * kRowStride + t] = R[p];
+            if (!(LIDFE_ABL & 2)) T_pl[K1 * kRowStride + t] = R[p];
           }
+          if (!(LIDFE_ABL & 2)) {
           __syncwarp();
     #pragma unroll
           for (int q = 0; q < 8; ++q) {                      // real parts back, transposed
@@ -910,21 +929,26 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
             I[2 * q] = make_float2(b.x, b.y);
             I[2 * q + 1] = make_float2(b.z, b.w);
           }
+          }   // LIDFE_ABL & 2
           // ---- stage 2: position p holds Z[t + 16*rev4(p)] ----------------------------------------------
-          fft16<false>(R, I);
+          if (!(LIDFE_ABL & 64)) fft16<false>(R, I);
           __syncwarp();   // all lanes finished reading the transpose planes before the power bins overwrite them
 
           // ---- real-FFT split + power; lane t pairs with lane 16-t ------------------------------------
-          if (t == 0) my_P[128] = mul2(fma2(R[2], R[2], mul2(I[2], I[2])), bc(4.f));   // 4|Z[128]|^2, Z[128] at rev4(8)
+          f2 abl_psum = make_float2(0.f, 0.f);
+          if (t == 0 && !(LIDFE_ABL & 4)) my_P[128] = mul2(fma2(R[2], R[2], mul2(I[2], I[2])), bc(4.f));   // 4|Z[128]|^2, Z[128] at rev4(8)
     #pragma unroll
           for (int i = 0; i < 8; ++i) {
             // partner's Z[(16-t) + 16 (15-i)]; lane 0 pairs k=16i with 256-16i = its own Z[16 (16-i)], k=0 with itself
             const int ps = rev4(15 - i);
             f2 br, bi;
-            br.x = __shfl_sync(0xffffffffu, R[ps].x, partner);
-            br.y = __shfl_sync(0xffffffffu, R[ps].y, partner);
-            bi.x = __shfl_sync(0xffffffffu, I[ps].x, partner);
-            bi.y = __shfl_sync(0xffffffffu, I[ps].y, partner);
+            if (LIDFE_ABL & 32) { br = R[ps]; bi = I[ps]; }
+            else {
+              br.x = __shfl_sync(0xffffffffu, R[ps].x, partner);
+              br.y = __shfl_sync(0xffffffffu, R[ps].y, partner);
+              bi.x = __shfl_sync(0xffffffffu, I[ps].x, partner);
+              bi.y = __shfl_sync(0xffffffffu, I[ps].y, partner);
+            }
             if (t == 0) {
               const int own = (i == 0) ? 0 : rev4(16 - i);
               br = R[own];
@@ -938,8 +962,12 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
             const f2 xar = add2(e2r, o2r), xai = add2(e2i, o2i);      // 2 X[k]
             const f2 xbr = sub2(e2r, o2r), xbi = sub2(e2i, o2i);      // 2 conj(X[256-k])
             const int k = t + 16 * i;
-            my_P[k] = fma2(xar, xar, mul2(xai, xai));                 // 4 |X[k]|^2   (the 1/4 lives in the mel weights)
-            my_P[256 - k] = fma2(xbr, xbr, mul2(xbi, xbi));
+            if (LIDFE_ABL & 4) {
+              abl_psum = add2(abl_psum, add2(fma2(xar, xar, mul2(xai, xai)), fma2(xbr, xbr, mul2(xbi, xbi))));
+            } else {
+              my_P[k] = fma2(xar, xar, mul2(xai, xai));                 // 4 |X[k]|^2   (the 1/4 lives in the mel weights)
+              my_P[256 - k] = fma2(xbr, xbr, mul2(xbi, xbi));
+            }
           }
           __syncwarp();
 
@@ -947,7 +975,10 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
           // Segment form: this lane walks the bins between the centres of filters d = t + 16 b and d + 1 once, with the
           // down-slope weight of its own filter (wa) and the up-slope weight of the next one (wb); the wb sum travels one
           // lane up (lane 15's goes to lane 0 of the next band).
-          {
+          if (LIDFE_ABL & 4) {
+#pragma unroll
+            for (int b = 0; b < kBands; ++b) val[b] = make_float2(abl_psum.x + b, abl_psum.y - b);
+          } else {
             f2 carry15 = make_float2(0.f, 0.f);                   // lane 0: what lane 15 accumulated for it in the last band
             const int src = (lane & 16) | ((t - 1) & 15);
     #pragma unroll
@@ -1036,7 +1067,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
               float* orow = P.out + (tl.out_row + flA) * P.out_ld + t;
     #pragma unroll
               for (int b = 0; b < kBands; ++b) {
-                if (t + 16 * b < n_out) {
+                if (t + 16 * b < n_out && (!(LIDFE_ABL & 16) || val[b].x == 123.456f)) {
                   orow[16 * b] = val[b].x;
                   orow[P.out_ld + 16 * b] = val[b].y;
                 }
@@ -1053,6 +1084,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
                     x = mul2(sub2(x, bc(nm.x)), bc(nm.y));
                   }
                   const bool dz = (dm >> b) & 1u;
+                  if ((LIDFE_ABL & 16) && x.x != 123.456f) continue;
                   if (actA) orow[16 * b] = (dz || rowA) ? 0.f : x.x;
                   if (actB) orow[P.out_ld + 16 * b] = (dz || rowB) ? 0.f : x.y;
                 }
