@@ -105,6 +105,23 @@ def kaldi_lifter(num_ceps: int, cepstral_lifter: float) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # Framing                                               ta: compliance/kaldi.py:44-83,154-217
 # --------------------------------------------------------------------------------------
+def kaldi_window(window_type: str, n: int, blackman_coeff: float = 0.42) -> torch.Tensor:
+    """The five windows of ``_feature_window_function``.          ta: compliance/kaldi.py:86-113"""
+    if window_type == "povey":
+        return povey_window(n)
+    if window_type == "hanning":
+        return torch.hann_window(n, periodic=False, dtype=torch.float32)
+    if window_type == "hamming":
+        return torch.hamming_window(n, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32)
+    if window_type == "rectangular":
+        return torch.ones(n, dtype=torch.float32)
+    if window_type == "blackman":
+        a = 2 * math.pi / (n - 1)
+        w = torch.arange(n, dtype=torch.float32)
+        return (blackman_coeff - 0.5 * torch.cos(a * w) + (0.5 - blackman_coeff) * torch.cos(2 * a * w)).to(torch.float32)
+    raise Exception("Invalid window type " + window_type)
+
+
 def kaldi_num_frames(num_samples: int, window_size: int = 400, window_shift: int = 160) -> int:
     """snip_edges=True frame count; 0 when the utterance is shorter than one window.
     ta: compliance/kaldi.py:63-67"""
@@ -114,7 +131,7 @@ def kaldi_num_frames(num_samples: int, window_size: int = 400, window_shift: int
 
 
 def kaldi_windowed_frames(wav1d: torch.Tensor, window_size: int, window_shift: int, padded: int,
-                          preemph: float, remove_dc: bool = True) -> torch.Tensor:
+                          preemph: float, remove_dc: bool = True, window_type: str = "povey") -> torch.Tensor:
     """(m, padded) windowed, zero-padded frames.        ta: compliance/kaldi.py:154-217"""
     n = wav1d.numel()
     # ta: compliance/kaldi.py:142  (the reference inherits this assertion; N < window raises)
@@ -127,7 +144,7 @@ def kaldi_windowed_frames(wav1d: torch.Tensor, window_size: int, window_shift: i
     if preemph != 0.0:
         shifted = torch.nn.functional.pad(frames.unsqueeze(0), (1, 0), mode="replicate").squeeze(0)
         frames = frames - preemph * shifted[:, :-1]
-    frames = frames * povey_window(window_size).unsqueeze(0)
+    frames = frames * kaldi_window(window_type, window_size).unsqueeze(0)
     if padded != window_size:
         frames = torch.nn.functional.pad(frames.unsqueeze(0), (0, padded - window_size),
                                          mode="constant", value=0).squeeze(0)
@@ -139,7 +156,8 @@ def kaldi_windowed_frames(wav1d: torch.Tensor, window_size: int, window_shift: i
 #                                                       ta: compliance/kaldi.py:514-645
 # --------------------------------------------------------------------------------------
 def kaldi_fbank(wav: torch.Tensor, n_mels: int = 80, sr: int = 16000, frame_length_ms: int = 25,
-                frame_shift_ms: int = 10, preemph: float = 1.0) -> torch.Tensor:
+                frame_shift_ms: int = 10, preemph: float = 1.0, window_type: str = "povey",
+                remove_dc: bool = True) -> torch.Tensor:
     """(1,N) or (N,) fp32 -> (m, n_mels) log-mel; dither 0, povey, remove_dc, snip_edges, power,
     low_freq 20, high_freq Nyquist -- the argument set of ``_kaidi_wav2mel``."""
     if wav.dim() == 2:
@@ -147,7 +165,7 @@ def kaldi_fbank(wav: torch.Tensor, n_mels: int = 80, sr: int = 16000, frame_leng
     shift = int(sr * frame_shift_ms * 0.001)
     size = int(sr * frame_length_ms * 0.001)
     padded = 1 if size == 0 else 2 ** (size - 1).bit_length()
-    frames = kaldi_windowed_frames(wav.to(torch.float32), size, shift, padded, preemph)
+    frames = kaldi_windowed_frames(wav.to(torch.float32), size, shift, padded, preemph, remove_dc, window_type)
     spectrum = torch.fft.rfft(frames).abs().pow(2.0)
     banks = kaldi_mel_banks(n_mels, padded, float(sr))
     mel = torch.mm(spectrum, banks.T)

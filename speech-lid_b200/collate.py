@@ -50,6 +50,6 @@ class DeviceCollate:
         masks: Optional[torch.Tensor] = None
         if self.train and self.mask_times > 0:
             masks = draw_masks(frames, self.frontend.n_out, self.t_mask, self.f_mask, self.mask_times)
-        feats, wav_percents = self.frontend.featurize(wavs, masks=masks, cmvn=self.cmvn)
+        feats, wav_percents = self.frontend.featurize(wavs, masks=masks, cmvn=self.cmvn, cache_plan=False)
         texts, text_percents, audio_paths, langs = collate_host_part(batch, self.lang2index)
         return feats, texts, wav_percents.to(torch.float32).cpu(), text_percents, audio_paths, langs

@@ -694,14 +694,27 @@ static long long pow2_at_least(long long v, long long lo) {
 static int acquire_block(lidfe_ctx* h, int B, long long n_spans, long long n_tiles, long long n_items, long long n_wspans, PlanBlock** out) {
   *out = nullptr;
   {
+    // first choice: a block that fits and whose previous work has finished (no waiting); second: while the handle owns
+    // fewer than kPoolAsyncBlocks blocks, a new one (so that a loop that creates and destroys a plan per batch can run
+    // ahead of the device); last: wait for a busy block that fits
+    constexpr long long kPoolAsyncBlocks = 4;
     std::lock_guard<std::mutex> g(*h->pool_mu);
+    int busy = -1;
     for (size_t i = 0; i < h->pool->size(); ++i) {
       PlanBlock* b = (*h->pool)[i];
       if (b->Bc >= B && b->Sc >= n_spans && b->Tc >= n_tiles && b->Ic >= n_items && b->Wc >= n_wspans) {
-        h->pool->erase(h->pool->begin() + i);
-        *out = b;
-        break;
+        if (cudaEventQuery(b->ev) == cudaSuccess) {
+          h->pool->erase(h->pool->begin() + i);
+          *out = b;
+          break;
+        }
+        cudaGetLastError();
+        if (busy < 0) busy = static_cast<int>(i);
       }
+    }
+    if (!*out && busy >= 0 && h->blocks_allocated >= kPoolAsyncBlocks) {
+      *out = (*h->pool)[busy];
+      h->pool->erase(h->pool->begin() + busy);
     }
   }
   if (*out) {

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           }
 
           float mA = 0.f, mB = 0.f;
-          if (kStdMel == 1 || (kStdMel == 0 && P.remove_dc)) {
+          if ((kStdMel == 1 && !LIDFE_UNIT_SHORTCUT) || (kStdMel == 0 && P.remove_dc)) {
             f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 13; ++j) {
@@ -334,7 +334,29 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
               I[j] = mul2(so, bc(w.y));
             }
           };
-          if (kStdMel == 1) frame_pass(std::true_type{});
+          if (kStdMel == 1 && LIDFE_UNIT_SHORTCUT) {
+            // The reference's call (DC removal, then pre-emphasis with coefficient 1.0, replicate-left): every output is
+            // (x[n] - m) - (x[n-1] - m), and y[0] = (x[0] - m) - (x[0] - m) = 0.  The frame mean m only enters through the
+            // rounding of the two inner differences; x[n] - x[n-1] rounded ONCE is the same value with less round-off (the
+            // two differ by < 1 ulp of |x|, which is what the reference itself is off by), and the 400-term mean reduction
+            // with its 8 shuffles per quad disappears.
+            float pA = 0.f, pB = 0.f;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) {
+              const int n = t + 16 * j;
+              const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
+              const float sA = (t == 15) ? pA : x[j].y, sB = (t == 15) ? pB : x[j + 5].y;
+              float qA = __shfl_sync(0xffffffffu, sA, up_lane);       // x[2n - 1]
+              float qB = __shfl_sync(0xffffffffu, sB, up_lane);
+              if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
+              pA = x[j].y;
+              pB = x[j + 5].y;
+              const f2 se = make_float2(__fsub_rn(x[j].x, qA), __fsub_rn(x[j + 5].x, qB));
+              const f2 so = make_float2(__fsub_rn(x[j].y, x[j].x), __fsub_rn(x[j + 5].y, x[j + 5].x));
+              R[j] = mul2(se, bc(w.x));
+              I[j] = mul2(so, bc(w.y));
+            }
+          } else if (kStdMel == 1) frame_pass(std::true_type{});
           else frame_pass(std::false_type{});
           if (t >= 8) R[12] = I[12] = make_float2(0.f, 0.f);
           R[13] = R[14] = R[15] = I[13] = I[14] = I[15] = make_float2(0.f, 0.f);
@@ -342,14 +364,24 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
 
         // ---- stage 1: 16-point DFT over j, twiddle W256^(K1*t), ONE transposition through shared memory --------------
         fft16<true>(R, I);
+        {
+          // (re_A, re_B) and (im_A, im_B) of a point go out as the two halves of its 16-byte element; the twiddle of point
+          // p + 2 is requested before point p is multiplied, so that its shared-memory latency hides behind two complex
+          // multiplications instead of stalling each one
+          f2* const X2 = reinterpret_cast<f2*>(X_pl);
+          float2 wa = sm_tw1[rev4(1) * 16 + t], wb = sm_tw1[rev4(2) * 16 + t];
+          X2[2 * t] = R[0];
+          X2[2 * t + 1] = I[0];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-          const int K1 = rev4(p);
-          if (K1 != 0) {
-            const float2 w = sm_tw1[K1 * 16 + t];
+          for (int p = 1; p < 16; ++p) {
+            const int K1 = rev4(p);
+            const float2 w = wa;
+            wa = wb;
+            if (p + 2 < 16) wb = sm_tw1[rev4(p + 2) * 16 + t];
             cmul2(R[p], I[p], w.x, w.y);
+            X2[2 * (K1 * kXRow + t)] = R[p];
+            X2[2 * (K1 * kXRow + t) + 1] = I[p];
           }
-          X_pl[K1 * kXRow + t] = make_float4(R[p].x, R[p].y, I[p].x, I[p].y);
         }
         __syncwarp();
 #pragma unroll
@@ -422,8 +454,8 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             got.y = __shfl_sync(0xffffffffu, nxt.y, src);
             const f2 acc = add2(own, t == 0 ? carry15 : got);
             carry15 = got;
-            val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.x) * P.log_scale,
-                                 acc.y <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.y) * P.log_scale);
+            val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : log2_scaled(acc.x, P.log_scale),
+                                 acc.y <= P.log_floor ? P.log_of_floor : log2_scaled(acc.y, P.log_scale));
           }
         }
         __syncwarp();   // the power bins have been read: the plane is free for the next quad's transposition

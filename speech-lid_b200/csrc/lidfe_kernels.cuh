@@ -29,6 +29,9 @@
 #ifndef LIDFE_ABL
 #define LIDFE_ABL 0
 #endif
+#ifndef LIDFE_UNIT_SHORTCUT
+#define LIDFE_UNIT_SHORTCUT 1    // reference call (DC removal + pre-emphasis 1.0): x[n] - x[n-1] without the frame mean
+#endif
 
 namespace lidfe {
 
@@ -216,6 +219,26 @@ __device__ __forceinline__ float lg2_ftz(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// log2(x) * scale for a normal positive x.  MUFU.LG2 alone is good to 2^-22 RELATIVE to the result (|log2| ~ 10-25 here:
+// ~4e-6 in the natural log, several times the reference's 1-ulp logf and enough to fail the "no worse than the reference"
+// metric in the bins where nothing else goes wrong); on a mantissa in [sqrt(1/2), sqrt(2)) its error is 2^-22 ABSOLUTE,
+// so the exponent is split off first: log2(x) = e + log2(m).
+#ifndef LIDFE_LOG_MODE
+#define LIDFE_LOG_MODE 2
+#endif
+__device__ __forceinline__ float log2_scaled(float x, float scale) {
+#if LIDFE_LOG_MODE == 0
+  return lg2_ftz(x) * scale;
+#elif LIDFE_LOG_MODE == 1
+  return log2f(x) * scale;
+#else
+  const int b = __float_as_int(x);
+  const int e = (b - 0x3f3504f3) >> 23;
+  const float m = __int_as_float(b - (e << 23));
+  return fmaf(static_cast<float>(e), scale, lg2_ftz(m) * scale);
+#endif
 }
 
 // (R + iI) *= (wr + i wi), both frames at once, one scalar twiddle
@@ -829,7 +852,7 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
               }
             }
             float mA = 0.f, mB = 0.f;
-            if (!(LIDFE_ABL & 2048) && (kStdMel == 1 || (kStdMel == 0 && P.remove_dc))) {
+            if (!(LIDFE_ABL & 2048) && ((kStdMel == 1 && !LIDFE_UNIT_SHORTCUT) || (kStdMel == 0 && P.remove_dc))) {
               f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
     #pragma unroll
               for (int j = 0; j < 13; ++j) {
@@ -887,6 +910,25 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
                 const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * (t + 16 * j));
                 R[j] = make_float2(__fmul_rn(x[j].x, w.x), __fmul_rn(x[j + 5].x, w.x));
                 I[j] = make_float2(__fmul_rn(x[j].y, w.y), __fmul_rn(x[j + 5].y, w.y));
+              }
+            } else if (kStdMel == 1 && LIDFE_UNIT_SHORTCUT) {
+              // the reference's call: (x[n] - m) - (x[n-1] - m) = x[n] - x[n-1] rounded once, y[0] = 0 -- the frame mean only
+              // enters through round-off (see lidfe_fbank_warp.cuh, same arithmetic: both kernels give the same bits)
+              float pA = 0.f, pB = 0.f;
+    #pragma unroll
+              for (int j = 0; j < 13; ++j) {
+                const int n = t + 16 * j;
+                const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
+                const float sA = (t == 15) ? pA : x[j].y, sB = (t == 15) ? pB : x[j + 5].y;
+                float qA = __shfl_sync(0xffffffffu, sA, up_lane);
+                float qB = __shfl_sync(0xffffffffu, sB, up_lane);
+                if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
+                pA = x[j].y;
+                pB = x[j + 5].y;
+                const f2 se = make_float2(__fsub_rn(x[j].x, qA), __fsub_rn(x[j + 5].x, qB));
+                const f2 so = make_float2(__fsub_rn(x[j].y, x[j].x), __fsub_rn(x[j + 5].y, x[j + 5].x));
+                R[j] = mul2(se, bc(w.x));
+                I[j] = mul2(so, bc(w.y));
               }
             } else if (kStdMel == 1) {
               frame_pass(std::true_type{});
@@ -1009,8 +1051,8 @@ __global__ void __launch_bounds__(kThreads, 4) fbank_kernel(const __grid_constan
               const f2 acc = add2(own, t == 0 ? carry15 : got);
               carry15 = got;
               // lg2.approx (abs. error ~1e-7 in the log) except at the floor, where the reference's log(eps) is returned exactly
-              val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.x) * P.log_scale,
-                                   acc.y <= P.log_floor ? P.log_of_floor : lg2_ftz(acc.y) * P.log_scale);
+              val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : log2_scaled(acc.x, P.log_scale),
+                                   acc.y <= P.log_floor ? P.log_of_floor : log2_scaled(acc.y, P.log_scale));
             }
           }
 

@@ -463,11 +463,17 @@ class FrontEnd:
         return host_out
 
     def featurize(self, wavs: Sequence[torch.Tensor], masks: Optional[torch.Tensor] = None, cmvn: str = "none",
-                  padded: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                  padded: bool = True, cache_plan: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """The batched public entry: list of waveforms -> ``(feats, wav_percents)`` with the collate contract
-        (ref: lid/raw_datasets.py:345-365).  ``feats`` stays on the device -- that is where the model consumes it."""
+        (ref: lid/raw_datasets.py:345-365).  ``feats`` stays on the device -- that is where the model consumes it.
+        ``cache_plan=False`` (ragged training batches: every batch has its own length signature): the plan is built for
+        this call and handed straight back to the handle's pool -- the pool re-uses its block only after the work
+        launched here has finished (an event per block), so nothing is allocated or freed in steady state."""
         lengths = [int(w.shape[-1]) for w in wavs]
-        plan = self.cached_plan(lengths, padded=padded)
+        plan = self.cached_plan(lengths, padded=padded) if cache_plan else self.make_plan(lengths, padded=padded)
         packed = self.pack(wavs, plan)
         out = self.featurize_packed(packed, plan, masks=masks, cmvn=cmvn)
-        return out, plan.wav_percents     # plan teardown (cudaFree) waits for the launched work
+        percents = plan.wav_percents
+        if not cache_plan:
+            plan.close()
+        return out, percents

@@ -120,6 +120,12 @@ def test_oracle_vs_torchaudio_live():
     x = O.synth_speechlike(8000, 4)
     ref = K.fbank(x, num_mel_bins=80, dither=0.0, preemphasis_coefficient=0.97, sample_frequency=16000)
     assert torch.equal(O.kaldi_fbank(x, preemph=0.97), ref)
+    # every window of _feature_window_function (ta: compliance/kaldi.py:86-113), with and without DC removal
+    for w in ("povey", "hanning", "hamming", "rectangular", "blackman"):
+        ref = K.fbank(x, num_mel_bins=80, dither=0.0, preemphasis_coefficient=1.0, window_type=w, sample_frequency=16000)
+        assert torch.equal(O.kaldi_fbank(x, window_type=w), ref), w
+    ref = K.fbank(x, num_mel_bins=80, dither=0.0, preemphasis_coefficient=0.97, window_type="hamming", remove_dc_offset=False)
+    assert torch.equal(O.kaldi_fbank(x, preemph=0.97, window_type="hamming", remove_dc=False), ref)
 
 
 def test_truth64_calibration():
