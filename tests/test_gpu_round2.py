@@ -357,3 +357,23 @@ def test_strict_metric_iv_per_bin_white_noise(fe):
         eg = (feats[i, :ref.shape[0]].double() - tru).abs().max(0).values
         er = (ref.double() - tru).abs().max(0).values
         assert bool((eg <= 1.5 * er).all())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cfg5: the reference's Conformer consumer on the device (row A10)
+# ---------------------------------------------------------------------------------------------------------------------
+@gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "lid", "ConformerLangModel.py")),
+                    reason="baseline/_ref/lid not staged (__graft_entry__.build() copies it where /root/reference exists)")
+def test_cfg5_reference_consumer_on_device():
+    """On-device features -> the reference's ConformerMutiLangModel forward on the GPU (random init, eval, lang=None;
+    ref: lid/ConformerLangModel.py:77-83, :272-294): CTC logits and language-id scores from the kernel's features equal
+    those from the oracle's features (the reference's arithmetic) to well under the spread between classes."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import cfg5_device
+    r = cfg5_device.run(B=16, n_check=8, steps=1)
+    assert r is not None
+    assert r["features_norm_rel_vs_oracle"] <= 3e-4
+    assert r["consumer_worst_abs_diff"] <= 1e-3, r["consumer"]
+    assert r["consumer_min_argmax_agreement"] >= 0.995, r["consumer"]
+    assert 0.0 < r["frontend_share"] < 1.0
