@@ -397,6 +397,19 @@ def run_gpu_arm(args):
 
     cfg4 = run_cfg4(lid, fe, dev, rank, world, barrier)
 
+    # ---- cfg5 (rank 0, N = 1): features feeding the reference's Conformer forward on the device, when the model files
+    #      have been staged (baseline/_ref, see __graft_entry__.stage_reference_model)
+    cfg5 = None
+    if world == 1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import cfg5_device
+            cfg5 = cfg5_device.run(B=128, n_check=8, steps=3)
+            if cfg5 is not None:
+                cfg5.pop("consumer", None)
+        except Exception as ex:       # the consumer is not the product: never let it take the bench line down
+            cfg5 = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -433,7 +446,7 @@ def run_gpu_arm(args):
             traffic = None
     # the bound that binds is the slower floor: FP32 flops here (41-44 us vs 30 us of HBM time)
     fp32_binds = fp32_floor_us >= hbm_floor_us
-    roofline = {"bound": "fp32" if fp32_binds else "hbm", "kernel": "fbank_kernel<float,false,1> (framing+FFT+mel+log+CMVN+masks, one kernel per step)",
+    roofline = {"bound": "fp32" if fp32_binds else "hbm", "kernel": "fbank_warp_kernel<float,1,true> (framing + FFT + mel + log + per-utterance sums; followed by cmvn_apply_kernel: 2 launches per step)",
                 "achieved": round(fp32_achieved if fp32_binds else hbm_achieved, 2),
                 "peak": round(fp32_peak if fp32_binds else hbm_peak, 2),
                 "peak_source": "in-run FFMA probe (lidfe_fp32_probe)" if fp32_binds else peak_src,
@@ -475,6 +488,7 @@ def run_gpu_arm(args):
             "e2e_ragged": ragged,
             "sustained": sustained,
             "cfg4": cfg4,
+            "cfg5": cfg5,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu}

@@ -31,11 +31,20 @@ def truth_mfcc(x):
     return (f @ dct) * O.kaldi_lifter(40, 22.0).double()
 
 
-def score(got, ref, tru):
+GROUPS = ((0, 3), (3, 10), (10, 40), (40, 80))
+group_fail = {}
+
+
+def score(got, ref, tru, tag=None):
     ii = float((got - ref).abs().max() / ref.abs().max())
     eg = (got.double() - tru).abs().max(0).values
     er = (ref.double() - tru).abs().max(0).values
     ratio = eg / er.clamp_min(1e-30)
+    if tag is not None:
+        for a, b in GROUPS:
+            if a < ratio.numel():
+                k = (tag, a, b)
+                group_fail[k] = group_fail.get(k, 0) + int((ratio[a:b] > 1.5).sum())
     return ii, float(ratio.max()), int((ratio > 1.5).sum())
 
 
@@ -48,7 +57,7 @@ def run(name, wavs, fe, oracle, truth, other=None):
         ref = oracle(w)
         tru = truth(w)
         got = feats[i, :ref.shape[0]]
-        ii, worst, nd = score(got, ref, tru)
+        ii, worst, nd = score(got, ref, tru, name)
         acc["ii_fail"] += ii > 1e-4; acc["ii_worst"] = max(acc["ii_worst"], ii)
         acc["iv_fail_utts"] += nd > 0; acc["iv_fail_dims"] += nd; acc["iv_worst"] = max(acc["iv_worst"], worst)
         acc["dims"] += ref.shape[1]
@@ -59,6 +68,7 @@ def run(name, wavs, fe, oracle, truth, other=None):
     line = ("%-34s utts %4d | (ii) fail %4d worst %.3g | (iv) fail utts %4d, dims %5d of %6d, worst ratio %.2f" % (
         name, acc["utts"], acc["ii_fail"], acc["ii_worst"], acc["iv_fail_utts"], acc["iv_fail_dims"], acc["dims"], acc["iv_worst"]))
     print(line, flush=True)
+    print("%-34s           | (iv) failing dims by output-dim group: %s" % ("", ", ".join("%d-%d: %d" % (a, b - 1, group_fail.get((name, a, b), 0)) for a, b in GROUPS)), flush=True)
     if other is not None:
         print("%-34s           | (ii) fail %4d worst %.3g | (iv) fail utts %4d, dims %5d of %6d, worst ratio %.2f" % (
             "   numpy pocketfft f32 (CPU) vs oracle", oth["ii_fail"], oth["ii_worst"], oth["iv_fail_utts"], oth["iv_fail_dims"], acc["dims"], oth["iv_worst"]), flush=True)
