@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LIDFE_ABI_VERSION 5
+#define LIDFE_ABI_VERSION 6
 
 /* error codes (negative) */
 #define LIDFE_OK 0
@@ -283,6 +283,15 @@ int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long lon
 /* FP32 ceiling of the device, measured: a dependent-free FFMA loop on every SM for about `ms_budget` milliseconds.
  * Writes the achieved TFLOP/s (2 flops per FFMA) -- bench.py reports the kernel against this, not against a data sheet. */
 int lidfe_fp32_probe(float ms_budget, double* tflops_out, void* stream);
+
+/* Host-side gather of a batch into the packed layout a plan describes (replaces the host half of the reference's
+ * collate, ref: lid/raw_datasets.py:345-351, whose pad_sequence copies every waveform once as well): utterance i
+ * (lengths[i] elements of elem_bytes = 4 for float32 or 2 for int16 PCM, at src_host[i]) is copied to
+ * dst_host + offsets[i] * elem_bytes; the alignment gaps and the tail up to total_elems are zeroed.  The byte range is
+ * split over `threads` host threads (0 = hardware concurrency, at most 32).  dst_host is normally pinned memory that
+ * the caller then ships with one cudaMemcpyAsync.  No CUDA call is made. */
+int lidfe_pack_host(void* dst_host, const void* const* src_host, const long long* offsets, const long long* lengths,
+                    int B, int elem_bytes, long long total_elems, int threads);
 
 const char* lidfe_strerror(int rc);
 int lidfe_abi_version(void);

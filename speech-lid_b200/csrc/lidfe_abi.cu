@@ -10,6 +10,7 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/lidfe.h"
@@ -62,6 +63,8 @@ struct lidfe_ctx {
   int w_tab_bytes;    // shared-memory bytes in front of the per-warp areas
   int w_static_pct;       // share of the quads dealt out as static per-warp runs (LIDFE_WSTATIC, default 90)
   int w_pool_quads;       // quads per span of the dynamically claimed pool (LIDFE_WPOOL, default 1)
+  int w_fused;            // per-utterance CMVN: second stage inside the warp kernel (LIDFE_WFUSED, default 1) instead of a second launch
+  int w_groups;           // fused second stage: the static runs are dealt out in this many utterance groups (LIDFE_WGROUPS)
   size_t w_smem;      // dynamic shared memory per CTA
   int apply_rows; // rows per CTA of cmvn_apply_kernel (LIDFE_APPLY_ROWS, read once)
   int span_tiles; // LIDFE_SPAN_TILES override (0 = automatic)
@@ -104,6 +107,8 @@ struct lidfe_plan_s {
   long long* d_offsets;   // [B]
   long long* d_lengths;   // [B]
   long long* d_utt_first_tile;   // [B]
+  int* d_first_item;             // [B + 1] first second-stage item of every utterance
+  int* d_wq;                     // ready queue of the warp kernel's fused second stage ([4 + Ic] int, at rest = 0)
   Span* d_spans;
   Span* d_wspans;         // warp spans (NULL when the handle cannot use the warp kernel)
   long long n_wspans;
@@ -366,6 +371,64 @@ extern "C" {
 int lidfe_abi_version(void) { return LIDFE_ABI_VERSION; }
 long long lidfe_launch_count(void) { return g_launches.load(); }
 
+// ---- host-side packer: B utterance buffers -> one packed (pinned) staging buffer -------------------------------------
+// The reference's collate builds its batch with pad_sequence on the host (ref: lid/raw_datasets.py:345-351); here the
+// host only gathers the raw samples at the plan's offsets.  A 256 x 1-20 s batch is 170 MB: one thread copies it at
+// 5-8 GB/s, which would make the packer -- not PCIe, not the kernel -- the slowest stage of the ragged end-to-end path,
+// so the byte range is cut into equal shares and copied by `threads` threads (utterances are split where a share ends).
+int lidfe_pack_host(void* dst_host, const void* const* src_host, const long long* offsets, const long long* lengths,
+                    int B, int elem_bytes, long long total_elems, int threads) {
+  if (!dst_host || !src_host || !offsets || !lengths) return LIDFE_E_NULL;
+  if (B <= 0 || (elem_bytes != 2 && elem_bytes != 4) || total_elems < 0) return LIDFE_E_ARG;
+  long long pos = 0;
+  for (int i = 0; i < B; ++i) {
+    if (!src_host[i] && lengths[i] > 0) return LIDFE_E_NULL;
+    if (lengths[i] < 0 || offsets[i] < pos || offsets[i] + lengths[i] > total_elems) return LIDFE_E_OFFSETS;
+    pos = offsets[i] + lengths[i];
+  }
+  unsigned char* const dst = static_cast<unsigned char*>(dst_host);
+  const long long eb = elem_bytes;
+  // alignment gaps between utterances (and the tail) are zeroed so the staging buffer is a function of the batch alone
+  auto work = [&](long long lo, long long hi) {          // bytes [lo, hi) of the packed buffer
+    long long prev_end = 0;
+    for (int i = 0; i < B; ++i) {
+      const long long a = offsets[i] * eb, b = (offsets[i] + lengths[i]) * eb;
+      const long long g0 = prev_end > lo ? prev_end : lo, g1 = a < hi ? a : hi;
+      if (g1 > g0) memset(dst + g0, 0, static_cast<size_t>(g1 - g0));
+      const long long c0 = a > lo ? a : lo, c1 = b < hi ? b : hi;
+      if (c1 > c0) memcpy(dst + c0, static_cast<const unsigned char*>(src_host[i]) + (c0 - a), static_cast<size_t>(c1 - c0));
+      prev_end = b;
+      if (a >= hi) return;
+    }
+    const long long g0 = prev_end > lo ? prev_end : lo;
+    if (hi > g0) memset(dst + g0, 0, static_cast<size_t>(hi - g0));
+  };
+  const long long total = total_elems * eb;
+  int T = threads > 0 ? threads : static_cast<int>(std::thread::hardware_concurrency());
+  if (T < 1) T = 1;
+  if (T > 32) T = 32;
+  if (total < (1ll << 20)) T = 1;
+  if (T == 1) {
+    work(0, total);
+    return LIDFE_OK;
+  }
+  const long long share = ((total + T - 1) / T + 63) / 64 * 64;
+  std::vector<std::thread> pool;
+  try {
+    for (int k = 1; k < T; ++k) {
+      const long long lo = share * k, hi = (share * (k + 1) < total) ? share * (k + 1) : total;
+      if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+  } catch (...) {
+    for (auto& th : pool) th.join();
+    work(0, total);                                      // could not start the threads: do all of it here
+    return LIDFE_OK;
+  }
+  work(0, share < total ? share : total);
+  for (auto& th : pool) th.join();
+  return LIDFE_OK;
+}
+
 const char* lidfe_strerror(int rc) {
   switch (rc) {
     case LIDFE_OK: return "ok";
@@ -592,6 +655,10 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   c->w_pool_quads = 1;
   if (const char* env = getenv("LIDFE_WSTATIC")) { const int v = atoi(env); if (v >= 0 && v <= 100) c->w_static_pct = v; }
   if (const char* env = getenv("LIDFE_WPOOL")) { const int v = atoi(env); if (v >= 1 && v <= 64) c->w_pool_quads = v; }
+  c->w_fused = 0;
+  c->w_groups = 1;
+  if (const char* env = getenv("LIDFE_WFUSED")) c->w_fused = atoi(env) != 0;
+  if (const char* env = getenv("LIDFE_WGROUPS")) { const int v = atoi(env); if (v >= 1 && v <= 64) c->w_groups = v; }
   if (e == cudaSuccess && c->warp_ok) {
     c->w_tab_bytes = static_cast<int>((kWTabOff + c->blob_bytes_fbank + kMaxMels * 8 + 127) / 128 * 128);
     const size_t per_warp = (cfg->in_dtype == LIDFE_IN_I16) ? WarpLayout<short>::kWarpBytes : WarpLayout<float>::kWarpBytes;
@@ -656,8 +723,8 @@ int lidfe_destroy(lidfe_handle h) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct BlockLayout {
-  size_t sched, utt_done, utt_max, utt_min, utt_stats, utt_wnorm, ws_bytes;
-  size_t frames, out_rows, offsets, lengths, first_tile, items, spans, wfirst, wspans, tiles, tab_bytes;   // tables: relative to ws_bytes
+  size_t sched, utt_done, utt_max, utt_min, utt_stats, utt_wnorm, wq, ws_bytes;
+  size_t frames, out_rows, offsets, lengths, first_tile, first_item, items, spans, wfirst, wspans, tiles, tab_bytes;   // tables: relative to ws_bytes
 };
 static BlockLayout block_layout(int Bc, long long Sc, long long Tc, long long Ic, long long Wc, int n_out, long long n_warps) {
   BlockLayout L;
@@ -668,6 +735,7 @@ static BlockLayout block_layout(int Bc, long long Sc, long long Tc, long long Ic
   L.utt_min = o; o = align_up(o + 2 * static_cast<size_t>(Bc) * 4, 16);
   L.utt_stats = o; o = align_up(o + 2 * static_cast<size_t>(Bc) * 2 * n_out * 8, 16);
   L.utt_wnorm = o; o = align_up(o + static_cast<size_t>(Bc) * 8, 256);
+  L.wq = o; o = align_up(o + (static_cast<size_t>(Ic) + 4) * 4, 256);
   L.ws_bytes = o;
   o = 0;
   L.frames = o; o += static_cast<size_t>(Bc) * 8;
@@ -675,6 +743,7 @@ static BlockLayout block_layout(int Bc, long long Sc, long long Tc, long long Ic
   L.offsets = o; o += static_cast<size_t>(Bc) * 8;
   L.lengths = o; o += static_cast<size_t>(Bc) * 8;
   L.first_tile = o; o = align_up(o + static_cast<size_t>(Bc) * 8, 32);
+  L.first_item = o; o = align_up(o + (static_cast<size_t>(Bc) + 1) * 4, 32);
   L.items = o; o = align_up(o + static_cast<size_t>(Ic) * 16, 32);
   L.spans = o; o += static_cast<size_t>(Sc) * sizeof(Span);
   L.wfirst = o; o = align_up(o + (Wc > 0 ? static_cast<size_t>(n_warps) + 1 : 0) * 4, 32);
@@ -859,8 +928,10 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
   }
   // items of the in-kernel second stage: <= apply_block rows of one utterance each, utterance-major
   std::vector<int4> items;
+  std::vector<int> first_item(static_cast<size_t>(B) + 1, 0);
   for (int i = 0; i < B; ++i) {
     const long long T = frames[i];
+    first_item[static_cast<size_t>(i)] = static_cast<int>(items.size());
     for (long long r = 0; r < T; r += h->apply_block)
       items.push_back(make_int4(i, static_cast<int>(r), static_cast<int>(T - r < h->apply_block ? T - r : h->apply_block),
                                 static_cast<int>(T)));
@@ -870,6 +941,7 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
     return LIDFE_E_ARG;
   }
   p->n_items = static_cast<int>(items.size());
+  first_item[static_cast<size_t>(B)] = p->n_items;
   // ---- warp spans (lidfe_fbank_warp.cuh).  The quads (4 frames) of the batch, utterance-major, are dealt out as
   //      W contiguous STATIC runs of s = floor(f Q / W) quads, one per warp (cut into spans where the utterance changes),
   //      followed by a POOL of short spans (zero-fill runs first, then the last Q - W s quads) that the warps claim one at
@@ -910,31 +982,71 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
         }
       }
     }
-    w_first.assign(static_cast<size_t>(W) + 1, 0);
-    long long quad_no = 0;      // quads dealt out so far
-    long long w_cur = 0;        // warp whose run is being filled
-    for (int i = 0; i < B; ++i) {
-      const long long T = frames[i];
-      for (long long f = 0; f < T;) {
-        const long long left_q = (T - f + kQuadFrames - 1) / kQuadFrames;      // quads left in this utterance
-        if (quad_no < static_quads) {
-          while (quad_no >= (w_cur + 1) * s_run) w_first[static_cast<size_t>(++w_cur)] = static_cast<int>(wspans.size());
-          long long q = (w_cur + 1) * s_run - quad_no;                         // quads left in this warp's run
-          if (q > left_q) q = left_q;
-          const long long nf = (T - f) < q * kQuadFrames ? (T - f) : q * kQuadFrames;
-          push_frames(wspans, i, f, nf);
-          quad_no += q;
-          f += nf;
-        } else {
-          long long q = h->w_pool_quads < left_q ? h->w_pool_quads : left_q;
-          const long long nf = (T - f) < q * kQuadFrames ? (T - f) : q * kQuadFrames;
-          push_frames(pool, i, f, nf);
-          quad_no += q;
-          f += nf;
-        }
+    // Utterance GROUPS (w_groups > 1, for the fused per-utterance second stage): the batch is cut into G runs of whole
+    // utterances with about Q / G quads each, and every warp's static run is the concatenation of its share of group 0,
+    // its share of group 1, ...: all warps work on group g at about the same time, so the utterances of group g are
+    // complete -- and their second stage can start -- while groups g + 1 ... are still being computed.  Groups before
+    // the last are dealt out completely (shares differ by at most one quad, the longer ones rotate over the warps);
+    // the last group keeps the static / pool split that balances the tail.  G = 1 is the plain schedule.
+    long long G = h->w_groups;
+    while (G > 1 && n_quads / G < 4 * W) --G;
+    std::vector<int> group_of(static_cast<size_t>(B), 0);
+    std::vector<long long> group_quads(static_cast<size_t>(G), 0);
+    {
+      long long before = 0;
+      for (int i = 0; i < B; ++i) {
+        long long g = n_quads > 0 ? (before * G) / n_quads : 0;
+        if (g > G - 1) g = G - 1;
+        group_of[static_cast<size_t>(i)] = static_cast<int>(g);
+        const long long q = (frames[i] + kQuadFrames - 1) / kQuadFrames;
+        group_quads[static_cast<size_t>(g)] += q;
+        before += q;
       }
     }
-    while (w_cur < W) w_first[static_cast<size_t>(++w_cur)] = static_cast<int>(wspans.size());
+    std::vector<std::vector<Span>> per_warp(static_cast<size_t>(W));
+    long long rot = 0;          // warp that takes the first run of the group
+    int i_next = 0;             // first utterance of the group
+    for (long long g = 0; g < G; ++g) {
+      const long long Qg = group_quads[static_cast<size_t>(g)];
+      const bool last = (g == G - 1);
+      const long long base = last ? (Qg * h->w_static_pct) / (100 * W) : Qg / W;
+      const long long extra = last ? 0 : Qg % W;           // the first `extra` runs are one quad longer
+      const long long static_q = last ? base * W : Qg;
+      long long quad_no = 0;      // quads of this group dealt out so far
+      long long k = 0;            // run being filled
+      long long run_end = base + (0 < extra ? 1 : 0);      // quad_no at which run k ends
+      for (int i = i_next; i < B && group_of[static_cast<size_t>(i)] == g; ++i, i_next = i) {
+        const long long T = frames[i];
+        for (long long f = 0; f < T;) {
+          const long long left_q = (T - f + kQuadFrames - 1) / kQuadFrames;      // quads left in this utterance
+          if (quad_no < static_q) {
+            while (quad_no >= run_end) {
+              ++k;
+              run_end += base + (k < extra ? 1 : 0);
+            }
+            long long q = run_end - quad_no;                                      // quads left in this run
+            if (q > left_q) q = left_q;
+            const long long nf = (T - f) < q * kQuadFrames ? (T - f) : q * kQuadFrames;
+            push_frames(per_warp[static_cast<size_t>((k + rot) % W)], i, f, nf);
+            quad_no += q;
+            f += nf;
+          } else {
+            long long q = h->w_pool_quads < left_q ? h->w_pool_quads : left_q;
+            const long long nf = (T - f) < q * kQuadFrames ? (T - f) : q * kQuadFrames;
+            push_frames(pool, i, f, nf);
+            quad_no += q;
+            f += nf;
+          }
+        }
+      }
+      rot = (rot + extra) % W;
+    }
+    w_first.assign(static_cast<size_t>(W) + 1, 0);
+    for (long long w = 0; w < W; ++w) {
+      w_first[static_cast<size_t>(w)] = static_cast<int>(wspans.size());
+      wspans.insert(wspans.end(), per_warp[static_cast<size_t>(w)].begin(), per_warp[static_cast<size_t>(w)].end());
+    }
+    w_first[static_cast<size_t>(W)] = static_cast<int>(wspans.size());
     p->n_wstatic = static_cast<int>(wspans.size());
     wspans.insert(wspans.end(), pool.begin(), pool.end());
     if (wspans.size() > 0x7fffffffull) {
@@ -971,6 +1083,8 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
   p->d_offsets = reinterpret_cast<long long*>(tab + L.offsets);
   p->d_lengths = reinterpret_cast<long long*>(tab + L.lengths);
   p->d_utt_first_tile = reinterpret_cast<long long*>(tab + L.first_tile);
+  p->d_first_item = reinterpret_cast<int*>(tab + L.first_item);
+  p->d_wq = reinterpret_cast<int*>(ws + L.wq);
   p->d_spans = reinterpret_cast<Span*>(tab + L.spans);
   p->d_wspans = wspans.empty() ? nullptr : reinterpret_cast<Span*>(tab + L.wspans);
   p->d_w_first = wspans.empty() ? nullptr : reinterpret_cast<int*>(tab + L.wfirst);
@@ -982,6 +1096,7 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
   memcpy(ht + L.offsets, wav_offsets_host, static_cast<size_t>(B) * 8);
   memcpy(ht + L.lengths, wav_lengths_host, static_cast<size_t>(B) * 8);
   memcpy(ht + L.first_tile, utt_first_tile.data(), static_cast<size_t>(B) * 8);
+  memcpy(ht + L.first_item, first_item.data(), (static_cast<size_t>(B) + 1) * 4);
   memcpy(ht + L.items, items.data(), items.size() * sizeof(int4));
   memcpy(ht + L.spans, spans.data(), spans.size() * sizeof(Span));
   if (!wspans.empty()) {
@@ -1148,6 +1263,8 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
   P.utt_frames = p->d_frames;
   P.utt_out_row = p->d_out_rows;
   P.utt_first_tile = p->d_utt_first_tile;
+  P.utt_first_item = p->d_first_item;
+  P.wq = p->d_wq;
   P.const_blob = h->d_blob;
   P.const_bytes = h->blob_bytes;
   for (int b = 0; b < kBands; ++b) P.band_taps[b] = h->band_taps[b];
@@ -1282,10 +1399,12 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
 
   if (use_warp && h->cfg.n_ceps == 0) {
     const int launch_parity_w = P.parity;
-    P.n_items = 0;
+    // per-utterance CMVN: the second stage runs inside the kernel (w_fused), else as a second launch
+    const bool fused_w = LIDFE_WFUSED_BUILD && h->w_fused && cmvn_mode == LIDFE_CMVN_PER_UTT && p->n_items > 0;
+    if (!fused_w) P.n_items = 0;
     const int rcw = launch_warp(P, true);
     if (rcw != LIDFE_OK) return rcw;
-    if (cmvn_mode == LIDFE_CMVN_PER_UTT)
+    if (cmvn_mode == LIDFE_CMVN_PER_UTT && !fused_w)
       return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 1, launch_parity_w);
     CU_TRY(cudaEventRecord(p->blk->ev, st));
     return LIDFE_OK;

@@ -46,6 +46,18 @@ constexpr int kWThreads = kWWarps * 32;
 #define LIDFE_FOLD_QUADS 8
 #endif
 constexpr int kFoldQuads = LIDFE_FOLD_QUADS;     // fp32 partial sums are folded into the fp64 accumulators this often
+#ifndef LIDFE_XPOSE_ST128
+#define LIDFE_XPOSE_ST128 1      // transposition stores: 1 = one STS.128 per point, 0 = two STS.64 halves
+#endif
+#ifndef LIDFE_PRE_SHARE
+#define LIDFE_PRE_SHARE 0        // unit pre-emphasis: 1 = frames A and B share the 18 "previous sample" shuffles
+#endif
+#ifndef LIDFE_WFUSED_BUILD
+#define LIDFE_WFUSED_BUILD 0      // 1: build the in-kernel per-utterance second stage (then LIDFE_WFUSED=1 selects it)
+#endif
+#ifndef LIDFE_MEL_COMPLEMENT
+#define LIDFE_MEL_COMPLEMENT 0   // experiment: next filter's share = segment sum - own share (weights as one LDS.32)
+#endif
 constexpr int kWTabOff = 128;                    // tables start here (the tables' mbarrier sits in front)
 
 // per half-warp transposition plane: 16 rows of 17 elements of 16 bytes (re_A, re_B, im_A, im_B); reused for the 257
@@ -67,6 +79,87 @@ struct WSpanRegs {     // the fields of a span a warp needs per quad, read from 
   long long wav_off, out_row;
   int nframes, utt, t0, aux;
 };
+
+// ---- fused per-utterance second stage (mode 1, P.n_items > 0), out of line: none of its state lives in the quad loop ----
+// Every hand-over announces its frames on the utterance's counter; the warp whose hand-over makes the count complete
+// publishes the utterance's items (<= apply_block rows each) in the ready queue.  A warp that has run out of spans takes
+// items by ticket (one atomicAdd each) until all have been handed out: the rows are rewritten out of L2 by the warps that
+// finish first while the others still compute, and by all of them at the end.
+// MEASURED (cfg2, one B200, tools/dev_fused.py): correct (equal to the two-launch path to 1 ulp on every case) and
+// SLOWER -- 155 us per step against 130 us for fbank_warp_kernel + cmvn_apply_kernel: an item is a chain of dependent
+// round trips (ticket, queue slot, descriptor, sums, rows) that 1.4 items per warp cannot hide, where the stand-alone
+// kernel has 1280 CTAs in flight.  Taking items INSIDE the span loop (to overlap them with the FFTs) makes ptxas keep
+// the quad loop's statistics registers on the stack whether the call is inlined or not (~30 local accesses per quad;
+// 174 us with the span body moved out of line instead, because kernel parameters then stop being constant-bank
+// operands), and a compare-and-swap claim serialises at one item per L2 round trip (3.3 ms).  Hence a build switch
+// (LIDFE_WFUSED_BUILD), off by default; the two-launch path stays the product.
+__device__ __noinline__ void announce_frames_warp(const FbankParams& P, int utt, int frames_held) {
+  const int lane = threadIdx.x & 31;
+  int* const done_cur = P.utt_done + (P.parity & 1) * P.b_cap;
+  __threadfence();       // release: this warp's rows and sums before its frames are announced
+  __syncwarp();
+  int complete = 0;
+  if (lane == 0) complete = (atomicAdd(&done_cur[utt], frames_held) + frames_held == static_cast<int>(__ldg(P.utt_frames + utt)));
+  complete = __shfl_sync(0xffffffffu, complete, 0);
+  if (!complete) return;
+  const int first = __ldg(P.utt_first_item + utt), n = __ldg(P.utt_first_item + utt + 1) - first;
+  int base = 0;
+  if (lane == 0) {
+    done_cur[utt] = 0;                                    // back to rest: nobody adds to a complete utterance
+    base = atomicAdd(&P.wq[0], n);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __threadfence();
+  for (int i = lane; i < n; i += 32) st_volatile_i(&P.wq[4 + base + i], first + i + 1);
+}
+
+__device__ __noinline__ void second_stage_warp(const FbankParams& P, unsigned char* scratch, int n_out) {
+  const int lane = threadIdx.x & 31;
+  float4* const c4 = reinterpret_cast<float4*>(scratch);                          // mean | inv | lo: 60 float4
+  float* const cf = reinterpret_cast<float*>(c4);
+  int* const amasks = reinterpret_cast<int*>(cf + 3 * kMaxMels);                   // [kMaxMasks][4]
+  const double* const stats_cur = P.utt_stats + static_cast<long long>(P.parity & 1) * P.b_cap * 2 * n_out;
+  for (;;) {
+    int e = -1;
+    if (lane == 0) {
+      // a ticket per item: the warp has no spans left, so waiting for a slot that other warps have yet to publish costs
+      // nothing (and cannot dead-lock: whoever still computes does not wait for anything)
+      const int slot = atomicAdd(&P.wq[1], 1);
+      if (slot < P.n_items) {
+        while ((e = ld_volatile_i(&P.wq[4 + slot])) == 0) __nanosleep(64);
+        P.wq[4 + slot] = 0;                               // the slot goes back to rest
+        __threadfence();                                  // acquire: the utterance's sums and rows
+        e -= 1;
+      }
+    }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e < 0) return;
+    const int4 item = __ldg(&P.items[e]);                 // (utt, first row, rows, frames of the utterance)
+    const int utt = item.x;
+    for (int d = lane; d < n_out; d += 32) {
+      const double n = static_cast<double>(item.w);
+      const double sm = __ldcg(stats_cur + (static_cast<long long>(utt) * 2 + 0) * n_out + d);
+      const double ss = __ldcg(stats_cur + (static_cast<long long>(utt) * 2 + 1) * n_out + d);
+      const double mu = sm / n;
+      double var = (ss - sm * mu) / (n - 1.0);            // n == 1 -> NaN, as torch.std of one sample
+      var = var > 0.0 ? var : (var == var ? 0.0 : var);
+      const float mean = static_cast<float>(mu);
+      cf[d] = mean;
+      cf[kMaxMels + d] = static_cast<float>(1.0 / (sqrt(var) + 1e-9));
+      cf[2 * kMaxMels + d] = static_cast<float>(-(mu - static_cast<double>(mean)) / (sqrt(var) + 1e-9));
+    }
+    if (P.n_masks > 0 && lane < P.n_masks * 4) amasks[lane] = __ldg(P.masks + static_cast<long long>(utt) * P.n_masks * 4 + lane);
+    if (item.y == 0) {         // first item of the utterance: the other launch parity's sums go back to rest
+      double* os = P.utt_stats + (static_cast<long long>((P.parity & 1) ^ 1) * P.b_cap + utt) * 2 * n_out;
+      for (int q = lane; q < 2 * n_out; q += 32) os[q] = 0.0;
+    }
+    __syncwarp();
+    const bool fast = (n_out == 80) && (P.out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0);
+    apply_rows_warp(P.out + (__ldg(P.utt_out_row + utt) + item.y) * P.out_ld, P.out_ld, n_out, P.n_masks, fast, item.y, item.z,
+                    1, 0.f, c4, amasks);
+    __syncwarp();              // the scratch is free again
+  }
+}
 
 template <typename TIn, int kStdMel, bool kStats>
 __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(const __grid_constant__ FbankParams P) {
@@ -193,37 +286,13 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
     if (lane == 0 && s0.nframes > 0) stage_quad(s0.wav_off, min(kQuadFrames, s0.nframes));
   }
 
-  // centred fp32 partial sums of this lane's dims over the last few quads: S = sum(x - c), Q = sum((x - c)^2), c = the
-  // first value of the period -- the squares are O(variance), not O(mean^2), so sum(x^2) - sum(x)^2 / n does not cancel
-  // the digits an fp32 partial sum has
-  float S[kBands], Q[kBands], C[kBands];
-#pragma unroll
-  for (int b = 0; b < kBands; ++b) S[b] = Q[b] = C[b] = 0.f;
-  int quads_since_fold = 0;
-  int cnt = 0;                         // frames this lane has added since the last fold
   int frames_acc = 0;                  // mode 3: frames of the spans this warp has processed
   int held_utt = -1;                   // mode 1: whose sums the accumulators hold
+  int frames_held = 0;                 // mode 1, fused second stage: frames of held_utt in the accumulators
 
-  // fp32 partials -> lane-owned fp64 accumulators (lanes 0..15 own dims t + 16 b)
-  auto fold = [&]() {
-    const double n = static_cast<double>(cnt);
-#pragma unroll
-    for (int b = 0; b < kBands; ++b) {
-      // un-centre in fp64: sum(x) = S + n c,  sum(x^2) = Q + 2 c S + n c^2
-      const double c = static_cast<double>(C[b]), sc = static_cast<double>(S[b]);
-      double s = fma(n, c, sc);
-      double q = fma(n * c, c, fma(2.0 * c, sc, static_cast<double>(Q[b])));
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-      q += __shfl_xor_sync(0xffffffffu, q, 16);
-      if (half == 0 && t + 16 * b < n_out) {
-        acc_s[t + 16 * b] += s;
-        acc_q[t + 16 * b] += q;
-      }
-      S[b] = Q[b] = 0.f;
-    }
-    quads_since_fold = 0;
-    cnt = 0;
-  };
+  // per-utterance second stage inside this kernel: compiled in only with -DLIDFE_WFUSED_BUILD=1 (see the note above
+  // announce_frames_warp: it is slower than the second launch, and its mere presence costs the statistics variant 4 us)
+  const bool fused2 = LIDFE_WFUSED_BUILD && kStats && mode == 1 && P.n_items > 0;
 
   while (have_cur) {
     // the next span's descriptor travels into the other slot while this span runs
@@ -247,6 +316,34 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
         if (nx.nframes > 0) stage_quad(nx.wav_off, min(kQuadFrames, nx.nframes));
       }
     } else {
+      // centred fp32 partial sums of this lane's dims over the last few quads: S = sum(x - c), Q = sum((x - c)^2), c = the
+      // first value of the period -- the squares are O(variance), not O(mean^2), so sum(x^2) - sum(x)^2 / n does not cancel
+      // the digits an fp32 partial sum has
+      float S[kBands], Q[kBands], C[kBands];
+    #pragma unroll
+      for (int b = 0; b < kBands; ++b) S[b] = Q[b] = C[b] = 0.f;
+      int quads_since_fold = 0;
+      int cnt = 0;                         // frames this lane has added since the last fold
+      // fp32 partials -> lane-owned fp64 accumulators (lanes 0..15 own dims t + 16 b)
+      auto fold = [&]() {
+        const double n = static_cast<double>(cnt);
+    #pragma unroll
+        for (int b = 0; b < kBands; ++b) {
+          // un-centre in fp64: sum(x) = S + n c,  sum(x^2) = Q + 2 c S + n c^2
+          const double c = static_cast<double>(C[b]), sc = static_cast<double>(S[b]);
+          double s = fma(n, c, sc);
+          double q = fma(n * c, c, fma(2.0 * c, sc, static_cast<double>(Q[b])));
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          q += __shfl_xor_sync(0xffffffffu, q, 16);
+          if (half == 0 && t + 16 * b < n_out) {
+            acc_s[t + 16 * b] += s;
+            acc_q[t + 16 * b] += q;
+          }
+          S[b] = Q[b] = 0.f;
+        }
+        quads_since_fold = 0;
+        cnt = 0;
+      };
       // ---- per-span set-up: the utterance's mask table (modes that mask in the epilogue) --------------------------
       unsigned dim_masked = 0u;
       const int n_masks = (!kStats && (mode == 0 || mode == 2)) ? P.n_masks : 0;
@@ -257,7 +354,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
         __syncwarp();
         for (int q = 0; q < n_masks; ++q) {
           const int f0 = wmasks[4 * q + 2], f1 = wmasks[4 * q + 3];
-#pragma unroll
+    #pragma unroll
           for (int b = 0; b < kBands; ++b) dim_masked |= (t + 16 * b >= f0 && t + 16 * b < f1) ? (1u << b) : 0u;
         }
       }
@@ -276,7 +373,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           // ---- load (frame B = frame A shifted by 5 loads), DC removal, pre-emphasis, window ----------------------
           const TIn* fr = sm_in + kFrameShift * (actA ? flA : 0);
           float2 x[18];
-#pragma unroll
+    #pragma unroll
           for (int j = 0; j < 18; ++j) {
             const int n = t + 16 * j;
             x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
@@ -296,7 +393,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           float mA = 0.f, mB = 0.f;
           if ((kStdMel == 1 && !LIDFE_UNIT_SHORTCUT) || (kStdMel == 0 && P.remove_dc)) {
             f2 sA = make_float2(0.f, 0.f), sB = make_float2(0.f, 0.f);
-#pragma unroll
+    #pragma unroll
             for (int j = 0; j < 13; ++j) {
               if (j < 12 || t < 8) {
                 sA = add2(sA, x[j]);
@@ -304,7 +401,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
               }
             }
             f2 sum = make_float2(sA.x + sA.y, sB.x + sB.y);
-#pragma unroll
+    #pragma unroll
             for (int o = 8; o >= 1; o >>= 1) {
               sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
               sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
@@ -316,7 +413,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           auto frame_pass = [&](auto unit_tag) {
             constexpr bool kUnit = decltype(unit_tag)::value;
             f2 to_prev = make_float2(0.f, 0.f);
-#pragma unroll
+    #pragma unroll
             for (int j = 0; j < 13; ++j) {
               const int n = t + 16 * j;
               const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
@@ -340,17 +437,33 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             // rounding of the two inner differences; x[n] - x[n-1] rounded ONCE is the same value with less round-off (the
             // two differ by < 1 ulp of |x|, which is what the reference itself is off by), and the 400-term mean reduction
             // with its 8 shuffles per quad disappears.
+    #if LIDFE_PRE_SHARE
+            // frame B is frame A five loads on: element j of B needs the same "previous sample" as element j + 5 of A,
+            // so 18 shuffles serve both frames (13 + 13 otherwise); only B's first sample (replicate-left) differs
+            float q[18];
+    #pragma unroll
+            for (int j = 0; j < 18; ++j) {
+              const float s = (t == 15) ? (j ? x[j - 1].y : 0.f) : x[j].y;
+              q[j] = __shfl_sync(0xffffffffu, s, up_lane);              // x[2n - 1], n = t + 16 j
+            }
+    #else
             float pA = 0.f, pB = 0.f;
-#pragma unroll
+    #endif
+    #pragma unroll
             for (int j = 0; j < 13; ++j) {
               const int n = t + 16 * j;
               const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
+    #if LIDFE_PRE_SHARE
+              float qA = q[j], qB = q[j + 5];
+              if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
+    #else
               const float sA = (t == 15) ? pA : x[j].y, sB = (t == 15) ? pB : x[j + 5].y;
               float qA = __shfl_sync(0xffffffffu, sA, up_lane);       // x[2n - 1]
               float qB = __shfl_sync(0xffffffffu, sB, up_lane);
               if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
               pA = x[j].y;
               pB = x[j + 5].y;
+    #endif
               const f2 se = make_float2(__fsub_rn(x[j].x, qA), __fsub_rn(x[j + 5].x, qB));
               const f2 so = make_float2(__fsub_rn(x[j].y, x[j].x), __fsub_rn(x[j + 5].y, x[j + 5].x));
               R[j] = mul2(se, bc(w.x));
@@ -368,23 +481,33 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           // (re_A, re_B) and (im_A, im_B) of a point go out as the two halves of its 16-byte element; the twiddle of point
           // p + 2 is requested before point p is multiplied, so that its shared-memory latency hides behind two complex
           // multiplications instead of stalling each one
+    #if !LIDFE_XPOSE_ST128
           f2* const X2 = reinterpret_cast<f2*>(X_pl);
+    #endif
           float2 wa = sm_tw1[rev4(1) * 16 + t], wb = sm_tw1[rev4(2) * 16 + t];
+    #if LIDFE_XPOSE_ST128
+          X_pl[t] = make_float4(R[0].x, R[0].y, I[0].x, I[0].y);
+    #else
           X2[2 * t] = R[0];
           X2[2 * t + 1] = I[0];
-#pragma unroll
+    #endif
+    #pragma unroll
           for (int p = 1; p < 16; ++p) {
             const int K1 = rev4(p);
             const float2 w = wa;
             wa = wb;
             if (p + 2 < 16) wb = sm_tw1[rev4(p + 2) * 16 + t];
             cmul2(R[p], I[p], w.x, w.y);
+    #if LIDFE_XPOSE_ST128
+            X_pl[K1 * kXRow + t] = make_float4(R[p].x, R[p].y, I[p].x, I[p].y);
+    #else
             X2[2 * (K1 * kXRow + t)] = R[p];
             X2[2 * (K1 * kXRow + t) + 1] = I[p];
+    #endif
           }
         }
         __syncwarp();
-#pragma unroll
+    #pragma unroll
         for (int m = 0; m < 16; ++m) {
           const int e = (m & 3) * 4 + (m >> 2);          // 0, 4, 8, 12, 1, ...: the order the first radix-4 layer consumes
           const float4 v = X_pl[t * kXRow + e];
@@ -397,7 +520,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
 
         // ---- real-FFT split + power ---------------------------------------------------------------------------------
         if (t == 0) my_P[128] = mul2(fma2(R[2], R[2], mul2(I[2], I[2])), bc(4.f));
-#pragma unroll
+    #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int ps = rev4(15 - i);
           f2 br, bi;
@@ -427,13 +550,23 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
         {
           f2 carry15 = make_float2(0.f, 0.f);
           const int src = (lane & 16) | ((t - 1) & 15);
-#pragma unroll
+    #pragma unroll
           for (int b = 0; b < kBands; ++b) {
             f2 own = make_float2(0.f, 0.f), nxt = make_float2(0.f, 0.f);
             const f2* pp = my_P + sm_k0[t + 16 * b];
             const float2* wp = reinterpret_cast<const float2*>(sm_melw) + tap_off[b] * 16 + t;
-            if (kStdMel) {
-#pragma unroll
+            if (kStdMel && LIDFE_MEL_COMPLEMENT) {
+              f2 tot = make_float2(0.f, 0.f);
+    #pragma unroll
+              for (int i = 0; i < std_taps(kStdMel, b); ++i) {
+                const f2 p = pp[i];
+                const float w = wp[i * 16].x;
+                own = fma2(p, bc(w), own);
+                tot = add2(tot, p);
+              }
+              nxt = sub2(tot, own);
+            } else if (kStdMel) {
+    #pragma unroll
               for (int i = 0; i < std_taps(kStdMel, b); ++i) {
                 const f2 p = pp[i];
                 const float2 w = wp[i * 16];
@@ -441,7 +574,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
                 nxt = fma2(p, bc(w.y), nxt);
               }
             } else {
-#pragma unroll 2
+    #pragma unroll 2
               for (int i = 0; i < taps[b]; ++i) {
                 const f2 p = pp[i];
                 const float2 w = wp[i * 16];
@@ -470,7 +603,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             const long long tile_idx = P.utt_first_tile[sp.utt] + tfA / kTileFrames;
             const int fl = tfA % kTileFrames;                   // even: A and B share the tile
             float* o = P.out + tile_idx * (kTileFrames * n_out) + (t >> 2) * 64 + (t & 3) + fl * 4;
-#pragma unroll
+    #pragma unroll
             for (int b = 0; b < kBands; ++b) {
               if (t + 16 * b < n_out) {
                 if (actA) o[256 * b] = val[b].x;
@@ -479,7 +612,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             }
           } else if (mode != 2 && n_masks == 0 && nf == kQuadFrames) {
             float* orow = P.out + row * P.out_ld + t;
-#pragma unroll
+    #pragma unroll
             for (int b = 0; b < kBands; ++b) {
               if (t + 16 * b < n_out) {
                 orow[16 * b] = val[b].x;
@@ -494,7 +627,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
               rowB |= (tfA + 1 >= m0 && tfA + 1 < m1);
             }
             float* orow = P.out + row * P.out_ld + t;
-#pragma unroll
+    #pragma unroll
             for (int b = 0; b < kBands; ++b) {
               const int d = t + 16 * b;
               if (d < n_out) {
@@ -514,11 +647,11 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
         // ---- statistics: centred fp32 partial sums in registers, folded into fp64 every kFoldQuads quads -------------
         if (kStats) {
           if (quads_since_fold == 0) {     // (a dead pair holds frame 0 of its quad: as good a centre as any)
-#pragma unroll
+    #pragma unroll
             for (int b = 0; b < kBands; ++b) C[b] = val[b].x;
           }
           if (nf == kQuadFrames) {
-#pragma unroll
+    #pragma unroll
             for (int b = 0; b < kBands; ++b) {
               const float dx = val[b].x - C[b], dy = val[b].y - C[b];
               S[b] += dx + dy;
@@ -526,7 +659,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             }
             cnt += 2;
           } else {
-#pragma unroll
+    #pragma unroll
             for (int b = 0; b < kBands; ++b) {
               const float dx = val[b].x - C[b], dy = val[b].y - C[b];
               if (actA) { S[b] += dx; Q[b] = fmaf(dx, dx, Q[b]); }
@@ -543,6 +676,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
         // order of the fp64 additions)
         if (quads_since_fold) fold();
         frames_acc += sp_nframes;
+        frames_held += sp_nframes;
         held_utt = read_span(cur).utt;
       }
     }
@@ -568,6 +702,10 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           if (a != 0.0) atomicAdd(g + e, a);
           if (b2 != 0.0) atomicAdd(g + n_out + e, b2);
         }
+        if (fused2) {
+          announce_frames_warp(P, held_utt, frames_held);
+        }
+        frames_held = 0;
         held_utt = -1;
       }
     }
@@ -581,9 +719,11 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
     nxt_idx = __shfl_sync(0xffffffffu, nxt_idx, 0);
   }
 
+  // ---- out of spans: the second stage of whatever is (or becomes) ready ------------------------------------------------
+  if (fused2) second_stage_warp(P, wbase + WL::off_plane, n_out);
+
   // ---- out of work: global sums leave the CTA once; the last CTA puts the claim counter back to rest ----------------
   if (kStats && mode == 3) {
-    if (quads_since_fold) fold();
     __syncthreads();
     for (int e = tid; e < 2 * kMaxMels; e += kWThreads) {
       const int which = e / kMaxMels, d = e - which * kMaxMels;
@@ -600,6 +740,10 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
     if (atomicAdd(&P.sched[1], 1) == static_cast<int>(gridDim.x) - 1) {
       P.sched[0] = 0;
       P.sched[1] = 0;
+      if (fused2) {
+        P.wq[0] = 0;
+        P.wq[1] = 0;
+      }
     }
   }
 }

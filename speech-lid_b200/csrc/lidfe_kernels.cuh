@@ -110,6 +110,10 @@ struct FbankParams {
   long long* dbg_buf;       // [grid][8] per-CTA timeline (LIDFE_DBG & 16), else NULL
   int dbg;                  // development switches (LIDFE_DBG): 1 skip apply_rows, 2 skip the stats atomics, 4 skip fences, 8 no help at span ends
   const long long* utt_frames;      // [B]
+  // warp kernel, fused per-utterance second stage (lidfe_fbank_warp.cuh): the warp whose hand-over completes an
+  // utterance publishes that utterance's items in the ready queue; warps take them at span ends and when out of spans
+  int* wq;                          // [0] entries published, [1] entries claimed, [4 + i] item index + 1 (0 = not yet written)
+  const int* utt_first_item;        // [B + 1] first item of every utterance (items are utterance-major)
   const long long* utt_out_row;     // [B]
   const long long* utt_first_tile;  // [B] (tile-blocked log-mel workspace of the two-kernel MFCC path)
   // constant tables: ONE device blob laid out exactly like the kernel's shared-memory table area, so a single TMA
@@ -518,6 +522,10 @@ __device__ __forceinline__ int ld_volatile_i(const int* p) {
   int v;
   asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+__device__ __forceinline__ void st_volatile_i(int* p, int v) {
+  asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -273,11 +273,45 @@ class FrontEnd:
             for w, o, n in zip(flat, plan.offsets, plan.lengths):
                 packed[o:o + n].copy_(w.to(self.in_dtype), non_blocking=True)
             return packed
-        if pinned is None or pinned.numel() < plan.total_samples:
-            pinned = torch.zeros(plan.total_samples, dtype=self.in_dtype).pin_memory()
-        for w, o, n in zip(flat, plan.offsets, plan.lengths):
-            pinned[o:o + n].copy_(w.to(self.in_dtype))
-        return pinned[:plan.total_samples].to(self.device, non_blocking=True)
+        # host inputs: the native packer (lidfe_pack_host, a few host threads) gathers them into a persistent pinned
+        # staging buffer -- two of them alternate, each guarded by the event of its last H2D copy, so nothing is
+        # pinned / allocated per batch and the packer of batch i+1 never overwrites bytes batch i is still shipping
+        host = []
+        for w in flat:
+            if w.is_cuda:
+                w = w.cpu()
+            if w.dtype != self.in_dtype or not w.is_contiguous():
+                w = w.to(self.in_dtype).contiguous()
+            host.append(w)
+        cur = torch.cuda.current_stream(self.device)
+        if pinned is not None and pinned.numel() >= plan.total_samples:
+            stage, ev = pinned, None
+        else:
+            stage, ev = self._staging(plan.total_samples)
+        B = len(host)
+        ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in host])
+        _lib.check(self.lib.lidfe_pack_host(stage.data_ptr(), ptrs, _ll_array(plan.offsets), _ll_array(plan.lengths), B,
+                                            stage.element_size(), plan.total_samples, int(self.pack_threads)))
+        with torch.cuda.device(self.device):
+            dev = stage[:plan.total_samples].to(self.device, non_blocking=True)
+            if ev is not None:
+                ev.record(cur)
+        return dev
+
+    pack_threads = 8      # host threads of the native packer (lidfe_pack_host)
+
+    def _staging(self, n: int):
+        """One of two persistent pinned staging buffers of at least ``n`` elements, free for reuse (its last H2D copy
+        has completed), with the event the caller records after shipping it."""
+        st = self.__dict__.setdefault("_stage", {"bufs": [None, None], "evs": [None, None], "i": 0})
+        i = st["i"] = st["i"] ^ 1
+        if st["evs"][i] is None:
+            st["evs"][i] = torch.cuda.Event()
+        else:
+            st["evs"][i].synchronize()
+        if st["bufs"][i] is None or st["bufs"][i].numel() < n:
+            st["bufs"][i] = torch.empty(int(n * 1.25) + 1024, dtype=self.in_dtype).pin_memory()
+        return st["bufs"][i], st["evs"][i]
 
     # ------------------------------------------------------------------ the hot path
     def featurize_packed(self, packed: torch.Tensor, plan: Plan, out: Optional[torch.Tensor] = None,

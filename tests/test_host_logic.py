@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, "liblidfe.so does not export %s" % missing
     assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
-    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 6
 
 
 def _cfg(**kw):
@@ -298,3 +298,54 @@ def test_resample_tables_bit_identical_to_torchaudio():
         assert w == wr and torch.equal(k, kr[:, 0, :])
         ko, wo, _, _ = O.sinc_resample_kernel(orig, 16000)
         assert wo == w and torch.equal(ko[:, 0, :], k)
+
+
+def test_draw_masks_vectorised_equals_the_serial_draw():
+    """draw_masks draws all uniforms with one torch.rand(K); the definition is mask_along_axis' two torch.rand(1) per
+    mask (ta: functional/functional.py:885-958).  Same integers and the same generator state afterwards."""
+    import random
+    from speech_lid_b200.specaug import draw_masks, _draw_masks_serial
+    rnd = random.Random(5)
+    for trial in range(120):
+        B = rnd.randint(1, 48)
+        frames = [rnd.choice([1, 5, 19, 20, 21, 98, 500, 1998, rnd.randint(1, 3000)]) for _ in range(B)]
+        t_mask = rnd.choice([0.05, 0.0, 0.1, 0.2])
+        n_mels = rnd.choice([80, 40, 23])
+        f_mask = rnd.choice([f for f in (27, 0, 1, 15, 80) if f <= n_mels])
+        times = rnd.choice([0, 1, 2, 3])
+        torch.manual_seed(trial)
+        want = _draw_masks_serial(frames, n_mels, t_mask, f_mask, times)
+        after_want = torch.rand(1)
+        torch.manual_seed(trial)
+        got = draw_masks(frames, n_mels, t_mask, f_mask, times)
+        after_got = torch.rand(1)
+        assert torch.equal(want, got) and torch.equal(after_want, after_got), (trial, frames, t_mask, f_mask, times)
+
+
+def test_pack_host_gathers_and_zeroes_gaps():
+    """lidfe_pack_host (the host half of the collate, ref: lid/raw_datasets.py:345-351): every thread count gives the
+    same bytes as a plain per-utterance copy, gaps and tail zeroed, bad arguments rejected."""
+    lib = lid.load_library()
+    g = torch.Generator().manual_seed(11)
+    ll = lambda v: (C.c_longlong * len(v))(*v)
+    for dtype, eb in ((torch.float32, 4), (torch.int16, 2)):
+        lens = torch.randint(400, 300000, (37,), generator=g).tolist() + [400, 401, 0]
+        ws = [(torch.randn(n, generator=g) * 1000).to(dtype) for n in lens]
+        offs, pos = [], 0
+        for n in lens:
+            offs.append(pos)
+            pos += (n + 7) // 8 * 8
+        total = pos + 333
+        want = torch.zeros(total, dtype=dtype)
+        for w, o, n in zip(ws, offs, lens):
+            want[o:o + n] = w
+        ptrs = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        for threads in (1, 2, 3, 8, 32, 0):
+            dst = torch.full((total,), 7, dtype=dtype)
+            assert lib.lidfe_pack_host(dst.data_ptr(), ptrs, ll(offs), ll(lens), len(ws), eb, total, threads) == 0
+            assert torch.equal(dst, want), (dtype, threads)
+        dst = torch.zeros(total, dtype=dtype)
+        assert lib.lidfe_pack_host(dst.data_ptr(), ptrs, ll(offs), ll(lens), len(ws), 3, total, 1) == _lib.E_ARG
+        assert lib.lidfe_pack_host(dst.data_ptr(), ptrs, ll(offs[::-1]), ll(lens), len(ws), eb, total, 1) == _lib.E_OFFSETS
+        assert lib.lidfe_pack_host(dst.data_ptr(), ptrs, ll(offs), ll(lens), len(ws), eb, pos - 1000, 1) == _lib.E_OFFSETS
+        assert lib.lidfe_pack_host(None, ptrs, ll(offs), ll(lens), len(ws), eb, total, 1) == _lib.E_NULL
