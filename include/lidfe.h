@@ -293,6 +293,12 @@ int lidfe_fp32_probe(float ms_budget, double* tflops_out, void* stream);
 int lidfe_pack_host(void* dst_host, const void* const* src_host, const long long* offsets, const long long* lengths,
                     int B, int elem_bytes, long long total_elems, int threads);
 
+/* The same gather for sources that already sit in pinned host memory (a DataLoader with pin_memory=True): no staging
+ * copy, one cudaMemcpyAsync per utterance on `stream` straight to dst_dev + offsets[i] * elem_bytes.  The gaps are not
+ * written (the kernels never read them).  The caller keeps the sources alive until the stream has passed this point. */
+int lidfe_h2d_gather(void* dst_dev, const void* const* src_host, const long long* offsets, const long long* lengths,
+                     int B, int elem_bytes, void* stream);
+
 const char* lidfe_strerror(int rc);
 int lidfe_abi_version(void);
 /* kernels launched by this library in this process so far (bench.py reports it as gpu_launches) */

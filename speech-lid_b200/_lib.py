@@ -27,7 +27,7 @@ EXPORTS = (
     "lidfe_featurize", "lidfe_cmvn_apply", "lidfe_wave_stages", "lidfe_wave_stages_i16", "lidfe_mask_apply", "lidfe_strerror",
     "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_profile_set_stride", "lidfe_mel_plan", "lidfe_mel_plan_expand",
     "lidfe_resampler_create", "lidfe_resampler_destroy", "lidfe_resample_out_len", "lidfe_resample",
-    "lidfe_plan_create_async", "lidfe_plan_num_spans", "lidfe_featurize_raw", "lidfe_fp32_probe", "lidfe_pool_stats", "lidfe_pack_host",
+    "lidfe_plan_create_async", "lidfe_plan_num_spans", "lidfe_featurize_raw", "lidfe_fp32_probe", "lidfe_pool_stats", "lidfe_pack_host", "lidfe_h2d_gather",
 )
 
 
@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
     lib.lidfe_pool_stats.restype = i32
     lib.lidfe_pack_host.argtypes = [vp, C.POINTER(vp), pll, pll, i32, i32, ll, i32]
     lib.lidfe_pack_host.restype = i32
+    lib.lidfe_h2d_gather.argtypes = [vp, C.POINTER(vp), pll, pll, i32, i32, vp]
+    lib.lidfe_h2d_gather.restype = i32
     lib.lidfe_cmvn_apply.argtypes = [vp, vp, vp, ll, vp, i32, vp, vp]
     lib.lidfe_cmvn_apply.restype = i32
     lib.lidfe_mask_apply.argtypes = [vp, vp, vp, ll, vp, i32, vp]

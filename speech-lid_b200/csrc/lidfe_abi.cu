@@ -429,6 +429,28 @@ int lidfe_pack_host(void* dst_host, const void* const* src_host, const long long
   return LIDFE_OK;
 }
 
+// Pinned sources need no staging copy at all: one cudaMemcpyAsync per utterance, straight to its place in the packed
+// device buffer (a DataLoader with pin_memory=True hands out exactly such tensors).
+int lidfe_h2d_gather(void* dst_dev, const void* const* src_host, const long long* offsets, const long long* lengths,
+                     int B, int elem_bytes, void* stream) {
+  if (!dst_dev || !src_host || !offsets || !lengths) return LIDFE_E_NULL;
+  if (B <= 0 || (elem_bytes != 2 && elem_bytes != 4)) return LIDFE_E_ARG;
+  long long pos = 0;
+  for (int i = 0; i < B; ++i) {
+    if (!src_host[i] && lengths[i] > 0) return LIDFE_E_NULL;
+    if (lengths[i] < 0 || offsets[i] < pos) return LIDFE_E_OFFSETS;
+    pos = offsets[i] + lengths[i];
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* const dst = static_cast<unsigned char*>(dst_dev);
+  for (int i = 0; i < B; ++i) {
+    if (lengths[i] == 0) continue;
+    CU_TRY(cudaMemcpyAsync(dst + offsets[i] * elem_bytes, src_host[i], static_cast<size_t>(lengths[i]) * elem_bytes,
+                           cudaMemcpyHostToDevice, st));
+  }
+  return LIDFE_OK;
+}
+
 const char* lidfe_strerror(int rc) {
   switch (rc) {
     case LIDFE_OK: return "ok";
@@ -549,6 +571,8 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   }
   // the unrolled variants also hard-wire the framing of the call they belong to (see the kernel)
   if (c->std_mel == 1 && !(cfg->remove_dc && cfg->preemph == 1.f)) c->std_mel = 0;
+  // ... and variant 1 the reference call's log: natural, floored at FLT_EPSILON (compile-time constants in the warp kernel)
+  if (c->std_mel == 1 && !(cfg->log_kind == LIDFE_LOG_NATURAL && cfg->log_floor == 1.1920928955078125e-07f)) c->std_mel = 0;
   if (c->std_mel == 2 && !(!cfg->remove_dc && cfg->preemph == 0.f)) c->std_mel = 0;
   std::vector<float> melw(mp.w);
   for (float& v : melw) v *= 0.25f;

@@ -587,8 +587,11 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             got.y = __shfl_sync(0xffffffffu, nxt.y, src);
             const f2 acc = add2(own, t == 0 ? carry15 : got);
             carry15 = got;
-            val[b] = make_float2(acc.x <= P.log_floor ? P.log_of_floor : log2_scaled(acc.x, P.log_scale),
-                                 acc.y <= P.log_floor ? P.log_of_floor : log2_scaled(acc.y, P.log_scale));
+            // variant 1 is the reference's call: log(max(x, FLT_EPSILON)) -- floor, its log and ln 2 are immediates
+            const float lfloor = (kStdMel == 1) ? 1.1920928955078125e-07f : P.log_floor;
+            const float lof = (kStdMel == 1) ? -15.9423847198486328125f : P.log_of_floor;
+            const float lsc = (kStdMel == 1) ? 0.693147180559945309f : P.log_scale;
+            val[b] = make_float2(acc.x <= lfloor ? lof : log2_scaled(acc.x, lsc), acc.y <= lfloor ? lof : log2_scaled(acc.y, lsc));
           }
         }
         __syncwarp();   // the power bins have been read: the plane is free for the next quad's transposition

@@ -9,6 +9,7 @@ batch plus ``wav_percents = T_i / T_max``) and of ``wav2mel(use_kaildi=True)``
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -284,21 +285,55 @@ class FrontEnd:
                 w = w.to(self.in_dtype).contiguous()
             host.append(w)
         cur = torch.cuda.current_stream(self.device)
+        if pinned is None and all(w.is_pinned() for w in host):
+            # already pinned (DataLoader(pin_memory=True)): no staging copy, one async copy per utterance straight to its
+            # place; the sources are kept referenced until the stream has passed the copies
+            keep = self.__dict__.setdefault("_h2d_keep", [])
+            while keep and keep[0][0].query():
+                keep.pop(0)
+            with torch.cuda.device(self.device):
+                dev = torch.zeros(plan.total_samples, dtype=self.in_dtype, device=self.device)
+                ptrs = (C.c_void_p * len(host))(*[w.data_ptr() for w in host])
+                _lib.check(self.lib.lidfe_h2d_gather(dev.data_ptr(), ptrs, _ll_array(plan.offsets), _ll_array(plan.lengths),
+                                                     len(host), dev.element_size(), cur.cuda_stream))
+                done = torch.cuda.Event()
+                done.record(cur)
+            keep.append((done, host))
+            return dev
         if pinned is not None and pinned.numel() >= plan.total_samples:
             stage, ev = pinned, None
         else:
             stage, ev = self._staging(plan.total_samples)
         B = len(host)
-        ptrs = (C.c_void_p * B)(*[w.data_ptr() for w in host])
-        _lib.check(self.lib.lidfe_pack_host(stage.data_ptr(), ptrs, _ll_array(plan.offsets), _ll_array(plan.lengths), B,
-                                            stage.element_size(), plan.total_samples, int(self.pack_threads)))
+        total, eb = plan.total_samples, stage.element_size()
+        # large batches go in a few groups of utterances: the H2D copy of one group runs while the next one is packed
+        groups = max(1, min(B, 4, (total * eb) >> 24))
+        bounds = [0]
+        for k in range(1, groups):
+            target = total * k // groups
+            i = bounds[-1]
+            while i < B and plan.offsets[i] < target:
+                i += 1
+            bounds.append(max(i, bounds[-1]))
+        bounds.append(B)
         with torch.cuda.device(self.device):
-            dev = stage[:plan.total_samples].to(self.device, non_blocking=True)
+            dev = torch.empty(total, dtype=self.in_dtype, device=self.device)
+            for k in range(groups):
+                a, b = bounds[k], bounds[k + 1]
+                if a == b:
+                    continue
+                lo = plan.offsets[a]
+                hi = plan.offsets[b] if b < B else total
+                ptrs = (C.c_void_p * (b - a))(*[w.data_ptr() for w in host[a:b]])
+                _lib.check(self.lib.lidfe_pack_host(stage.data_ptr() + lo * eb, ptrs, _ll_array([o - lo for o in plan.offsets[a:b]]),
+                                                    _ll_array(plan.lengths[a:b]), b - a, eb, hi - lo, int(self.pack_threads)))
+                dev[lo:hi].copy_(stage[lo:hi], non_blocking=True)
             if ev is not None:
                 ev.record(cur)
         return dev
 
-    pack_threads = 8      # host threads of the native packer (lidfe_pack_host)
+    # host threads of the native packer (lidfe_pack_host): up to 16, the host's cores shared between the local ranks
+    pack_threads = max(1, min(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
     def _staging(self, n: int):
         """One of two persistent pinned staging buffers of at least ``n`` elements, free for reuse (its last H2D copy

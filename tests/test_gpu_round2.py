@@ -216,6 +216,32 @@ def test_featurize_raw_fused_normalize(lid):
 
 
 @gpu
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.int16])
+def test_pack_paths_agree(lid, in_dtype):
+    """FrontEnd.pack: pageable sources (native threaded packer -> pinned staging, shipped in groups), pinned sources
+    (lidfe_h2d_gather, no staging) and device sources give the same packed buffer, gaps zero; repeated calls re-use the
+    two staging buffers without tearing (the ragged collate path, ref: lid/raw_datasets.py:345-351)."""
+    kw = dict(in_dtype=torch.int16, in_scale=1.0 / 32768) if in_dtype == torch.int16 else {}
+    f = lid.FrontEnd(**kw)
+    g = torch.Generator().manual_seed(21)
+    for rep, B in enumerate((3, 40, 200)):
+        lens = torch.randint(400, 200000 if B < 100 else 120000, (B,), generator=g).tolist()
+        wavs = [(torch.randn(n, generator=g) * 2000).to(in_dtype) for n in lens]
+        plan = f.make_plan(lens, padded=True)
+        want = torch.zeros(plan.total_samples, dtype=in_dtype)
+        for w, o, n in zip(wavs, plan.offsets, plan.lengths):
+            want[o:o + n] = w
+        a = f.pack(wavs, plan)
+        b = f.pack([w.pin_memory() for w in wavs], plan)
+        c = f.pack([w.cuda() for w in wavs], plan)
+        d = f.pack([w.unsqueeze(0) for w in wavs], plan)                  # (1, N): channel 0
+        torch.cuda.synchronize()
+        for name, got in (("pageable", a), ("pinned", b), ("device", c), ("2-d", d)):
+            assert torch.equal(got.cpu(), want), (name, rep)
+        plan.close()
+
+
+@gpu
 def test_plan_pool_serves_ragged_batches_without_allocating(lid):
     """a new length signature every step (ref: lid/raw_datasets.py:345-365) must not allocate once the
     pool is warm: plans take their device / pinned memory from the handle's pool."""
