@@ -95,18 +95,24 @@ def normalize_wav(wav: torch.Tensor):
 
 
 def _wave(fe: FrontEnd, wav: torch.Tensor, normalize=False, dither=0.0, noise=None, preemph=0.0):
-    if wav.dim() != 2 or wav.shape[0] != 1:
-        raise ValueError("expected a (1, T) waveform")
-    n = int(wav.shape[-1])
+    """(C, T) waveform through the wave-stage kernel; every channel is an utterance of its own, as the reference's
+    ``torch.std_mean(wav, dim=-1)`` / element-wise stages treat the rows (ref: lid/audio_processor.py:108-134)."""
+    if wav.dim() != 2 or wav.shape[0] < 1:
+        raise ValueError("expected a (C, T) waveform")
+    C, n = int(wav.shape[0]), int(wav.shape[-1])
+    if normalize and C > 1 and C != n:
+        # the reference subtracts a (C,) mean from a (C, T) tensor: only mono broadcasts (ref: lid/audio_processor.py:112-113)
+        raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (%d) at non-singleton dimension 1" % (n, C))
     if n < fe.frame_len:
+        # (the plan machinery is built around frames; the reference's element-wise stages would accept it)
         raise AssertionError("waveform shorter than one frame")
-    plan = fe.cached_plan([n], padded=False)
-    packed = fe.pack([wav.to(torch.float32)], plan)
+    plan = fe.cached_plan([n] * C, padded=False)
+    packed = fe.pack([wav[c].to(torch.float32) for c in range(C)], plan)
     nz = None
     if noise is not None:
-        nz = fe.pack([noise.to(torch.float32)], plan)
+        nz = fe.pack([noise[c].to(torch.float32) for c in range(C)], plan)
     out = fe.wave_stages(packed, plan, normalize=normalize, dither=dither, noise=nz, preemph=preemph)
-    out = out[:n].unsqueeze(0)
+    out = torch.stack([out[o:o + n] for o in plan.offsets], 0)
     return out if wav.is_cuda else out.cpu()
 
 

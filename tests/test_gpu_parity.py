@@ -394,6 +394,20 @@ def test_dropin_audio_processor(lid, golden_dir):
     b = O.spectrogram_augment(want, mask_times=2)
     assert torch.equal(a, b)
     assert ap.spectrogram_augment(want, mask_times=0) is want
+    # stereo input: dither + pre-emphasis are element-wise per channel; normalize_wav only broadcasts for mono, in the
+    # reference as here (ref: lid/audio_processor.py:112-113, 128-134)
+    st = torch.stack([x[0], 0.3 * x[0].flip(0) + 0.01], 0)
+    with pytest.raises(RuntimeError):
+        O.normalize_wav(st)
+    with pytest.raises(RuntimeError):
+        ap.normalize_wav(st)
+    torch.manual_seed(5)
+    a2, _ = ap.wav_augment(st.clone(), 16000)
+    torch.manual_seed(5)
+    w2 = st.clone()
+    w2 += 1e-5 * torch.rand_like(w2)
+    b2 = torch.cat((w2[:, 0].unsqueeze(1), w2[:, 1:] - 0.97 * w2[:, :-1]), dim=1)
+    assert torch.equal(a2, b2)
 
 
 def test_full_size_properties(fe, lid):
