@@ -16,6 +16,7 @@
 #include "../../include/lidfe.h"
 #include "lidfe_kernels.cuh"
 #include "lidfe_fbank_warp.cuh"
+#include "lidfe_resample_tc.cuh"
 
 using namespace lidfe;
 
@@ -1613,7 +1614,23 @@ struct lidfe_resampler_s {
   float* d_wt;                     // [K4][nw] transposed bank (FP32 kernel)
   int K8, KS, use_mma;             // tensor-core path (nw % 16 == 0): taps padded to 8, shared-memory row stride
   float* d_w;                      // [nw][K8] row-major bank (tensor-core kernel)
+  // tcgen05 path (lidfe_resample_tc.cuh): the bank as shared-memory images, one per (phase tile, 32-tap block, hi | lo)
+  int use_tc, tc_N, tc_tiles, tc_KB, tc_stages, tc_cols;
+  size_t tc_smem;
+  unsigned char* d_wimg;
 };
+
+// fp32 -> tf32, round to nearest with ties away from zero (what cvt.rna.tf32.f32 does), on the host
+static float tf32_rna_host(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return v;         // inf / nan
+  u += 0x1000u;
+  u &= 0xffffe000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
 
 int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, const float* kernel_host, int taps, int width) {
   if (!out || !kernel_host) return LIDFE_E_NULL;
@@ -1647,10 +1664,60 @@ int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, co
       e = cudaFuncSetAttribute(resample_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(static_cast<size_t>(kRmFrames) * r->KS * sizeof(float)));
   }
+  // tcgen05 path: phases in tiles of N (a multiple of 32 that divides nw, <= 256: 160 for both of the reference's rates)
+  r->use_tc = 0;
+  r->d_wimg = nullptr;
+  {
+    int N = 0;
+    for (int c = 256; c >= 32; c -= 32)
+      if (nw % c == 0) { N = c; break; }
+    const char* et = getenv("LIDFE_RESAMPLE_TC");
+    int dev = 0, cc_major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess && N > 0 && cc_major == 10 && !(et && et[0] == '0')) {
+      r->tc_N = N;
+      r->tc_tiles = nw / N;
+      r->tc_KB = (taps + kTcKB - 1) / kTcKB;
+      const size_t stage = 2 * static_cast<size_t>(kTcABytes) + 2 * static_cast<size_t>(N) * 128;
+      int stages = static_cast<int>((220 * 1024) / stage);
+      if (stages > 4) stages = 4;
+      if (stages > r->tc_KB) stages = r->tc_KB;
+      r->tc_stages = stages;
+      r->tc_cols = 32;
+      while (r->tc_cols < N) r->tc_cols <<= 1;
+      r->tc_smem = stages * stage + 1024 + (3 * static_cast<size_t>(stages) + 2) * 8;
+      if (stages >= 2) {
+        // image of (tile t, block kb, part h): row n (phase t N + n) holds taps 32 kb .. 32 kb + 31 in 128 bytes, its eight
+        // 16-byte chunks XOR-swizzled by n % 8 (the layout tcgen05.mma reads with a SWIZZLE_128B K-major descriptor)
+        const size_t img = static_cast<size_t>(N) * 128;
+        std::vector<float> buf(static_cast<size_t>(r->tc_tiles) * r->tc_KB * 2 * (img / 4), 0.f);
+        for (int t = 0; t < r->tc_tiles; ++t)
+          for (int kb = 0; kb < r->tc_KB; ++kb)
+            for (int n = 0; n < N; ++n)
+              for (int kk = 0; kk < kTcKB; ++kk) {
+                const int k = kb * kTcKB + kk;
+                const float w = (k < taps) ? kernel_host[static_cast<size_t>(t * N + n) * taps + k] : 0.f;
+                const float hi = tf32_rna_host(w), lo = w - hi;
+                const size_t off = (static_cast<size_t>(n) * 128 + ((((kk >> 2) ^ (n & 7)) << 4) | ((kk & 3) << 2))) / 4;
+                const size_t base = (static_cast<size_t>(t) * r->tc_KB + kb) * 2 * (img / 4);
+                buf[base + off] = hi;
+                buf[base + img / 4 + off] = lo;
+              }
+        float* dimg = nullptr;
+        e = upload(&dimg, buf.data(), buf.size());
+        r->d_wimg = reinterpret_cast<unsigned char*>(dimg);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(resample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(r->tc_smem));
+        r->use_tc = (e == cudaSuccess);
+      }
+    }
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
     cudaFree(r->d_wt);
     cudaFree(r->d_w);
+    cudaFree(r->d_wimg);
     delete r;
     return static_cast<int>(e);
   }
@@ -1662,6 +1729,7 @@ int lidfe_resampler_destroy(lidfe_resampler r) {
   if (!r) return LIDFE_E_NULL;
   cudaFree(r->d_wt);
   cudaFree(r->d_w);
+  cudaFree(r->d_wimg);
   delete r;
   return LIDFE_OK;
 }
@@ -1677,6 +1745,21 @@ int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long lon
   if (!r || !in_dev || !in_off_dev || !in_len_dev || !out_dev || !out_off_dev || !out_len_dev) return LIDFE_E_NULL;
   if (B <= 0 || max_out_len < 0) return LIDFE_E_ARG;
   if (max_out_len == 0) return LIDFE_OK;
+  if (r->use_tc) {
+    ResampleTcParams T;
+    T.in = in_dev; T.in_off = in_off_dev; T.in_len = in_len_dev;
+    T.out = out_dev; T.out_off = out_off_dev; T.out_len = out_len_dev;
+    T.wimg = r->d_wimg; T.orig = r->orig; T.nw = r->nw; T.K = r->K; T.KB = r->tc_KB; T.width = r->width;
+    T.N = r->tc_N; T.stages = r->tc_stages; T.tmem_cols = r->tc_cols;
+    const long long fr = (max_out_len + r->nw - 1) / r->nw;
+    const long long gxt = (fr + kTcM - 1) / kTcM;
+    if (gxt > 0x7fffffffLL || B > 65535 || r->tc_tiles > 65535) return LIDFE_E_ARG;
+    resample_tc_kernel<<<dim3(static_cast<unsigned>(gxt), static_cast<unsigned>(B), static_cast<unsigned>(r->tc_tiles)),
+                         kTcThreads, r->tc_smem, static_cast<cudaStream_t>(stream)>>>(T);
+    g_launches.fetch_add(1);
+    CU_TRY(cudaGetLastError());
+    return LIDFE_OK;
+  }
   if (r->use_mma) {
     ResampleMmaParams M;
     M.in = in_dev; M.in_off = in_off_dev; M.in_len = in_len_dev;
