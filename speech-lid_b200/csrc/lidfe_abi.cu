@@ -1615,7 +1615,7 @@ struct lidfe_resampler_s {
   int K8, KS, use_mma;             // tensor-core path (nw % 16 == 0): taps padded to 8, shared-memory row stride
   float* d_w;                      // [nw][K8] row-major bank (tensor-core kernel)
   // tcgen05 path (lidfe_resample_tc.cuh): the bank as shared-memory images, one per (phase tile, 32-tap block, hi | lo)
-  int use_tc, tc_N, tc_tiles, tc_KB, tc_stages, tc_cols;
+  int use_tc, tc_N, tc_tiles, tc_KB, tc_stages, tc_cols, tc_dbg;
   size_t tc_smem;
   unsigned char* d_wimg;
 };
@@ -1666,6 +1666,7 @@ int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, co
   }
   // tcgen05 path: phases in tiles of N (a multiple of 32 that divides nw, <= 256: 160 for both of the reference's rates)
   r->use_tc = 0;
+  r->tc_dbg = getenv("LIDFE_TC_DBG") != nullptr;      // development: per-role cycle counters of CTA 0 on stderr (synchronises)
   r->d_wimg = nullptr;
   {
     int N = 0;
@@ -1685,9 +1686,10 @@ int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, co
       if (stages > r->tc_KB) stages = r->tc_KB;
       r->tc_stages = stages;
       r->tc_cols = 32;
-      while (r->tc_cols < N) r->tc_cols <<= 1;
-      r->tc_smem = stages * stage + 1024 + (3 * static_cast<size_t>(stages) + 2) * 8;
-      if (stages >= 2) {
+      while (r->tc_cols < 2 * N) r->tc_cols <<= 1;            // two accumulator buffers of tc_cols / 2 >= N columns each
+      if (r->tc_cols / 2 < N) r->tc_cols = 0;
+      r->tc_smem = stages * stage + 1024 + (3 * static_cast<size_t>(stages) + 5) * 8;
+      if (stages >= 2 && r->tc_cols >= 32 && r->tc_cols <= 512 && r->tc_KB >= 2) {
         // image of (tile t, block kb, part h): row n (phase t N + n) holds taps 32 kb .. 32 kb + 31 in 128 bytes, its eight
         // 16-byte chunks XOR-swizzled by n % 8 (the layout tcgen05.mma reads with a SWIZZLE_128B K-major descriptor)
         const size_t img = static_cast<size_t>(N) * 128;
@@ -1754,10 +1756,28 @@ int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long lon
     const long long fr = (max_out_len + r->nw - 1) / r->nw;
     const long long gxt = (fr + kTcM - 1) / kTcM;
     if (gxt > 0x7fffffffLL || B > 65535 || r->tc_tiles > 65535) return LIDFE_E_ARG;
-    resample_tc_kernel<<<dim3(static_cast<unsigned>(gxt), static_cast<unsigned>(B), static_cast<unsigned>(r->tc_tiles)),
-                         kTcThreads, r->tc_smem, static_cast<cudaStream_t>(stream)>>>(T);
+    T.gx = static_cast<int>(gxt); T.B = B; T.n_tiles = r->tc_tiles;
+    T.dbg = nullptr;
+    static long long* g_tc_dbg = nullptr;
+    if (r->tc_dbg) {
+      if (!g_tc_dbg) { cudaMalloc(reinterpret_cast<void**>(&g_tc_dbg), 16 * 8); cudaMemset(g_tc_dbg, 0, 16 * 8); }
+      T.dbg = g_tc_dbg;
+    }
+    const long long n_lin = gxt * B * r->tc_tiles;
+    int dev = 0, sms = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long grid = n_lin < sms ? n_lin : sms;         // persistent: one CTA per SM walks the tiles
+    resample_tc_kernel<<<static_cast<unsigned>(grid), kTcThreads, r->tc_smem, static_cast<cudaStream_t>(stream)>>>(T);
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
+    if (T.dbg) {
+      long long h[16];
+      cudaDeviceSynchronize();
+      cudaMemcpy(h, T.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[tc dbg] CTA0: mma lane total %lld cyc, wait A %lld, wait B %lld, wait acc_empty %lld, issue %lld, tiles %lld | builder w4: wait empty %lld, publish %lld | w8: wait empty %lld, publish %lld | w4 load-wait %lld, stores %lld\n",
+              h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[9], h[10], h[11], h[12], h[13]);
+    }
     return LIDFE_OK;
   }
   if (r->use_mma) {
