@@ -68,6 +68,20 @@ def fe(lid):
     return lid.FrontEnd(n_mels=80)
 
 
+def _fresh(ctor, env, *args, **kw):
+    """An object created under temporary environment switches (they are read once, at creation)."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return ctor(*args, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _fresh_frontend(lid, env, **kw):
     """A FrontEnd created under temporary environment switches (they are read once, at lidfe_create)."""
     old = {k: os.environ.get(k) for k in env}
@@ -213,6 +227,37 @@ def test_featurize_raw_fused_normalize(lid):
         want = O.kaldi_fbank(O.normalize_wav(w.float().unsqueeze(0) * (1.0 / 32768.0)))
         got = fused[i, :want.shape[0]].cpu()
         assert float((got - want).abs().max() / want.abs().max()) <= 3e-4, i
+
+
+@gpu
+@pytest.mark.parametrize("orig", [44100, 22050])
+def test_resampler_kernels_agree_tcgen05_mma_fp32(lid, orig):
+    """Row f4: the three kernels behind lidfe_resample -- resample_tc_kernel (tcgen05 + TMEM, 3 x TF32, the default on
+    sm_100), resample_mma_kernel (mma.sync 3 x TF32) and the FP32 resample_kernel -- against an fp64 evaluation of the same
+    polyphase sum with the same fp32 FIR bank (ta: functional/functional.py _apply_sinc_resample_kernel), on ragged
+    utterances: shorter than one tile, one sample, exact multiples of the period, several 128-frame tiles (the persistent
+    CTA walks them through both TMEM accumulator buffers and wraps the 3-stage pipeline many times)."""
+    import math
+    g = torch.Generator().manual_seed(orig)
+    lens = [int(orig * s) for s in (0.05, 0.31, 1.0, 2.57, 0.011, 6.3)] + [441, 1, 44101, 441 * 128, 441 * 128 + 1]
+    wavs = [torch.randn(n, generator=g) for n in lens]
+    outs = {}
+    for kind in ("tc", "mma", "fp32"):
+        rs = _fresh(lid.Resampler, {"LIDFE_RESAMPLE_TC": "1" if kind == "tc" else "0",
+                                    "LIDFE_RESAMPLE_MMA": "0" if kind == "fp32" else "1"}, orig, 16000)
+        gg = math.gcd(rs.orig_freq, rs.new_freq)
+        o_red = rs.orig_freq // gg
+        k64 = rs.kernel.double()
+        res = rs.resample_list([w.cuda() for w in wavs])
+        torch.cuda.synchronize()
+        for w, o in zip(wavs, res):
+            x = torch.nn.functional.pad(w.double(), (rs.width, rs.width + o_red))
+            want = (x.unfold(0, k64.shape[1], o_red) @ k64.T).reshape(-1)[:rs.out_len(w.numel())]
+            assert o.numel() == want.numel(), (kind, w.numel())
+            assert float((o.double().cpu() - want).abs().max()) <= 1e-5, (kind, w.numel())
+        outs[kind] = [o.cpu() for o in res]
+    for a, b in zip(outs["tc"], outs["mma"]):          # same decomposition, same split: equal to accumulation order
+        assert float((a - b).abs().max()) <= 2e-6
 
 
 @gpu
