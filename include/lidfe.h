@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LIDFE_ABI_VERSION 6
+#define LIDFE_ABI_VERSION 7
 
 /* error codes (negative) */
 #define LIDFE_OK 0
@@ -279,6 +279,20 @@ long long lidfe_resample_out_len(lidfe_resampler r, long long n_in);
 int lidfe_resample(lidfe_resampler r, int B, const float* in_dev, const long long* in_off_dev, const long long* in_len_dev,
                    float* out_dev, const long long* out_off_dev, const long long* out_len_dev, long long max_out_len,
                    void* stream);
+
+/* -- the wav2vec-exp FBank variant (ref: wav2vec-exp/s3prl_model.py:174-204) --------------------------------------------
+ * lidfe_wgemm_create: the resampler kernels as a general windowed GEMM,
+ *     out[f * n_rows + p] = sum_k bank_host[p][k] * xpad[f * hop - left_pad + k]     (n_rows even, run with lidfe_resample,
+ *     out_len = frames * n_rows).  The FBank variant passes a windowed DFT basis: row 2 b = w[k] cos(2 pi b k / n_fft),
+ *     row 2 b + 1 = -w[k] sin(...), hop = n_fft / 2, left_pad 0 (torch.stft center=False), rows padded with zeros to a
+ *     count the tensor-core kernel tiles (speech_lid_b200.S3prlFBank does this).
+ * lidfe_stft_mel_db: rows of that GEMM -> |X|^2 -> mel (melT_dev[n_mels][n_bins], non-zero range mel_lo/mel_hi per filter:
+ *     F.melscale_fbanks transposed) -> 10 log10(max(., amin)) into out_dev[(out_row[i] + t) * n_mels + m]; normalize != 0:
+ *     then (x - mean) / (std + 1e-9) with one mean / unbiased std per utterance (stats_dev[B][2] is workspace). */
+int lidfe_wgemm_create(lidfe_resampler* out, int hop, int n_rows, const float* bank_host, int taps, int left_pad);
+int lidfe_stft_mel_db(const float* g_dev, const long long* g_off_dev, const long long* frames_dev, int B, long long max_frames,
+                      int nw, const float* melT_dev, const int* mel_lo_dev, const int* mel_hi_dev, int n_bins, int n_mels,
+                      float amin, float* out_dev, const long long* out_row_dev, double* stats_dev, int normalize, void* stream);
 
 /* FP32 ceiling of the device, measured: a dependent-free FFMA loop on every SM for about `ms_budget` milliseconds.
  * Writes the achieved TFLOP/s (2 flops per FFMA) -- bench.py reports the kernel against this, not against a data sheet. */

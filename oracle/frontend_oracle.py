@@ -428,3 +428,30 @@ def data_processor(x: Sequence[torch.Tensor], sample_rate: int) -> Sequence[torc
     y = resample(padded, sample_rate, 16000)
     lens = [int(p * y.shape[-1]) for p in percent]
     return [y[i, :lens[i]] for i in range(len(lens))]
+
+
+# --------------------------------------------------------------------------------------
+# f4b  the wav2vec-exp FBank variant                      ref: wav2vec-exp/s3prl_model.py:174-204
+#      F.spectrogram(pad=0, hann_window(n_fft), n_fft, hop=n_fft//2, win=n_fft, power=2, center=False)
+#      -> HTK mel (f_max 8000, norm=None) -> amplitude_to_DB(10, amin=1e-10, db_multiplier=0, top_db=None)
+#      -> (spec - mean) / (std + 1e-9) with ONE mean / unbiased std over the whole (n_mels, T) spectrogram
+#      ta: functional/functional.py:54-146 (spectrogram), :356-403 (amplitude_to_DB), :492-588 (melscale_fbanks)
+# --------------------------------------------------------------------------------------
+def s3prl_fbank_num_frames(num_samples: int, n_fft: int = 640) -> int:
+    """torch.stft(center=False): 1 + (N - n_fft) // hop, hop = n_fft // 2"""
+    return 1 + (num_samples - n_fft) // (n_fft // 2) if num_samples >= n_fft else 0
+
+
+def s3prl_fbank(x: torch.Tensor, fbank_size: int = 80, n_fft: int = 640, normalize: bool = True) -> torch.Tensor:
+    """(T,) -> (fbank_size, frames), as ``FBank.forward`` (ref: wav2vec-exp/s3prl_model.py:181-204)."""
+    fb = htk_mel_fbanks(n_fft // 2 + 1, 0.0, 8000.0, fbank_size, 16000)
+    window = torch.hann_window(n_fft)
+    spec = torch.stft(input=x.reshape(-1, x.shape[-1]), n_fft=n_fft, hop_length=n_fft // 2, win_length=n_fft, window=window,
+                      center=False, pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    spec = spec.reshape(x.shape[:-1] + spec.shape[-2:]).abs().pow(2.0).float()     # (n_fft/2+1, T)
+    spec = torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2).float()
+    spec = (10.0 * torch.log10(torch.clamp(spec, min=1e-10))).float()
+    if not normalize:
+        return spec
+    std, mean = torch.std_mean(spec)
+    return (spec - mean) / (std + 1e-9)

@@ -9,8 +9,9 @@ from ._lib import LIB_PATH, LidfeError, load_library
 from .collate import DeviceCollate, collate_host_part
 from .frontend import FrontEnd, Plan
 from .resample import Resampler
+from .s3prl_fbank import S3prlFBank
 from .sharding import allreduce_stats, finalize_stats, lpt_partition
 from .specaug import draw_masks
 
-__all__ = ["FrontEnd", "Plan", "DeviceCollate", "collate_host_part", "Resampler", "draw_masks", "lpt_partition", "allreduce_stats", "finalize_stats",
+__all__ = ["FrontEnd", "Plan", "DeviceCollate", "collate_host_part", "Resampler", "S3prlFBank", "draw_masks", "lpt_partition", "allreduce_stats", "finalize_stats",
            "load_library", "LidfeError", "LIB_PATH", "tables"]

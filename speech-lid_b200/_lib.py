@@ -18,7 +18,7 @@ IN_F32, IN_I16 = 0, 1
 CMVN_NONE, CMVN_PER_UTT, CMVN_APPLY_GLOBAL, CMVN_ACCUM_GLOBAL, POST_TOPDB = 0, 1, 2, 3, 4
 FRAMING_KALDI, FRAMING_CENTER = 0, 1
 LOG_NATURAL, LOG_DB10 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 WINDOW_POVEY, WINDOW_HANNING, WINDOW_HAMMING, WINDOW_RECTANGULAR, WINDOW_BLACKMAN, WINDOW_HANN_PERIODIC = 0, 1, 2, 3, 4, 5
 
 EXPORTS = (
@@ -27,7 +27,7 @@ EXPORTS = (
     "lidfe_featurize", "lidfe_cmvn_apply", "lidfe_wave_stages", "lidfe_wave_stages_i16", "lidfe_mask_apply", "lidfe_strerror",
     "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_profile_set_stride", "lidfe_mel_plan", "lidfe_mel_plan_expand",
     "lidfe_resampler_create", "lidfe_resampler_destroy", "lidfe_resample_out_len", "lidfe_resample",
-    "lidfe_plan_create_async", "lidfe_plan_num_spans", "lidfe_featurize_raw", "lidfe_fp32_probe", "lidfe_pool_stats", "lidfe_pack_host", "lidfe_h2d_gather",
+    "lidfe_plan_create_async", "lidfe_plan_num_spans", "lidfe_featurize_raw", "lidfe_fp32_probe", "lidfe_pool_stats", "lidfe_pack_host", "lidfe_h2d_gather", "lidfe_wgemm_create", "lidfe_stft_mel_db",
 )
 
 
@@ -93,6 +93,10 @@ def load_library() -> C.CDLL:
     lib.lidfe_pack_host.restype = i32
     lib.lidfe_h2d_gather.argtypes = [vp, C.POINTER(vp), pll, pll, i32, i32, vp]
     lib.lidfe_h2d_gather.restype = i32
+    lib.lidfe_wgemm_create.argtypes = [C.POINTER(vp), i32, i32, vp, i32, i32]
+    lib.lidfe_wgemm_create.restype = i32
+    lib.lidfe_stft_mel_db.argtypes = [vp, vp, vp, i32, ll, i32, vp, vp, vp, i32, i32, f32, vp, vp, vp, i32, vp]
+    lib.lidfe_stft_mel_db.restype = i32
     lib.lidfe_cmvn_apply.argtypes = [vp, vp, vp, ll, vp, i32, vp, vp]
     lib.lidfe_cmvn_apply.restype = i32
     lib.lidfe_mask_apply.argtypes = [vp, vp, vp, ll, vp, i32, vp]

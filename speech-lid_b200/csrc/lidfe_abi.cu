@@ -17,6 +17,7 @@
 #include "lidfe_kernels.cuh"
 #include "lidfe_fbank_warp.cuh"
 #include "lidfe_resample_tc.cuh"
+#include "lidfe_stft_fbank.cuh"
 
 using namespace lidfe;
 
@@ -448,6 +449,38 @@ int lidfe_h2d_gather(void* dst_dev, const void* const* src_host, const long long
     if (lengths[i] == 0) continue;
     CU_TRY(cudaMemcpyAsync(dst + offsets[i] * elem_bytes, src_host[i], static_cast<size_t>(lengths[i]) * elem_bytes,
                            cudaMemcpyHostToDevice, st));
+  }
+  return LIDFE_OK;
+}
+
+int lidfe_stft_mel_db(const float* g_dev, const long long* g_off_dev, const long long* frames_dev, int B, long long max_frames,
+                      int nw, const float* melT_dev, const int* mel_lo_dev, const int* mel_hi_dev, int n_bins, int n_mels,
+                      float amin, float* out_dev, const long long* out_row_dev, double* stats_dev, int normalize, void* stream) {
+  if (!g_dev || !g_off_dev || !frames_dev || !melT_dev || !mel_lo_dev || !mel_hi_dev || !out_dev || !out_row_dev || !stats_dev)
+    return LIDFE_E_NULL;
+  if (B <= 0 || B > 65535 || max_frames < 0 || nw < 2 * n_bins || (nw & 1) || n_bins < 2 || n_bins > kSfMaxBins || n_mels < 1)
+    return LIDFE_E_ARG;
+  if (max_frames == 0) return LIDFE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU_TRY(cudaMemsetAsync(stats_dev, 0, static_cast<size_t>(B) * 2 * sizeof(double), st));
+  StftMelParams M;
+  M.g = g_dev; M.g_off = g_off_dev; M.frames = frames_dev; M.out = out_dev; M.out_row = out_row_dev;
+  M.melT = melT_dev; M.mel_lo = mel_lo_dev; M.mel_hi = mel_hi_dev; M.stats = stats_dev;
+  M.nw = nw; M.n_bins = n_bins; M.n_mels = n_mels; M.amin = amin;
+  const long long gx = (max_frames + kSfWarps - 1) / kSfWarps;
+  if (gx > 0x7fffffffLL) return LIDFE_E_ARG;
+  stft_mel_db_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(B)), kSfWarps * 32, 0, st>>>(M);
+  g_launches.fetch_add(1);
+  CU_TRY(cudaGetLastError());
+  if (normalize) {
+    ScalarNormParams N;
+    N.out = out_dev; N.out_row = out_row_dev; N.frames = frames_dev; N.stats = stats_dev; N.n_mels = n_mels;
+    long long chunks = (max_frames * n_mels + 256 * 8 - 1) / (256 * 8);
+    if (chunks < 1) chunks = 1;
+    if (chunks > 4096) chunks = 4096;
+    scalar_norm_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(B)), 256, 0, st>>>(N);
+    g_launches.fetch_add(1);
+    CU_TRY(cudaGetLastError());
   }
   return LIDFE_OK;
 }
@@ -1632,6 +1665,8 @@ static float tf32_rna_host(float v) {
   return r;
 }
 
+static int create_bank(lidfe_resampler* out, int orig, int nw, const float* kernel_host, int taps, int width);
+
 int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, const float* kernel_host, int taps, int width) {
   if (!out || !kernel_host) return LIDFE_E_NULL;
   *out = nullptr;
@@ -1640,6 +1675,19 @@ int lidfe_resampler_create(lidfe_resampler* out, int orig_freq, int new_freq, co
   while (b) { const int t = a % b; a = b; b = t; }
   const int orig = orig_freq / a, nw = new_freq / a;
   if (taps != 2 * width + orig) return LIDFE_E_ARG;     // ta: functional/functional.py _get_sinc_resample_kernel
+  return create_bank(out, orig, nw, kernel_host, taps, width);
+}
+
+// The resampler kernels are a windowed GEMM -- out[f * n_rows + p] = sum_k bank[p][k] * xpad[f * hop - left_pad + k] --
+// and any bank can be run through them: the wav2vec-exp FBank variant uses a windowed DFT basis (lidfe_stft_fbank.cuh).
+int lidfe_wgemm_create(lidfe_resampler* out, int hop, int n_rows, const float* bank_host, int taps, int left_pad) {
+  if (!out || !bank_host) return LIDFE_E_NULL;
+  *out = nullptr;
+  if (hop <= 0 || n_rows <= 0 || taps <= 0 || left_pad < 0 || taps > 8192 || (n_rows & 1)) return LIDFE_E_ARG;
+  return create_bank(out, hop, n_rows, bank_host, taps, left_pad);
+}
+
+static int create_bank(lidfe_resampler* out, int orig, int nw, const float* kernel_host, int taps, int width) {
   lidfe_resampler_s* r = new (std::nothrow) lidfe_resampler_s();
   if (!r) return LIDFE_E_NOMEM;
   r->orig = orig; r->nw = nw; r->K = taps; r->K4 = (taps + 3) & ~3; r->width = width; r->d_wt = nullptr;

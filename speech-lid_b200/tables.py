@@ -132,3 +132,23 @@ def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: in
     kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
     kernels *= window * scale
     return kernels.to(dtype=torch.float32)[:, 0, :].contiguous(), width
+
+
+def windowed_dft_bank(n_fft: int):
+    """The wav2vec-exp FBank's transform as a GEMM bank: rows 2 b / 2 b + 1 are hann(n_fft)[k] * cos / -sin(2 pi b k / n_fft),
+    b = 0 .. n_fft / 2 (ref: wav2vec-exp/s3prl_model.py:192-196: F.spectrogram with torch.hann_window(n_fft), periodic).
+    Built in float64 and rounded once.  The row count is padded with zero rows to what the tensor-core kernel tiles:
+    a multiple of 32 with a divisor that is a multiple of 32 in [128, 256] (or the count itself when <= 256)."""
+    n_bins = n_fft // 2 + 1
+    k = torch.arange(n_fft, dtype=torch.float64)
+    w = torch.hann_window(n_fft, dtype=torch.float64)
+    b = torch.arange(n_bins, dtype=torch.float64).unsqueeze(1)
+    ang = 2.0 * math.pi * torch.remainder(b * k, float(n_fft)) / n_fft
+    rows = torch.stack([w * torch.cos(ang), -w * torch.sin(ang)], 1).reshape(2 * n_bins, n_fft)
+    need = 2 * n_bins
+    nw = (need + 31) // 32 * 32
+    while nw > 256 and not any(nw % c == 0 for c in range(128, 257, 32)):
+        nw += 32
+    bank = torch.zeros((nw, n_fft), dtype=torch.float32)
+    bank[:need] = rows.to(torch.float32)
+    return bank.contiguous(), nw

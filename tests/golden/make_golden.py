@@ -133,6 +133,22 @@ def main():
             rs["out_%d_%d" % (rate, i)] = y.numpy()
     np.savez_compressed(os.path.join(HERE, "resample.npz"), **rs)
 
+    # ---- the wav2vec-exp FBank variant (row f4): the reference's own class, cut out of its module by name (importing
+    #      wav2vec-exp/s3prl_model.py whole pulls in s3prl and fairseq, which are not installed) ---------------------------
+    import ast
+    src = open("/root/reference/wav2vec-exp/s3prl_model.py").read()
+    node = [n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "FBank"][0]
+    ns = {"torch": torch, "nn": torch.nn}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "wav2vec-exp/s3prl_model.py", "exec"), ns)
+    FBank = ns["FBank"]
+    fbk = {}
+    for name, n_fft, n in (("a", 640, 640), ("b", 640, 16000), ("c", 640, 48017), ("d", 320, 8000), ("e", 640, 959)):
+        xw = O.synth_noise(n, 900 + n) if name != "c" else O.synth_speechlike(n, 901)
+        fbk["in_" + name] = xw.numpy()
+        fbk["nfft_" + name] = np.int64(n_fft)
+        fbk["out_" + name] = FBank(80, n_fft)(xw).numpy()
+    np.savez_compressed(os.path.join(HERE, "s3prl_fbank.npz"), **fbk)
+
     with open(os.path.join(HERE, "VERSIONS.txt"), "w") as f:
         f.write("generated by tests/golden/make_golden.py from /root/reference (kouyt5/speech-lid)\n")
         for k, v in meta.items():

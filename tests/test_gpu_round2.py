@@ -230,6 +230,39 @@ def test_featurize_raw_fused_normalize(lid):
 
 
 @gpu
+def test_s3prl_fbank_variant_matches_reference_module(lid):
+    """Row f4: speech_lid_b200.S3prlFBank (windowed-DFT GEMM on the tensor cores + mel / dB / scalar normalisation)
+    against outputs of the reference's own FBank class (ref: wav2vec-exp/s3prl_model.py:174-204) and, on a ragged batch,
+    against the oracle.  Tolerance: 1e-4 of the feature range (the values are (x - mean) / std of a dB spectrogram)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "s3prl_fbank.npz"))
+    mods = {}
+    for k in "abcde":
+        n_fft = int(z["nfft_" + k])
+        fb = mods.setdefault(n_fft, lid.S3prlFBank(80, n_fft))
+        x = torch.from_numpy(z["in_" + k]).reshape(-1)
+        want = torch.from_numpy(z["out_" + k])
+        got = fb(x)
+        assert got.shape == want.shape and got.device.type == "cpu", (k, got.shape, want.shape)
+        if want.shape[-1] > 1:
+            assert float((got - want).abs().max() / want.abs().max()) <= 1e-4, k
+        assert fb(x.cuda()).is_cuda
+    g = torch.Generator().manual_seed(4)
+    wavs = [torch.randn(n, generator=g) for n in (640, 641, 16000, 40017, 959, 128 * 320 + 640, 3200)]
+    fb = mods[640]
+    outs = fb.forward_list([w.cuda() for w in wavs])
+    raw = fb.forward_list([w.cuda() for w in wavs], normalize=False)
+    for w, o, r in zip(wavs, outs, raw):
+        want = O.s3prl_fbank(w, 80, 640)[0].T if O.s3prl_fbank(w, 80, 640).dim() == 3 else O.s3prl_fbank(w, 80, 640).T
+        want_raw = O.s3prl_fbank(w, 80, 640, normalize=False)
+        want_raw = (want_raw[0] if want_raw.dim() == 3 else want_raw).T
+        assert o.shape == want.shape == (fb.num_frames(w.numel()), 80)
+        assert float((r.cpu() - want_raw).abs().max() / want_raw.abs().max()) <= 1e-4, w.numel()
+        assert float((o.cpu() - want).abs().max() / want.abs().max()) <= 1e-4, w.numel()
+    with pytest.raises(RuntimeError):
+        fb.forward_list([torch.randn(639)])
+
+
+@gpu
 @pytest.mark.parametrize("orig", [44100, 22050])
 def test_resampler_kernels_agree_tcgen05_mma_fp32(lid, orig):
     """Row f4: the three kernels behind lidfe_resample -- resample_tc_kernel (tcgen05 + TMEM, 3 x TF32, the default on

@@ -160,3 +160,16 @@ def test_oracle_data_processor_matches_reference_resampling(golden_dir):
             assert torch.allclose(ys[i], want, rtol=0, atol=1e-6), (rate, i, (ys[i] - want).abs().max())
     x = torch.randn(2, 3000)
     assert torch.equal(O.data_processor([x[0], x[1]], 16000)[0], x[0])         # other rates pass through untouched
+
+
+def test_oracle_s3prl_fbank_matches_reference_module(golden_dir):
+    """Row f4: the wav2vec-exp FBank variant (ref: wav2vec-exp/s3prl_model.py:174-204).  The fixtures are outputs of the
+    reference's own class (tests/golden/make_golden.py cuts it out of its module by name); the restatement is bit-equal."""
+    z = np.load(os.path.join(golden_dir, "s3prl_fbank.npz"))
+    for k in "abcde":
+        x = torch.from_numpy(z["in_" + k])
+        want = torch.from_numpy(z["out_" + k])
+        n_fft = int(z["nfft_" + k])
+        got = O.s3prl_fbank(x, 80, n_fft)
+        assert got.shape == want.shape and got.shape[-1] == O.s3prl_fbank_num_frames(x.shape[-1], n_fft)
+        assert torch.equal(got, want), k
