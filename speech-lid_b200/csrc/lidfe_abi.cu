@@ -143,13 +143,15 @@ static cudaError_t upload(T** dst, const T* src, size_t n) {
 }
 
 typedef void (*fbank_fn)(const FbankParams);
-static fbank_fn pick_warp_kernel(int in_dtype, int std_mel, bool stats) {
-  if (in_dtype == LIDFE_IN_I16) {
-    if (stats) return std_mel == 1 ? fbank_warp_kernel<short, 1, true> : fbank_warp_kernel<short, 0, true>;
-    return std_mel == 1 ? fbank_warp_kernel<short, 1, false> : fbank_warp_kernel<short, 0, false>;
-  }
-  if (stats) return std_mel == 1 ? fbank_warp_kernel<float, 1, true> : fbank_warp_kernel<float, 0, true>;
-  return std_mel == 1 ? fbank_warp_kernel<float, 1, false> : fbank_warp_kernel<float, 0, false>;
+// stats: 0 = none, 1 = sums (per-utterance / global CMVN), 2 = extrema (AmplitudeToDB top_db)
+template <typename TIn>
+static fbank_fn pick_warp_kernel_t(int std_mel, int stats) {
+  if (std_mel == 2) return stats == 2 ? fbank_warp_kernel<TIn, 2, 2> : stats == 1 ? fbank_warp_kernel<TIn, 2, 1> : fbank_warp_kernel<TIn, 2, 0>;
+  if (std_mel == 1) return stats == 1 ? fbank_warp_kernel<TIn, 1, 1> : fbank_warp_kernel<TIn, 1, 0>;
+  return stats == 1 ? fbank_warp_kernel<TIn, 0, 1> : fbank_warp_kernel<TIn, 0, 0>;
+}
+static fbank_fn pick_warp_kernel(int in_dtype, int std_mel, int stats) {
+  return in_dtype == LIDFE_IN_I16 ? pick_warp_kernel_t<short>(std_mel, stats) : pick_warp_kernel_t<float>(std_mel, stats);
 }
 template <typename TIn>
 static fbank_fn pick_kernel_t(bool mfcc, int std_mel) {
@@ -707,7 +709,10 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
     }
   }
   // warp-autonomous kernel: KALDI framing without in-kernel dither; the HTK / CENTER variant (std_mel 2) stays with fbank_kernel
-  c->warp_ok = (cfg->framing == LIDFE_FRAMING_KALDI && cfg->dither == 0.f && c->std_mel != 2) ? 1 : 0;
+  // ... and the reference's default branch as a whole (CENTER framing + HTK-80 bank + window-only framing, pad a multiple
+  // of 4 samples so that interior quads stay 16-byte aligned)
+  c->warp_ok = ((cfg->framing == LIDFE_FRAMING_KALDI && cfg->dither == 0.f && c->std_mel != 2) ||
+                (cfg->framing == LIDFE_FRAMING_CENTER && cfg->dither == 0.f && c->std_mel == 2 && cfg->pad % 4 == 0 && cfg->n_ceps == 0)) ? 1 : 0;
   if (const char* env = getenv("LIDFE_WARP_KERNEL")) c->warp_ok = c->warp_ok && atoi(env) != 0;
   c->w_static_pct = 90;
   c->w_pool_quads = 1;
@@ -721,10 +726,10 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
     c->w_tab_bytes = static_cast<int>((kWTabOff + c->blob_bytes_fbank + kMaxMels * 8 + 127) / 128 * 128);
     const size_t per_warp = (cfg->in_dtype == LIDFE_IN_I16) ? WarpLayout<short>::kWarpBytes : WarpLayout<float>::kWarpBytes;
     c->w_smem = static_cast<size_t>(c->w_tab_bytes) + kWWarps * per_warp;
-    fbank_fn wf = pick_warp_kernel(cfg->in_dtype, c->std_mel, true);
+    fbank_fn wf = pick_warp_kernel(cfg->in_dtype, c->std_mel, 1);
     e = cudaFuncSetAttribute(wf, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->w_smem));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(pick_warp_kernel(cfg->in_dtype, c->std_mel, false), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    for (int sk = 0; sk <= 2 && e == cudaSuccess; sk += 2)
+      e = cudaFuncSetAttribute(pick_warp_kernel(cfg->in_dtype, c->std_mel, sk), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(c->w_smem));
     if (e == cudaSuccess) {
       int per_sm = 0;
@@ -886,6 +891,7 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
   if (B <= 0) return LIDFE_E_ARG;
   const size_t in_elt = (h->cfg.in_dtype == LIDFE_IN_I16) ? 2 : 4;
   const bool center = h->cfg.framing == LIDFE_FRAMING_CENTER;
+  const long long cpad_w = h->cfg.pad;
   const bool need_tiles = h->cfg.n_ceps > 0 && h->cfg.n_ceps <= kDctMaxCeps && h->cfg.n_mels % 4 == 0;   // mfcc_dct_kernel's table
   std::vector<long long> frames(B), utt_first_tile(B);
   long long total = 0, n_tiles = 0, max_frames = 0;
@@ -1015,15 +1021,39 @@ int lidfe_plan_create_async(lidfe_handle h, lidfe_plan* out, int B, const long l
     const long long s_run = (n_quads * h->w_static_pct) / (100 * W);          // static quads per warp
     const long long static_quads = s_run * W;
     std::vector<Span> pool;
-    auto push_frames = [&](std::vector<Span>& dst, int i, long long f, long long nf) {
+    // CENTER framing: frame f covers p[160 f - 200, 160 f + 200) of the constant-padded signal (see the span builder above);
+    // a run is cut so that the quads that touch the padding / the reflection -- the first quad of an utterance and its last
+    // one or two -- are spans of their own with aux = 0 (staged element by element), everything else stays on TMA
+    auto push_one = [&](std::vector<Span>& dst, int i, long long f, long long nf, int aux) {
       Span sp;
-      sp.wav_off = wav_offsets_host[i] + f * kFrameShift;
+      sp.wav_off = wav_offsets_host[i] + (center ? f * kFrameShift - kFrameLen / 2 - cpad_w : f * kFrameShift);
       sp.out_row = out_rows_host[i] + f;
       sp.nframes = static_cast<int>(nf);
       sp.utt = i;
       sp.t0 = static_cast<int>(f);
-      sp.aux = 1;
+      sp.aux = aux;
       dst.push_back(sp);
+    };
+    auto push_frames = [&](std::vector<Span>& dst, int i, long long f, long long nf) {
+      if (!center) {
+        push_one(dst, i, f, nf, 1);
+        return;
+      }
+      const long long N = wav_lengths_host[i];
+      auto interior = [&](long long q0) {          // quad starting at frame q0 (<= 4 frames, never past the utterance's last)
+        const long long fr = (frames[i] - q0) < kQuadFrames ? (frames[i] - q0) : kQuadFrames;
+        const long long rel = q0 * kFrameShift - kFrameLen / 2 - cpad_w;
+        return rel >= 0 && rel + fr * kFrameShift + (kFrameLen - kFrameShift) <= N;
+      };
+      long long g = f;
+      while (g < f + nf) {                          // maximal runs of quads of one kind
+        const bool in0 = interior(g);
+        long long e = g + kQuadFrames;
+        while (e < f + nf && interior(e) == in0) e += kQuadFrames;
+        if (e > f + nf) e = f + nf;
+        push_one(dst, i, g, e - g, in0 ? 1 : 0);
+        g = e;
+      }
     };
     if (pad_rows_host) {
       for (int i = 0; i < B; ++i) {
@@ -1358,7 +1388,8 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
   P.utt_stats = p->d_utt_stats;
 
   // the warp-autonomous kernel takes every call inside its scope (see lidfe_fbank_warp.cuh)
-  const bool use_warp = h->warp_ok && !raw && p->d_wspans != nullptr && !h->fused_apply && cmvn_mode != LIDFE_POST_TOPDB;
+  const bool use_warp = h->warp_ok && !raw && p->d_wspans != nullptr && !h->fused_apply &&
+                        (cmvn_mode != LIDFE_POST_TOPDB || h->std_mel == 2);
   auto launch_warp = [&](FbankParams& F, bool profile) -> int {
     F.wspans = p->d_wspans;
     F.n_wspans = static_cast<int>(p->n_wspans);
@@ -1369,7 +1400,8 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     if (grid_w < 1) grid_w = 1;
     F.w_first = p->d_w_first;
     F.n_wstatic = p->n_wstatic;
-    fbank_fn wf = pick_warp_kernel(h->cfg.in_dtype, h->std_mel, F.mode == LIDFE_CMVN_PER_UTT || F.mode == LIDFE_CMVN_ACCUM_GLOBAL);
+    fbank_fn wf = pick_warp_kernel(h->cfg.in_dtype, h->std_mel,
+                                   (F.mode == LIDFE_CMVN_PER_UTT || F.mode == LIDFE_CMVN_ACCUM_GLOBAL) ? 1 : F.mode == LIDFE_POST_TOPDB ? 2 : 0);
     bool prof = profile && h->prof_events && (h->prof_used + 2 <= static_cast<int>(h->prof_events->size()));
     if (prof) prof = (h->prof_calls++ % (h->prof_stride > 0 ? h->prof_stride : 1)) == 0;
     if (prof) CU_TRY(cudaEventRecord((*h->prof_events)[h->prof_used], st));
@@ -1462,6 +1494,8 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     if (!fused_w) P.n_items = 0;
     const int rcw = launch_warp(P, true);
     if (rcw != LIDFE_OK) return rcw;
+    if (cmvn_mode == LIDFE_POST_TOPDB)
+      return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 2, launch_parity_w);
     if (cmvn_mode == LIDFE_CMVN_PER_UTT && !fused_w)
       return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 1, launch_parity_w);
     CU_TRY(cudaEventRecord(p->blk->ev, st));

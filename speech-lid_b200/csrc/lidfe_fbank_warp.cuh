@@ -22,9 +22,10 @@
 //     are folded into lane-owned fp64 accumulators in the warp's shared memory every kFoldQuads quads; they leave the
 //     warp with fp64 atomics when the utterance changes (per-utterance mode) or once per CTA at the end (global mode).
 //     The statistics-free instantiation (kStats = false) carries none of those registers.
-// Scope: KALDI framing, TMA-eligible (16-byte aligned) utterances, cmvn modes none / per-utterance statistics / global
-// apply / global accumulate, fbank output (the MFCC two-kernel path uses it with the tile-blocked workspace layout).
-// Everything else (CENTER framing, in-kernel dither / normalize_wav, in-kernel DCT, unaligned offsets, AmplitudeToDB) stays
+// Scope: KALDI framing (kStdMel 0 / 1) and the reference's default branch -- CENTER framing, HTK mel, 10 log10, per-utterance
+// extrema for AmplitudeToDB(top_db) (kStdMel 2) --, 16-byte aligned utterances, cmvn modes none / per-utterance statistics /
+// global apply / global accumulate / top_db, fbank output (the MFCC two-kernel path uses it with the tile-blocked workspace
+// layout).  Everything else (in-kernel dither / normalize_wav, in-kernel DCT, unaligned offsets, generic CENTER configs) stays
 // with fbank_kernel.
 #pragma once
 #include "lidfe_kernels.cuh"
@@ -161,7 +162,8 @@ __device__ __noinline__ void second_stage_warp(const FbankParams& P, unsigned ch
   }
 }
 
-template <typename TIn, int kStdMel, bool kStats>
+// kStats: 0 = no statistics, 1 = sums for per-utterance / global CMVN, 2 = per-utterance extrema for AmplitudeToDB(top_db)
+template <typename TIn, int kStdMel, int kStats>
 __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(const __grid_constant__ FbankParams P) {
   using L0 = SmemLayout<float, false>;
   using WL = WarpLayout<TIn>;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
 
   const int n_out = (kStdMel != 0) ? 80 : P.n_out;
   const int mode = P.mode;
+  constexpr bool kSums = (kStats == 1), kExt = (kStats == 2);
 
   int taps[kBands], tap_off[kBands + 1];
   tap_off[0] = 0;
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (kStats)
+  if (kSums)
     for (int e = lane; e < 2 * kMaxMels; e += 32) acc_s[e] = 0.0;
   if (mode == 2 && tid < n_out) {
     const double n = P.stats_in[2 * n_out];
@@ -267,6 +270,32 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
     mbar_expect_tx(bar, bytes);
     tma_bulk_g2s(const_cast<TIn*>(sm_in), reinterpret_cast<const TIn*>(P.wav) + wav_off, bytes, bar, l2_evict_first_policy());
   };
+  // CENTER framing (kStdMel == 2, the reference's torch.stft branch): quads that touch the constant padding or the
+  // reflection at either end of the utterance (spans the host marks aux = 0: the first quad and the last one or two) are
+  // staged element by element by the whole warp -- index u of the padded signal p (length N + 2 pad), mirrored once at
+  // either end like torch.stft(center=True, pad_mode="reflect"), zeros inside the padding; a plain arrival completes the
+  // mbarrier phase.  Interior quads take the TMA copy like the Kaldi framing.   ref: lid/audio_processor.py:91-103
+  auto stage_any = [&](const WSpanRegs& sp, int qi) {
+    const int nf = min(kQuadFrames, sp.nframes - qi * kQuadFrames);
+    if (sp.aux != 0) {
+      if (lane == 0) stage_quad(sp.wav_off + static_cast<long long>(qi) * (kQuadFrames * kFrameShift), nf);
+    } else {
+      const int nsamp = kFrameShift * nf + (kFrameLen - kFrameShift);
+      const long long N = P.utt_lengths[sp.utt];
+      const TIn* x = reinterpret_cast<const TIn*>(P.wav) + P.utt_offsets[sp.utt];
+      const long long Lp = N + 2 * P.pad;
+      const long long u0 = static_cast<long long>(kFrameShift) * (sp.t0 + qi * kQuadFrames) - (kFrameLen / 2);
+      TIn* dst = const_cast<TIn*>(sm_in);
+      for (int i = lane; i < nsamp; i += 32) {
+        long long u = u0 + i;
+        u = u < 0 ? -u : (u >= Lp ? 2 * (Lp - 1) - u : u);
+        const long long r = u - P.pad;
+        dst[i] = (r >= 0 && r < N) ? x[r] : static_cast<TIn>(0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    }
+  };
   auto fetch_span = [&](int idx, int which) {    // lane 0: descriptor idx -> slot `which`, asynchronously
     const int4* g = reinterpret_cast<const int4*>(P.wspans + idx);
     cp_async16(const_cast<int4*>(slot_of(which)), g);
@@ -283,16 +312,19 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
     }
     __syncwarp();
     const WSpanRegs s0 = read_span(0);
-    if (lane == 0 && s0.nframes > 0) stage_quad(s0.wav_off, min(kQuadFrames, s0.nframes));
+    if (kStdMel == 2) {
+      if (s0.nframes > 0) stage_any(s0, 0);
+    } else if (lane == 0 && s0.nframes > 0) stage_quad(s0.wav_off, min(kQuadFrames, s0.nframes));
   }
 
   int frames_acc = 0;                  // mode 3: frames of the spans this warp has processed
+  float ex_max = -INFINITY, ex_min = INFINITY;      // kExt: extrema of held_utt's features seen by this lane
   int held_utt = -1;                   // mode 1: whose sums the accumulators hold
   int frames_held = 0;                 // mode 1, fused second stage: frames of held_utt in the accumulators
 
   // per-utterance second stage inside this kernel: compiled in only with -DLIDFE_WFUSED_BUILD=1 (see the note above
   // announce_frames_warp: it is slower than the second launch, and its mere presence costs the statistics variant 4 us)
-  const bool fused2 = LIDFE_WFUSED_BUILD && kStats && mode == 1 && P.n_items > 0;
+  const bool fused2 = LIDFE_WFUSED_BUILD && kSums && mode == 1 && P.n_items > 0;
 
   while (have_cur) {
     // the next span's descriptor travels into the other slot while this span runs
@@ -310,7 +342,14 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
         const int r = i / n_out;
         P.out[(sp.out_row + r) * P.out_ld + (i - r * n_out)] = 0.f;
       }
-      if (lane == 0 && nxt_idx < P.n_wspans) {
+      if (kStdMel == 2) {
+        if (nxt_idx < P.n_wspans) {
+          if (lane == 0) cp_async_wait<0>();
+          __syncwarp();
+          const WSpanRegs nx = read_span(cur ^ 1);
+          if (nx.nframes > 0) stage_any(nx, 0);
+        }
+      } else if (lane == 0 && nxt_idx < P.n_wspans) {
         cp_async_wait<0>();
         const WSpanRegs nx = read_span(cur ^ 1);
         if (nx.nframes > 0) stage_quad(nx.wav_off, min(kQuadFrames, nx.nframes));
@@ -346,8 +385,8 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
       };
       // ---- per-span set-up: the utterance's mask table (modes that mask in the epilogue) --------------------------
       unsigned dim_masked = 0u;
-      const int n_masks = (!kStats && (mode == 0 || mode == 2)) ? P.n_masks : 0;
-      if (!kStats && n_masks > 0) {
+      const int n_masks = (kStats == 0 && (mode == 0 || mode == 2)) ? P.n_masks : 0;
+      if (kStats == 0 && n_masks > 0) {
         const int utt = read_span(cur).utt;
         __syncwarp();
         if (lane < n_masks * 4) wmasks[lane] = __ldg(P.masks + static_cast<long long>(utt) * n_masks * 4 + lane);
@@ -379,7 +418,16 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             x[j] = (j < 17 || t < 8) ? InTraits<TIn>::ld2(fr + 2 * n, P.in_scale) : make_float2(0.f, 0.f);
           }
           __syncwarp();     // every lane holds its samples: the buffer is free for the next quad
-          if (lane == 0) {
+          if (kStdMel == 2) {
+            if (qi + 1 < n_quads) {
+              stage_any(read_span(cur), qi + 1);
+            } else if (nxt_idx < P.n_wspans) {
+              if (lane == 0) cp_async_wait<0>();
+              __syncwarp();
+              const WSpanRegs nx = read_span(cur ^ 1);
+              if (nx.nframes > 0) stage_any(nx, 0);
+            }
+          } else if (lane == 0) {
             if (qi + 1 < n_quads) {
               stage_quad(read_span(cur).wav_off + static_cast<long long>(qi + 1) * (kQuadFrames * kFrameShift),
                          min(kQuadFrames, sp_nframes - (qi + 1) * kQuadFrames));
@@ -431,7 +479,15 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
               I[j] = mul2(so, bc(w.y));
             }
           };
-          if (kStdMel == 1 && LIDFE_UNIT_SHORTCUT) {
+          if (kStdMel == 2) {
+            // the reference's torch.stft call: window only; the (A, B) pairs are formed by the scalar multiplies themselves
+    #pragma unroll
+            for (int j = 0; j < 13; ++j) {
+              const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * (t + 16 * j));
+              R[j] = make_float2(__fmul_rn(x[j].x, w.x), __fmul_rn(x[j + 5].x, w.x));
+              I[j] = make_float2(__fmul_rn(x[j].y, w.y), __fmul_rn(x[j + 5].y, w.y));
+            }
+          } else if (kStdMel == 1 && LIDFE_UNIT_SHORTCUT) {
             // The reference's call (DC removal, then pre-emphasis with coefficient 1.0, replicate-left): every output is
             // (x[n] - m) - (x[n-1] - m), and y[0] = (x[0] - m) - (x[0] - m) = 0.  The frame mean m only enters through the
             // rounding of the two inner differences; x[n] - x[n-1] rounded ONCE is the same value with less round-off (the
@@ -647,8 +703,17 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           }
         }
 
+        // ---- AmplitudeToDB(top_db): running extrema of this lane's live features (ta: functional/functional.py:391-403) ------
+        if (kExt) {
+    #pragma unroll
+          for (int b = 0; b < kBands; ++b)
+            if (t + 16 * b < n_out) {
+              if (actA) { ex_max = fmaxf(ex_max, val[b].x); ex_min = fminf(ex_min, val[b].x); }
+              if (actB) { ex_max = fmaxf(ex_max, val[b].y); ex_min = fminf(ex_min, val[b].y); }
+            }
+        }
         // ---- statistics: centred fp32 partial sums in registers, folded into fp64 every kFoldQuads quads -------------
-        if (kStats) {
+        if (kSums) {
           if (quads_since_fold == 0) {     // (a dead pair holds frame 0 of its quad: as good a centre as any)
     #pragma unroll
             for (int b = 0; b < kBands; ++b) C[b] = val[b].x;
@@ -673,7 +738,8 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           if (++quads_since_fold == kFoldQuads) fold();
         }
       }   // quads of the span
-      if (kStats) {
+      if (kExt) held_utt = read_span(cur).utt;
+      if (kSums) {
         // every span's contribution is folded before the next one starts: what a span adds to the sums is then a function
         // of the span alone, not of which warp happened to claim it after what (bit-reproducible statistics up to the
         // order of the fp64 additions)
@@ -690,7 +756,28 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
       if (lane == 0) cp_async_wait<0>();
       __syncwarp();
     }
-    if (kStats && mode == 1 && held_utt >= 0) {
+    if (kExt && held_utt >= 0) {
+      bool hand_over = !have_next;
+      if (have_next) {
+        const WSpanRegs nx = read_span(cur ^ 1);
+        hand_over = (nx.nframes == 0) || (nx.utt != held_utt);
+      }
+      if (hand_over) {
+    #pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          ex_max = fmaxf(ex_max, __shfl_xor_sync(0xffffffffu, ex_max, o));
+          ex_min = fminf(ex_min, __shfl_xor_sync(0xffffffffu, ex_min, o));
+        }
+        if (lane == 0) {
+          atomicMax(P.utt_max + (P.parity & 1) * P.b_cap + held_utt, f2ord(ex_max));
+          atomicMin(P.utt_min + (P.parity & 1) * P.b_cap + held_utt, f2ord(ex_min));
+        }
+        ex_max = -INFINITY;
+        ex_min = INFINITY;
+        held_utt = -1;
+      }
+    }
+    if (kSums && mode == 1 && held_utt >= 0) {
       bool hand_over = !have_next;
       if (have_next) {
         const WSpanRegs nx = read_span(cur ^ 1);
@@ -726,7 +813,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
   if (fused2) second_stage_warp(P, wbase + WL::off_plane, n_out);
 
   // ---- out of work: global sums leave the CTA once; the last CTA puts the claim counter back to rest ----------------
-  if (kStats && mode == 3) {
+  if (kSums && mode == 3) {
     __syncthreads();
     for (int e = tid; e < 2 * kMaxMels; e += kWThreads) {
       const int which = e / kMaxMels, d = e - which * kMaxMels;

@@ -131,6 +131,40 @@ def test_warp_kernel_equals_cta_kernel(lid):
 
 
 @gpu
+@pytest.mark.parametrize("pad", [0, 16])
+def test_warp_kernel_equals_cta_kernel_default_branch(lid, pad):
+    """The reference's default branch (MelSpectrogram + AmplitudeToDB(top_db=80), ref: lid/audio_processor.py:72-105) through
+    the warp-autonomous kernel (CENTER framing: interior quads by TMA, the first quad and the last one or two of every
+    utterance staged element by element with the reflection; per-utterance extrema by atomics) against fbank_kernel:
+    same arithmetic per frame, max / min are order-free, so the outputs are bit-equal -- raw dB values, with masks, and after
+    the top_db clamp -- on ragged padded / packed batches including utterances that are edge from end to end, with a
+    quiet tail that the clamp actually touches, over repeated launches (launch parity of the extrema workspace)."""
+    g = torch.Generator().manual_seed(50 + pad)
+    lens = [16000, 4000, 24000, 8560, 400, 559, 257, 64000, 1040, 720, 128000, 300, 880, 881]
+    wavs = [torch.randn(n, generator=g) for n in lens]
+    wavs[3][4000:] *= 1e-5                      # 100 dB down: AmplitudeToDB's clamp is active there
+    wavs[10][96000:] *= 1e-6
+    fw = _fresh_frontend(lid, {"LIDFE_WARP_KERNEL": "1"}, kind="melspec_db", pad=pad)
+    fc = _fresh_frontend(lid, {"LIDFE_WARP_KERNEL": "0"}, kind="melspec_db", pad=pad)
+    for padded in (True, False):
+        pw, pc = fw.make_plan(lens, padded=padded), fc.make_plan(lens, padded=padded)
+        assert pw.frames == pc.frames == [1 + (n + 2 * pad) // 160 for n in lens]
+        packed = fw.pack(wavs, pw)
+        torch.manual_seed(3)
+        masks = lid.draw_masks(pw.frames, 80, 0.05, 27, 2).cuda()
+        for rep in range(3):
+            a = fw.featurize_packed(packed, pw, masks=masks if rep % 2 else None)
+            b = fc.featurize_packed(packed, pc, masks=masks if rep % 2 else None)
+            assert torch.equal(a, b), (pad, padded, rep)
+            assert bool(torch.isfinite(a).all())
+    # and against the oracle on one utterance with a clamped tail
+    want = O.melspec_db(wavs[3].unsqueeze(0), pad=pad)[0].T
+    got = fw.featurize([wavs[3]])[0][0].cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max() / want.abs().max()) <= 1e-4
+
+
+@gpu
 def test_many_short_utterances_padded_equals_packed(lid):
     """ADVICE.md (round 1): a padded batch of many short utterances with cmvn='none' (zero-fill work between real work)
     must give the packed layout's bits, row for row, launch after launch."""
