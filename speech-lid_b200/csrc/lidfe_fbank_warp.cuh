@@ -44,14 +44,14 @@ constexpr int kWWarps = LIDFE_WWARPS;            // warps per CTA (they only sha
 constexpr int kWCtasPerSm = LIDFE_WCTAS;
 constexpr int kWThreads = kWWarps * 32;
 #ifndef LIDFE_FOLD_QUADS
-#define LIDFE_FOLD_QUADS 8
+#define LIDFE_FOLD_QUADS 32
 #endif
 constexpr int kFoldQuads = LIDFE_FOLD_QUADS;     // fp32 partial sums are folded into the fp64 accumulators this often
 #ifndef LIDFE_XPOSE_ST128
 #define LIDFE_XPOSE_ST128 1      // transposition stores: 1 = one STS.128 per point, 0 = two STS.64 halves
 #endif
 #ifndef LIDFE_PRE_SHARE
-#define LIDFE_PRE_SHARE 0        // unit pre-emphasis: 1 = frames A and B share the 18 "previous sample" shuffles
+#define LIDFE_PRE_SHARE 0        // unit pre-emphasis: 1 = frames A and B share the 18 "previous sample" shuffles in EVERY variant (the statistics variant always does)
 #endif
 #ifndef LIDFE_WFUSED_BUILD
 #define LIDFE_WFUSED_BUILD 0      // 1: build the in-kernel per-utterance second stage (then LIDFE_WFUSED=1 selects it)
@@ -493,37 +493,44 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             // rounding of the two inner differences; x[n] - x[n-1] rounded ONCE is the same value with less round-off (the
             // two differ by < 1 ulp of |x|, which is what the reference itself is off by), and the 400-term mean reduction
             // with its 8 shuffles per quad disappears.
-    #if LIDFE_PRE_SHARE
-            // frame B is frame A five loads on: element j of B needs the same "previous sample" as element j + 5 of A,
-            // so 18 shuffles serve both frames (13 + 13 otherwise); only B's first sample (replicate-left) differs
-            float q[18];
+            // Frame B is frame A five loads on: element j of B needs the same "previous sample" as element j + 5 of A, so 18
+            // shuffles can serve both frames (13 + 13 otherwise); only B's first sample (replicate-left) differs.  Same
+            // values either way.  The shared form holds 18 floats at once: it pays in the statistics variant (-2 us on the
+            // per-utterance CMVN step) and spills in the statistics-free one, hence the choice per instantiation.
+            constexpr bool kPreShare = LIDFE_PRE_SHARE || (kStats == 1);
+            if constexpr (kPreShare) {
+              float q[18];
     #pragma unroll
-            for (int j = 0; j < 18; ++j) {
-              const float s = (t == 15) ? (j ? x[j - 1].y : 0.f) : x[j].y;
-              q[j] = __shfl_sync(0xffffffffu, s, up_lane);              // x[2n - 1], n = t + 16 j
-            }
-    #else
-            float pA = 0.f, pB = 0.f;
-    #endif
+              for (int j = 0; j < 18; ++j) {
+                const float s = (t == 15) ? (j ? x[j - 1].y : 0.f) : x[j].y;
+                q[j] = __shfl_sync(0xffffffffu, s, up_lane);              // x[2n - 1], n = t + 16 j
+              }
     #pragma unroll
-            for (int j = 0; j < 13; ++j) {
-              const int n = t + 16 * j;
-              const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * n);
-    #if LIDFE_PRE_SHARE
-              float qA = q[j], qB = q[j + 5];
-              if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
-    #else
-              const float sA = (t == 15) ? pA : x[j].y, sB = (t == 15) ? pB : x[j + 5].y;
-              float qA = __shfl_sync(0xffffffffu, sA, up_lane);       // x[2n - 1]
-              float qB = __shfl_sync(0xffffffffu, sB, up_lane);
-              if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
-              pA = x[j].y;
-              pB = x[j + 5].y;
-    #endif
-              const f2 se = make_float2(__fsub_rn(x[j].x, qA), __fsub_rn(x[j + 5].x, qB));
-              const f2 so = make_float2(__fsub_rn(x[j].y, x[j].x), __fsub_rn(x[j + 5].y, x[j + 5].x));
-              R[j] = mul2(se, bc(w.x));
-              I[j] = mul2(so, bc(w.y));
+              for (int j = 0; j < 13; ++j) {
+                const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * (t + 16 * j));
+                float qA = q[j], qB = q[j + 5];
+                if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
+                const f2 se = make_float2(__fsub_rn(x[j].x, qA), __fsub_rn(x[j + 5].x, qB));
+                const f2 so = make_float2(__fsub_rn(x[j].y, x[j].x), __fsub_rn(x[j + 5].y, x[j + 5].x));
+                R[j] = mul2(se, bc(w.x));
+                I[j] = mul2(so, bc(w.y));
+              }
+            } else {
+              float pA = 0.f, pB = 0.f;
+    #pragma unroll
+              for (int j = 0; j < 13; ++j) {
+                const float2 w = *reinterpret_cast<const float2*>(sm_window + 2 * (t + 16 * j));
+                const float sA = (t == 15) ? pA : x[j].y, sB = (t == 15) ? pB : x[j + 5].y;
+                float qA = __shfl_sync(0xffffffffu, sA, up_lane);       // x[2n - 1]
+                float qB = __shfl_sync(0xffffffffu, sB, up_lane);
+                if (j == 0 && t == 0) { qA = x[0].x; qB = x[5].x; }
+                pA = x[j].y;
+                pB = x[j + 5].y;
+                const f2 se = make_float2(__fsub_rn(x[j].x, qA), __fsub_rn(x[j + 5].x, qB));
+                const f2 so = make_float2(__fsub_rn(x[j].y, x[j].x), __fsub_rn(x[j + 5].y, x[j + 5].x));
+                R[j] = mul2(se, bc(w.x));
+                I[j] = mul2(so, bc(w.y));
+              }
             }
           } else if (kStdMel == 1) frame_pass(std::true_type{});
           else frame_pass(std::false_type{});
