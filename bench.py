@@ -220,6 +220,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def pipe_floors(frames, sms, mhz):
+    """Per-launch floors of the two SM pipes the fused kernel loads most, from the per-quad (4-frame) counts of
+    profiles/r2_fbank_warp_ncu_summary.txt: 480 shared-memory wavefronts (1 per clock and SM), 615 packed f32x2 operations
+    at 2 issue cycles each + 190 scalar ones spread over the 4 sub-partitions."""
+    quads_per_sm = frames / 4.0 / sms
+    return {"smem_data_pipe": round(quads_per_sm * 480.0 / mhz, 1),
+            "fma_pipe_instruction_mix": round(quads_per_sm * (615.0 * 2.0 + 190.0) / 4.0 / mhz, 1),
+            "source": "profiles/r2_fbank_warp_ncu_summary.txt (per quad: 480 wavefronts, 615 f32x2 + 190 scalar FP instructions)"}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -476,6 +486,10 @@ def run_gpu_arm(args):
                 "kernel_timing": "CUDA event pair around every %d-th launch of the timed region (%d samples)" % (prof_stride, len(kernel_ms)),
                 "alg_flop_per_launch": frames_per_step * ALG_FLOP_PER_FRAME, "alg_bytes_per_launch": alg_bytes,
                 "floors_us": {"fp32": round(fp32_floor_us, 1), "hbm": round(hbm_floor_us, 1)},
+                # what actually binds (ncu counters of the committed capture, scaled to this launch and the max clock): the
+                # shared-memory data pipe delivers one 128-byte wavefront per clock and SM; the FFT is add-dominated, so its
+                # 15 kflop per frame take more FMA-pipe cycles than as many flops of pure FFMA would
+                "pipe_floors_us": pipe_floors(frames_per_step, sms, clocks.get("sm_max_mhz") or 1965),
                 "fp32": {"achieved_tflops": round(fp32_achieved, 2), "peak_tflops_measured": round(fp32_peak, 2),
                          "peak_tflops_theoretical_at_max_clock": round(fp32_theory, 1),
                          "frac_of_measured": round(fp32_achieved / fp32_peak, 4),
