@@ -56,9 +56,6 @@ constexpr int kFoldQuads = LIDFE_FOLD_QUADS;     // fp32 partial sums are folded
 #ifndef LIDFE_WFUSED_BUILD
 #define LIDFE_WFUSED_BUILD 0      // 1: build the in-kernel per-utterance second stage (then LIDFE_WFUSED=1 selects it)
 #endif
-#ifndef LIDFE_MEL_COMPLEMENT
-#define LIDFE_MEL_COMPLEMENT 0   // experiment: next filter's share = segment sum - own share (weights as one LDS.32)
-#endif
 constexpr int kWTabOff = 128;                    // tables start here (the tables' mbarrier sits in front)
 
 // per half-warp transposition plane: 16 rows of 17 elements of 16 bytes (re_A, re_B, im_A, im_B); reused for the 257
@@ -618,17 +615,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
             f2 own = make_float2(0.f, 0.f), nxt = make_float2(0.f, 0.f);
             const f2* pp = my_P + sm_k0[t + 16 * b];
             const float2* wp = reinterpret_cast<const float2*>(sm_melw) + tap_off[b] * 16 + t;
-            if (kStdMel && LIDFE_MEL_COMPLEMENT) {
-              f2 tot = make_float2(0.f, 0.f);
-    #pragma unroll
-              for (int i = 0; i < std_taps(kStdMel, b); ++i) {
-                const f2 p = pp[i];
-                const float w = wp[i * 16].x;
-                own = fma2(p, bc(w), own);
-                tot = add2(tot, p);
-              }
-              nxt = sub2(tot, own);
-            } else if (kStdMel) {
+            if (kStdMel) {
     #pragma unroll
               for (int i = 0; i < std_taps(kStdMel, b); ++i) {
                 const f2 p = pp[i];
