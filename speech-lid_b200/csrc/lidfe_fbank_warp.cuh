@@ -53,6 +53,9 @@ constexpr int kFoldQuads = LIDFE_FOLD_QUADS;     // fp32 partial sums are folded
 #ifndef LIDFE_PRE_SHARE
 #define LIDFE_PRE_SHARE 0        // unit pre-emphasis: 1 = frames A and B share the 18 "previous sample" shuffles in EVERY variant (the statistics variant always does)
 #endif
+#ifndef LIDFE_TW2_REGS
+#define LIDFE_TW2_REGS 1           // 1: instantiations without CMVN sums keep the 8 split twiddles of a lane in registers
+#endif
 #ifndef LIDFE_WFUSED_BUILD
 #define LIDFE_WFUSED_BUILD 0      // 1: build the in-kernel per-utterance second stage (then LIDFE_WFUSED=1 selects it)
 #endif
@@ -395,6 +398,14 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
         }
       }
       const int n_quads = (sp_nframes + kQuadFrames - 1) / kQuadFrames;
+      // the statistics-free instantiations have the registers the sums would take: the lane's 8 split twiddles stay
+      // resident for the span (16 wavefronts per quad less on the shared-memory pipe)
+      constexpr bool kTw2Regs = LIDFE_TW2_REGS && (kStats != 1);
+      float2 tw2r[8];
+      if constexpr (kTw2Regs) {
+    #pragma unroll
+        for (int i = 0; i < 8; ++i) tw2r[i] = sm_tw2[i * 16 + t];
+      }
 
       for (int qi = 0; qi < n_quads; ++qi) {
         const int nf = min(kQuadFrames, sp_nframes - qi * kQuadFrames);     // live frames of this quad
@@ -596,7 +607,7 @@ __global__ void __launch_bounds__(kWThreads, kWCtasPerSm) fbank_warp_kernel(cons
           const f2 ar = R[rev4(i)], ai = I[rev4(i)];
           const f2 e2r = add2(ar, br), e2i = sub2(ai, bi);
           f2 o2r = add2(ai, bi), o2i = sub2(br, ar);
-          const float2 w = sm_tw2[i * 16 + t];
+          const float2 w = kTw2Regs ? tw2r[i] : sm_tw2[i * 16 + t];
           cmul2(o2r, o2i, w.x, w.y);
           const f2 xar = add2(e2r, o2r), xai = add2(e2i, o2i);
           const f2 xbr = sub2(e2r, o2r), xbi = sub2(e2i, o2i);
