@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define LIDFE_ABI_VERSION 7
+#define LIDFE_ABI_VERSION 8
 
 /* error codes (negative) */
 #define LIDFE_OK 0
@@ -293,6 +293,15 @@ int lidfe_wgemm_create(lidfe_resampler* out, int hop, int n_rows, const float* b
 int lidfe_stft_mel_db(const float* g_dev, const long long* g_off_dev, const long long* frames_dev, int B, long long max_frames,
                       int nw, const float* melT_dev, const int* mel_lo_dev, const int* mel_hi_dev, int n_bins, int n_mels,
                       float amin, float* out_dev, const long long* out_row_dev, double* stats_dev, int normalize, void* stream);
+
+/* Arithmetic mode of lidfe_featurize on this handle.  0 (default): the fast fp32 kernels.  1: "precise" -- the reference's
+ * formula (ref: lid/audio_processor.py:41-69 -> ta: compliance/kaldi.py:183-217, 514-645, 648-813) evaluated in float64
+ * from the samples to the logarithm (through DCT + lifter for MFCC) on the same fp32 tables, rounded once at the store:
+ * within half an ulp of the fp64 truth, i.e. at least as close to it as the reference's own fp32 result on every mel bin
+ * (SURVEY.md 8c metric iv).  About 4 x the time of the fast path.  Scope: KALDI framing, natural log, no in-kernel dither
+ * (LIDFE_E_CONFIG otherwise); every cmvn mode except LIDFE_POST_TOPDB; lidfe_featurize_raw is not served (LIDFE_E_ARG).
+ * May upload two small tables on first use (synchronises the device once). */
+int lidfe_set_precision(lidfe_handle h, int precise);
 
 /* FP32 ceiling of the device, measured: a dependent-free FFMA loop on every SM for about `ms_budget` milliseconds.
  * Writes the achieved TFLOP/s (2 flops per FFMA) -- bench.py reports the kernel against this, not against a data sheet. */

@@ -18,7 +18,7 @@ IN_F32, IN_I16 = 0, 1
 CMVN_NONE, CMVN_PER_UTT, CMVN_APPLY_GLOBAL, CMVN_ACCUM_GLOBAL, POST_TOPDB = 0, 1, 2, 3, 4
 FRAMING_KALDI, FRAMING_CENTER = 0, 1
 LOG_NATURAL, LOG_DB10 = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 WINDOW_POVEY, WINDOW_HANNING, WINDOW_HAMMING, WINDOW_RECTANGULAR, WINDOW_BLACKMAN, WINDOW_HANN_PERIODIC = 0, 1, 2, 3, 4, 5
 
 EXPORTS = (
@@ -28,6 +28,7 @@ EXPORTS = (
     "lidfe_abi_version", "lidfe_launch_count", "lidfe_profile_begin", "lidfe_profile_end", "lidfe_profile_set_stride", "lidfe_mel_plan", "lidfe_mel_plan_expand",
     "lidfe_resampler_create", "lidfe_resampler_destroy", "lidfe_resample_out_len", "lidfe_resample",
     "lidfe_plan_create_async", "lidfe_plan_num_spans", "lidfe_featurize_raw", "lidfe_fp32_probe", "lidfe_pool_stats", "lidfe_pack_host", "lidfe_h2d_gather", "lidfe_wgemm_create", "lidfe_stft_mel_db",
+    "lidfe_set_precision",
 )
 
 
@@ -87,6 +88,8 @@ def load_library() -> C.CDLL:
     lib.lidfe_featurize_raw.restype = i32
     lib.lidfe_fp32_probe.argtypes = [f32, C.POINTER(C.c_double), vp]
     lib.lidfe_fp32_probe.restype = i32
+    lib.lidfe_set_precision.argtypes = [vp, i32]
+    lib.lidfe_set_precision.restype = i32
     lib.lidfe_pool_stats.argtypes = [vp, pll, pll]
     lib.lidfe_pool_stats.restype = i32
     lib.lidfe_pack_host.argtypes = [vp, C.POINTER(vp), pll, pll, i32, i32, ll, i32]

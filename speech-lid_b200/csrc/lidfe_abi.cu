@@ -18,6 +18,7 @@
 #include "lidfe_fbank_warp.cuh"
 #include "lidfe_resample_tc.cuh"
 #include "lidfe_stft_fbank.cuh"
+#include "lidfe_fbank_precise.cuh"
 
 using namespace lidfe;
 
@@ -84,6 +85,11 @@ struct lidfe_ctx {
   int prof_used;
   int prof_stride;   // bracket every prof_stride-th featurize call (event records between kernels cost a few us)
   int prof_calls;
+  // precise mode (lidfe_set_precision, lidfe_fbank_precise.cuh): fp64 arithmetic on the reference's fp32 tables
+  int precise;
+  std::vector<float>* melbank_host;   // the dense bank lidfe_create was given (uploaded when precise mode is first selected)
+  float* d_melbank;                   // [n_mels][257]
+  int2* d_mel_range;                  // [n_mels] non-zero range of every filter
 };
 
 struct lidfe_plan_s {
@@ -586,6 +592,11 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   memset(c, 0, sizeof(*c));
   c->cfg = *cfg;
   c->n_out = cfg->n_ceps > 0 ? cfg->n_ceps : cfg->n_mels;
+  c->melbank_host = new (std::nothrow) std::vector<float>(melbank_host, melbank_host + static_cast<size_t>(cfg->n_mels) * kBins);
+  if (!c->melbank_host) {
+    delete c;
+    return LIDFE_E_NOMEM;
+  }
 
   // ---- dense bank -> segment plan (see build_mel_plan).  The kernel leaves the power bins scaled by 4 (it skips the
   //      1/2 of the real-FFT split), so the weights carry the exact factor 1/4.
@@ -593,6 +604,7 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   {
     const int rc = build_mel_plan(cfg->n_mels, melbank_host, mp);
     if (rc != LIDFE_OK) {
+      delete c->melbank_host;
       delete c;
       return rc;
     }
@@ -757,6 +769,9 @@ static void free_block(PlanBlock* b) {
 
 static void destroy_now(lidfe_ctx* h) {
   cudaFree(h->d_blob);
+  cudaFree(h->d_melbank);
+  cudaFree(h->d_mel_range);
+  delete h->melbank_host;
   if (h->pool) {
     for (PlanBlock* b : *h->pool) free_block(b);
     delete h->pool;
@@ -1387,6 +1402,45 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
   P.stats_out = stats_out_dev;
   P.utt_stats = p->d_utt_stats;
 
+  if (h->precise) {
+    // precise mode: fp64 arithmetic in fbank_precise_kernel (statistics included), normalisation / masks in the apply kernel
+    if (raw || cmvn_mode == LIDFE_POST_TOPDB) return LIDFE_E_ARG;
+    PreciseParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.wav = wav_dev;
+    Q.out = out_dev;
+    Q.out_ld = out_ld;
+    Q.spans = p->d_spans;
+    Q.n_spans = static_cast<int>(p->n_spans);
+    Q.window = reinterpret_cast<const float*>(h->d_blob);
+    Q.melbank = h->d_melbank;
+    Q.mel_range = h->d_mel_range;
+    Q.dct = h->cfg.n_ceps > 0 ? reinterpret_cast<const float*>(h->d_blob + h->dct_off) : nullptr;
+    Q.lifter = h->cfg.n_ceps > 0 ? reinterpret_cast<const float*>(h->d_blob + h->lifter_off) : nullptr;
+    Q.n_mels = h->cfg.n_mels;
+    Q.n_ceps = h->cfg.n_ceps;
+    Q.n_out = h->n_out;
+    Q.preemph = h->cfg.preemph;
+    Q.in_scale = h->cfg.in_scale;
+    Q.log_floor = h->cfg.log_floor;
+    Q.log_of_floor = logf(h->cfg.log_floor);
+    Q.remove_dc = h->cfg.remove_dc;
+    Q.mode = cmvn_mode;
+    Q.utt_stats = p->d_utt_stats + static_cast<long long>(P.parity & 1) * P.b_cap * 2 * h->n_out;
+    Q.stats_out = stats_out_dev;
+    long long gp = p->n_spans < static_cast<long long>(h->num_sms) * 8 ? p->n_spans : static_cast<long long>(h->num_sms) * 8;
+    if (gp < 1) gp = 1;
+    if (h->cfg.in_dtype == LIDFE_IN_I16) fbank_precise_kernel<short><<<static_cast<unsigned>(gp), kPThreads, 0, st>>>(Q);
+    else fbank_precise_kernel<float><<<static_cast<unsigned>(gp), kPThreads, 0, st>>>(Q);
+    g_launches.fetch_add(1);
+    CU_TRY(cudaGetLastError());
+    if (cmvn_mode == LIDFE_CMVN_PER_UTT) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 1, P.parity);
+    if (cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, stats_in_dev, st, 1);
+    if (cmvn_mode == LIDFE_CMVN_NONE && masks_dev && n_masks > 0) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 0);
+    CU_TRY(cudaEventRecord(p->blk->ev, st));
+    return LIDFE_OK;
+  }
+
   // the warp-autonomous kernel takes every call inside its scope (see lidfe_fbank_warp.cuh)
   const bool use_warp = h->warp_ok && !raw && p->d_wspans != nullptr && !h->fused_apply &&
                         (cmvn_mode != LIDFE_POST_TOPDB || h->std_mel == 2);
@@ -1551,6 +1605,35 @@ int lidfe_featurize_raw(lidfe_handle h, lidfe_plan p, const void* wav_dev, float
                         const int* masks_dev, int n_masks, int cmvn_mode, const double* stats_in_dev,
                         double* stats_out_dev, void* stream) {
   return featurize_impl(h, p, wav_dev, out_dev, out_ld, masks_dev, n_masks, cmvn_mode, stats_in_dev, stats_out_dev, stream, true);
+}
+
+int lidfe_set_precision(lidfe_handle h, int precise) {
+  if (!h) return LIDFE_E_NULL;
+  if (precise != 0 && precise != 1) return LIDFE_E_ARG;
+  if (precise) {
+    // scope of fbank_precise_kernel: the reference's Kaldi call and its relatives
+    if (h->cfg.framing != LIDFE_FRAMING_KALDI || h->cfg.log_kind != LIDFE_LOG_NATURAL || h->cfg.dither != 0.f) return LIDFE_E_CONFIG;
+    if (!h->d_melbank) {
+      const int n_mels = h->cfg.n_mels;
+      std::vector<int2> range(n_mels);
+      for (int m = 0; m < n_mels; ++m) {
+        int lo = kBins, hi = 0;
+        for (int k = 0; k < kBins; ++k)
+          if ((*h->melbank_host)[static_cast<size_t>(m) * kBins + k] != 0.f) { if (k < lo) lo = k; hi = k + 1; }
+        if (hi == 0) lo = 0;
+        range[m] = make_int2(lo, hi);
+      }
+      cudaError_t e = upload(&h->d_melbank, h->melbank_host->data(), h->melbank_host->size());
+      if (e == cudaSuccess) e = upload(&h->d_mel_range, range.data(), range.size());
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();     // landed whatever stream the caller launches on
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return static_cast<int>(e);
+      }
+    }
+  }
+  h->precise = precise;
+  return LIDFE_OK;
 }
 
 int lidfe_cmvn_apply(lidfe_handle h, lidfe_plan p, float* feats_dev, long long ld, const int* masks_dev, int n_masks,

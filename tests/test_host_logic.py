@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, "liblidfe.so does not export %s" % missing
     assert sorted(_lib.EXPORTS) == declared, "python binding and header disagree"
-    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.lidfe_abi_version() == _lib.ABI_VERSION == 8
 
 
 def _cfg(**kw):

@@ -6,7 +6,7 @@
 (the test-suite asserts a relaxed form of both, see tests/test_gpu_parity.py; this table is the unrelaxed statement.)
 Also printed: the same two metrics for an INDEPENDENT CPU fp32 implementation of the reference's arithmetic (identical
 fp32 frames and tables, numpy's pocketfft instead of torch's FFT) against the oracle, i.e. how two CPU libraries fare
-under the same rule.  Run on the GPU box: python tools/parity_matrix.py [--quick]"""
+under the same rule.  Run on the GPU box: python tools/parity_matrix.py [--quick] [--precise]"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -15,6 +15,7 @@ import speech_lid_b200 as lid
 from oracle import frontend_oracle as O
 
 quick = "--quick" in sys.argv
+precise = "--precise" in sys.argv      # FrontEnd(precise=True): the float64 kernel (lidfe_fbank_precise.cuh)
 torch.set_num_threads(max(1, (os.cpu_count() or 8) // 2))
 
 
@@ -76,8 +77,9 @@ def run(name, wavs, fe, oracle, truth, other=None):
 
 
 def main():
-    fe = lid.FrontEnd(n_mels=80)
-    fem = lid.FrontEnd(n_mels=80, n_ceps=40)
+    fe = lid.FrontEnd(n_mels=80, precise=precise)
+    fem = lid.FrontEnd(n_mels=80, n_ceps=40, precise=precise)
+    print("arithmetic: %s" % ("precise (float64 kernel)" if precise else "fast (fp32 kernels)"), flush=True)
     res = {}
     n2, n3, n4 = (32, 32, 32) if quick else (256, 512, 256)
     g = torch.Generator().manual_seed(3)
@@ -88,7 +90,7 @@ def main():
     res["cfg3"] = run("cfg3 %d x 4 s noise, MFCC-40" % n3, [O.synth_noise(64000, 300 + s) for s in range(n3)], fem, O.kaldi_mfcc, truth_mfcc)
     res["cfg4"] = run("cfg4 %d x 1-20 s noise, fbank" % n4, [O.synth_noise(n, 400 + s) for s, n in enumerate(lens4)], fe, O.kaldi_fbank, O.truth64_fbank)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/parity_matrix.json", "w"), indent=1)
+    json.dump(res, open("gpurun_out/parity_matrix%s.json" % ("_precise" if precise else ""), "w"), indent=1)
 
 
 if __name__ == "__main__":
