@@ -427,6 +427,34 @@ def run_gpu_arm(args):
 
     cfg4 = run_cfg4(lid, fe, dev, rank, world, barrier)
 
+    # ---- precise mode (rank 0, N = 1; informational): the same cfg2 step through the float64 kernel
+    #      (FrontEnd(precise=True) -> lidfe_set_precision -> fbank_precise_kernel), the arithmetic under which SURVEY.md 8(c)
+    #      metric (iv) holds unrelaxed (tests/test_gpu_precise.py); device-resident like `value`, and end to end through
+    #      featurize_host like `e2e` (where PCIe, not the kernel, sets the pace) -----------------------------------------
+    precise = None
+    if world == 1:
+        fep = lid.FrontEnd(n_mels=N_MELS, device=dev, precise=True)
+        planp = fep.make_plan([N_SAMPLES] * B_UTTS, padded=True)
+        for i in range(3):
+            fep.featurize_packed(ins[i % NBUF], planp, out=outs[i % NBUF], masks=masks, cmvn="utt")
+        p_steps = max(5, min(args.steps, 30))
+        barrier()
+        ev0.record()
+        for i in range(p_steps):
+            fep.featurize_packed(ins[i % NBUF], planp, out=outs[i % NBUF], masks=masks, cmvn="utt")
+        ev1.record()
+        barrier()
+        p_ms = ev0.elapsed_time(ev1) / p_steps
+
+        def precise_e2e_step():
+            fep.featurize_host(host_in, planp, host_out, masks=host_masks, cmvn="utt", chunks=e2e_chunks)
+
+        p_e2e = AUDIO_S_PER_BATCH / timed_blocks(precise_e2e_step, n_steps=max(3, min(args.steps, 10)))
+        precise = {"value": round(AUDIO_S_PER_BATCH / (p_ms * 1e-3), 1), "unit": "audio-s/s", "ms_per_step": round(p_ms, 5),
+                   "steps": p_steps, "e2e": round(p_e2e, 1), "dtype": "f64 internally, one rounding to f32 at the store",
+                   "slowdown_vs_fast": round(p_ms / ms_step, 2),
+                   "note": "informational: lidfe_set_precision(h, 1); parity metric (iv) of SURVEY.md 8(c) holds unrelaxed in this mode"}
+
     # ---- cfg5 (rank 0, N = 1): features feeding the reference's Conformer forward on the device, when the model files
     #      have been staged (baseline/_ref, see __graft_entry__.stage_reference_model)
     cfg5 = None
@@ -524,6 +552,7 @@ def run_gpu_arm(args):
             "l2_cold_warm": l2_pair,
             "cfg4": cfg4,
             "cfg5": cfg5,
+            "precise": precise,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu}

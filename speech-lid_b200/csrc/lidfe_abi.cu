@@ -1428,10 +1428,10 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     Q.mode = cmvn_mode;
     Q.utt_stats = p->d_utt_stats + static_cast<long long>(P.parity & 1) * P.b_cap * 2 * h->n_out;
     Q.stats_out = stats_out_dev;
-    long long gp = p->n_spans < static_cast<long long>(h->num_sms) * 8 ? p->n_spans : static_cast<long long>(h->num_sms) * 8;
+    long long gp = p->n_spans * kMaxSpanTiles < static_cast<long long>(h->num_sms) * LIDFE_PRECISE_CTAS ? p->n_spans * kMaxSpanTiles : static_cast<long long>(h->num_sms) * LIDFE_PRECISE_CTAS;
     if (gp < 1) gp = 1;
-    if (h->cfg.in_dtype == LIDFE_IN_I16) fbank_precise_kernel<short><<<static_cast<unsigned>(gp), kPThreads, 0, st>>>(Q);
-    else fbank_precise_kernel<float><<<static_cast<unsigned>(gp), kPThreads, 0, st>>>(Q);
+    if (h->cfg.in_dtype == LIDFE_IN_I16) fbank_precise_kernel<short><<<static_cast<unsigned>(gp), kPThreads, kPSmemBytes, st>>>(Q);
+    else fbank_precise_kernel<float><<<static_cast<unsigned>(gp), kPThreads, kPSmemBytes, st>>>(Q);
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
     if (cmvn_mode == LIDFE_CMVN_PER_UTT) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 1, P.parity);
@@ -1623,7 +1623,12 @@ int lidfe_set_precision(lidfe_handle h, int precise) {
         if (hi == 0) lo = 0;
         range[m] = make_int2(lo, hi);
       }
-      cudaError_t e = upload(&h->d_melbank, h->melbank_host->data(), h->melbank_host->size());
+      cudaError_t e = cudaFuncSetAttribute(fbank_precise_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+      long long nz = 0;
+      for (const int2& r : range) nz += r.y - r.x;
+      if (nz > kPMelW) return LIDFE_E_MELBANK;
+      if (e == cudaSuccess) e = upload(&h->d_melbank, h->melbank_host->data(), h->melbank_host->size());
       if (e == cudaSuccess) e = upload(&h->d_mel_range, range.data(), range.size());
       if (e == cudaSuccess) e = cudaDeviceSynchronize();     // landed whatever stream the caller launches on
       if (e != cudaSuccess) {

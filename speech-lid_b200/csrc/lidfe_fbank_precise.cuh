@@ -40,6 +40,9 @@ struct PreciseParams {
   double* stats_out;        // [2 * n_out + 1]
 };
 
+#ifndef LIDFE_PRECISE_CTAS
+#define LIDFE_PRECISE_CTAS 4
+#endif
 constexpr int kPThreads = 128;
 constexpr int kPHalfWarps = kPThreads / 16;
 constexpr int kPRow = 17;                               // double2 elements per transposition row (conflict-free both ways)
@@ -89,11 +92,24 @@ __device__ __forceinline__ double ld_sample<short>(const short* p, float scale) 
   return static_cast<double>(static_cast<float>(__ldg(p)) * scale);      // the fp32 product torchaudio.load forms (exact for 2^-15)
 }
 
+// dynamic shared memory: tw[256] double2 | window[400] double | mel weights (compact rows) [kPMelW] double |
+// mel (first bin, count, offset) [80] int4 | acc[160] double | planes
+constexpr int kPMelW = 640;        // >= the non-zeros of a bank in which every bin feeds at most two filters (build_mel_plan insists)
+constexpr int kPOffWin = 256 * 16;
+constexpr int kPOffMelW = kPOffWin + 400 * 8;
+constexpr int kPOffMelR = kPOffMelW + kPMelW * 8;
+constexpr int kPOffAcc = kPOffMelR + kMaxMels * 16;
+constexpr int kPOffPlane = kPOffAcc + 2 * kMaxMels * 8;
+constexpr int kPSmemBytes = kPOffPlane + kPHalfWarps * kPPlane * 16;
+
 template <typename TIn>
-__global__ void __launch_bounds__(kPThreads) fbank_precise_kernel(const PreciseParams P) {
-  __shared__ double2 sm_tw[256];                          // W512^k = (cos, -sin)(2 pi k / 512), k = 0..255
-  __shared__ double2 sm_plane[kPHalfWarps * kPPlane];
-  __shared__ double sm_acc[2 * kMaxMels];                 // sums | sums of squares of the current span's features
+__global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_kernel(const PreciseParams P) {
+  extern __shared__ __align__(16) unsigned char psmem[];
+  double2* const sm_tw = reinterpret_cast<double2*>(psmem);                        // W512^k = (cos, -sin)(2 pi k / 512), k = 0..255
+  double* const sm_win = reinterpret_cast<double*>(psmem + kPOffWin);
+  double* const sm_melw = reinterpret_cast<double*>(psmem + kPOffMelW);
+  int4* const sm_melr = reinterpret_cast<int4*>(psmem + kPOffMelR);                // (first bin, bins, offset into sm_melw, -)
+  double2* const sm_plane = reinterpret_cast<double2*>(psmem + kPOffPlane);
 
   const int tid = threadIdx.x, lane = tid & 31, t = lane & 15;
   const int hw = tid >> 4;
@@ -101,6 +117,7 @@ __global__ void __launch_bounds__(kPThreads) fbank_precise_kernel(const PreciseP
   double* const Pw = reinterpret_cast<double*>(X_pl);
   double* const LM = Pw + kPLogmelOff;
   const int partner = (lane & 16) | ((16 - t) & 15);
+  const int up_lane = (lane & 16) | ((t - 1) & 15);
   const bool stats = (P.mode == 1 || P.mode == 3);
 
   for (int k = tid; k < 256; k += kPThreads) {
@@ -108,25 +125,44 @@ __global__ void __launch_bounds__(kPThreads) fbank_precise_kernel(const PreciseP
     sincospi(static_cast<double>(k) / 256.0, &s, &c);
     sm_tw[k] = make_double2(c, -s);
   }
-  for (int e = tid; e < 2 * kMaxMels; e += kPThreads) sm_acc[e] = 0.0;
+  for (int k = tid; k < kFrameLen; k += kPThreads) sm_win[k] = static_cast<double>(__ldg(P.window + k));
+  if (tid < 32) {     // compact rows of the dense bank: warp 0 lays the filters out one after the other
+    int off = 0;
+    for (int m = 0; m < P.n_mels; ++m) {
+      const int2 rg = __ldg(P.mel_range + m);
+      const int cnt = rg.y - rg.x;
+      for (int k = lane; k < cnt; k += 32) sm_melw[off + k] = static_cast<double>(__ldg(P.melbank + static_cast<long long>(m) * kBins + rg.x + k));
+      if (lane == 0) sm_melr[m] = make_int4(rg.x, cnt, off, 0);
+      off += cnt;
+    }
+  }
   __syncthreads();
 
   const double cpre = static_cast<double>(P.preemph);
   const TIn* const wav = reinterpret_cast<const TIn*>(P.wav);
 
-  for (int si = blockIdx.x; si < P.n_spans; si += gridDim.x) {
+  // work unit = one of the kMaxSpanTiles 16-frame tiles of a span (a span is <= 128 frames of one utterance), dealt out
+  // round-robin: ~20 units per CTA on cfg2, so the last round costs a few per cent (whole spans: 3 per CTA, +30 %)
+  const int n_units = P.n_spans * kMaxSpanTiles;
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    const int ch = u / P.n_spans, si = u - ch * P.n_spans;     // tile-major: the live units (spans may hold fewer than 8 tiles) stay contiguous in u
     const Span sp = P.spans[si];
-    if (sp.nframes == 0) {        // pad_sequence's zero rows (ref: lid/raw_datasets.py:347-350)
-      const long long total = static_cast<long long>(sp.aux) * P.n_out;
-      for (long long i = tid; i < total; i += kPThreads) {
-        const long long r = i / P.n_out;
-        P.out[(sp.out_row + r) * P.out_ld + (i - r * P.n_out)] = 0.f;
-      }
+    if (sp.nframes == 0) {        // pad_sequence's zero rows (ref: lid/raw_datasets.py:347-350), an eighth of them per unit
+      const int r0 = static_cast<int>(static_cast<long long>(sp.aux) * ch / kMaxSpanTiles);
+      const int r1 = static_cast<int>(static_cast<long long>(sp.aux) * (ch + 1) / kMaxSpanTiles);
+      for (int r = r0; r < r1; ++r)
+        for (int d = tid; d < P.n_out; d += kPThreads) P.out[(sp.out_row + r) * P.out_ld + d] = 0.f;
       continue;
     }
-    for (int f0 = 0; f0 < sp.nframes; f0 += kPHalfWarps) {
-      const bool active = f0 + hw < sp.nframes;
-      const int f = active ? f0 + hw : sp.nframes - 1;
+    const int fbeg = ch * kTileFrames;
+    if (fbeg >= sp.nframes) continue;
+    const int fend = min(sp.nframes, fbeg + kTileFrames);
+    double ssum[kBands], qsum[kBands];      // this lane's share of the unit's sums (dims t + 16 b, frames of its half-warp)
+#pragma unroll
+    for (int b = 0; b < kBands; ++b) ssum[b] = qsum[b] = 0.0;
+    for (int f0 = fbeg; f0 < fend; f0 += kPHalfWarps) {
+      const bool active = f0 + hw < fend;
+      const int f = active ? f0 + hw : fend - 1;
       const TIn* const x = wav + sp.wav_off + static_cast<long long>(kFrameShift) * f;
 
       // ---- framing in fp64: DC removal, pre-emphasis with replicate-left, window (ta: compliance/kaldi.py:183-204) ----
@@ -138,7 +174,12 @@ __global__ void __launch_bounds__(kPThreads) fbank_precise_kernel(const PreciseP
         const bool valid = (j < 12 || t < 8);
         a0[j] = valid ? ld_sample<TIn>(x + 2 * n, P.in_scale) : 0.0;
         a1[j] = valid ? ld_sample<TIn>(x + 2 * n + 1, P.in_scale) : 0.0;
-        pm[j] = valid ? ld_sample<TIn>(x + (n == 0 ? 0 : 2 * n - 1), P.in_scale) : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 13; ++j) {      // x[2n - 1] sits in lane t - 1 (lane 15 of the previous j for t = 0); x[-1] := x[0]
+        const double send = (t == 15) ? (j ? a1[j - 1] : 0.0) : a1[j];
+        pm[j] = __shfl_sync(0xffffffffu, send, up_lane);
+        if (j == 0 && t == 0) pm[j] = a0[0];
       }
       double mean = 0.0;
       if (P.remove_dc) {
@@ -153,8 +194,8 @@ __global__ void __launch_bounds__(kPThreads) fbank_precise_kernel(const PreciseP
       for (int j = 0; j < 13; ++j) {
         const int n = t + 16 * j;
         const bool valid = (j < 12 || t < 8);
-        const double w0 = valid ? static_cast<double>(__ldg(P.window + 2 * n)) : 0.0;
-        const double w1 = valid ? static_cast<double>(__ldg(P.window + 2 * n + 1)) : 0.0;
+        const double2 w = valid ? *reinterpret_cast<const double2*>(sm_win + 2 * n) : make_double2(0.0, 0.0);
+        const double w0 = w.x, w1 = w.y;
         const double e = a0[j] - mean, o = a1[j] - mean, p = pm[j] - mean;
         R[j] = (e - cpre * p) * w0;
         I[j] = (o - cpre * e) * w1;
@@ -215,10 +256,17 @@ __global__ void __launch_bounds__(kPThreads) fbank_precise_kernel(const PreciseP
         double v = 0.0;
         val[b] = 0.f;
         if (m < P.n_mels) {
-          const int2 rg = __ldg(P.mel_range + m);
-          const float* wrow = P.melbank + static_cast<long long>(m) * kBins;
-          double E = 0.0;
-          for (int k = rg.x; k < rg.y; ++k) E = fma(static_cast<double>(__ldg(wrow + k)), Pw[k], E);
+          const int4 rg = sm_melr[m];
+          const double* wrow = sm_melw + rg.z;
+          const double* prow = Pw + rg.x;
+          double E0 = 0.0, E1 = 0.0;
+          int k = 0;
+          for (; k + 1 < rg.y; k += 2) {
+            E0 = fma(wrow[k], prow[k], E0);
+            E1 = fma(wrow[k + 1], prow[k + 1], E1);
+          }
+          if (k < rg.y) E0 = fma(wrow[k], prow[k], E0);
+          const double E = E0 + E1;
           const bool floored = !(E > static_cast<double>(P.log_floor));
           v = floored ? static_cast<double>(P.log_of_floor) : log(E);
           val[b] = floored ? P.log_of_floor : static_cast<float>(v);
@@ -245,28 +293,33 @@ __global__ void __launch_bounds__(kPThreads) fbank_precise_kernel(const PreciseP
           const int d = t + 16 * b;
           if (d < P.n_out) {
             orow[d] = val[b];
-            if (stats) {
-              const double xv = static_cast<double>(val[b]);
-              atomicAdd(&sm_acc[d], xv);
-              atomicAdd(&sm_acc[kMaxMels + d], xv * xv);
-            }
+            const double xv = static_cast<double>(val[b]);
+            ssum[b] += xv;
+            qsum[b] = fma(xv, xv, qsum[b]);
           }
         }
       }
       __syncwarp();       // the power bins / log-mels have been read: the plane is free for the next frame
     }
     if (stats) {
+      // the half-warps park their sums in their (now idle) planes; 160 threads-worth of adds, then one atomic per dim
+#pragma unroll
+      for (int b = 0; b < kBands; ++b) {
+        Pw[t + 16 * b] = ssum[b];
+        Pw[kMaxMels + t + 16 * b] = qsum[b];
+      }
       __syncthreads();
       for (int e = tid; e < 2 * kMaxMels; e += kPThreads) {
         const int which = e / kMaxMels, d = e - which * kMaxMels;
-        const double a = sm_acc[e];
-        sm_acc[e] = 0.0;
+        double a = 0.0;
+#pragma unroll
+        for (int h = 0; h < kPHalfWarps; ++h) a += reinterpret_cast<const double*>(sm_plane + h * kPPlane)[e];
         if (d < P.n_out && a != 0.0) {
           if (P.mode == 1) atomicAdd(P.utt_stats + (static_cast<long long>(sp.utt) * 2 + which) * P.n_out + d, a);
           else atomicAdd(P.stats_out + which * P.n_out + d, a);
         }
       }
-      if (P.mode == 3 && tid == 0) atomicAdd(P.stats_out + 2 * P.n_out, static_cast<double>(sp.nframes));
+      if (P.mode == 3 && tid == 0) atomicAdd(P.stats_out + 2 * P.n_out, static_cast<double>(fend - fbeg));
       __syncthreads();
     }
   }
