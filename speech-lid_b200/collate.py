@@ -46,10 +46,11 @@ class DeviceCollate:
         if len(batch) == 0:
             raise ValueError("empty batch")
         wavs: List[torch.Tensor] = [item[0][0] if item[0].dim() == 2 else item[0] for item in batch]   # channel 0
-        frames = [self.frontend.num_frames(int(w.shape[-1])) for w in wavs]
-        masks: Optional[torch.Tensor] = None
+        masks = None
         if self.train and self.mask_times > 0:
-            masks = draw_masks(frames, self.frontend.n_out, self.t_mask, self.f_mask, self.mask_times)
+            # drawn inside featurize once the H2D copies of the waveforms are under way (same RNG consumption)
+            def masks(frames):
+                return draw_masks(frames, self.frontend.n_out, self.t_mask, self.f_mask, self.mask_times)
         feats, wav_percents = self.frontend.featurize(wavs, masks=masks, cmvn=self.cmvn, cache_plan=False)
         texts, text_percents, audio_paths, langs = collate_host_part(batch, self.lang2index)
         return feats, texts, wav_percents.to(torch.float32).cpu(), text_percents, audio_paths, langs

@@ -31,6 +31,14 @@ def _ll_array(values: Sequence[int]):
 
 
 @dataclass
+class _Layout:
+    """What ``FrontEnd.pack`` needs of a plan: where every utterance goes in the packed buffer."""
+    lengths: List[int]
+    offsets: List[int]
+    total_samples: int
+
+
+@dataclass
 class Plan:
     """Segment-offset table of one batch (host copy + the device-side tile table inside ``handle``)."""
     handle: int
@@ -386,6 +394,10 @@ class FrontEnd:
         if masks is not None:
             if masks.dtype != torch.int32 or masks.dim() != 3 or masks.shape[0] != plan.batch or masks.shape[2] != 4:
                 raise ValueError("masks must be int32 [B, n_masks, 4]")
+            if not masks.is_cuda:
+                # pinned + non-blocking: a pageable copy would hold the host until everything queued ahead of it on the
+                # stream (the waveforms' H2D copies) has drained
+                masks = masks.contiguous().pin_memory().to(self.device, non_blocking=True)
             masks = masks.to(self.device).contiguous()
             n_masks = masks.shape[1]
             if n_masks == 0:
@@ -545,10 +557,26 @@ class FrontEnd:
         (ref: lid/raw_datasets.py:345-365).  ``feats`` stays on the device -- that is where the model consumes it.
         ``cache_plan=False`` (ragged training batches: every batch has its own length signature): the plan is built for
         this call and handed straight back to the handle's pool -- the pool re-uses its block only after the work
-        launched here has finished (an event per block), so nothing is allocated or freed in steady state."""
+        launched here has finished (an event per block), so nothing is allocated or freed in steady state.
+        ``masks`` may be a callable ``frames -> int32 [B, n_masks, 4]``: it is evaluated after the H2D copies have been
+        issued (``DeviceCollate`` draws its SpecAugment bounds this way, under the DMA)."""
         lengths = [int(w.shape[-1]) for w in wavs]
-        plan = self.cached_plan(lengths, padded=padded) if cache_plan else self.make_plan(lengths, padded=padded)
-        packed = self.pack(wavs, plan)
+        if cache_plan:
+            plan = self.cached_plan(lengths, padded=padded)
+            packed = self.pack(wavs, plan)
+        else:
+            # ship first, plan afterwards: the layout (16-byte aligned prefix sums) is all the packer needs, so the H2D
+            # copies are already running while the host fills the plan tables and draws the masks
+            if lengths and min(lengths) < self.frame_len:
+                _lib.check(_lib.E_SHORT)
+            offsets, pos = [], 0
+            for n in lengths:
+                offsets.append(pos)
+                pos += (n + self.align - 1) // self.align * self.align
+            packed = self.pack(wavs, _Layout(lengths=lengths, offsets=offsets, total_samples=pos))
+            plan = self.make_plan(lengths, padded=padded, offsets=offsets)
+        if callable(masks):
+            masks = masks(plan.frames)
         out = self.featurize_packed(packed, plan, masks=masks, cmvn=cmvn)
         percents = plan.wav_percents
         if not cache_plan:
