@@ -136,6 +136,26 @@ def run_cpu_single_core(n_utts=4, n_samples=N_SAMPLES):
     return n_utts * n_samples / SR / times[1]
 
 
+_JSON_OUT = None
+
+
+def keep_stdout_clean():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+    collective): file descriptor 1 is pointed at stderr for the whole run and the line goes out through a private
+    duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def config_dict(world):
     """Identical in both arms."""
     return {"workload": WORKLOAD, "utterances_per_gpu": B_UTTS, "samples_per_utterance": N_SAMPLES,
@@ -556,7 +576,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -646,7 +666,7 @@ def run_reference_arm(args):
                              "sample": "every step = the full 256 x 8-s batch split over %d single-thread worker "
                                        "processes; per utterance: %s + CMVN" % (cores, _reference_path()[2])},
             "e2e": {"value": round(v, 1), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -658,6 +678,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    keep_stdout_clean()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
