@@ -40,5 +40,15 @@ ms.featurize(wavs, masks=masks)
 
 i16 = lid.FrontEnd(n_mels=80, in_dtype=torch.int16, in_scale=1.0 / 32768.0)
 i16.featurize([(w * 3000).clamp(-32768, 32767).to(torch.int16) for w in wavs])
+
+pr = lid.FrontEnd(n_mels=80, precise=True)           # float64 kernel (lidfe_fbank_precise.cuh)
+pr.featurize(wavs)
+pr.featurize(wavs, masks=masks, cmvn="utt")
+pr.featurize(wavs, padded=False)
+pstats = torch.zeros(161, dtype=torch.float64, device="cuda")
+pplan = pr.make_plan(lens, padded=False)
+pr.featurize_packed(pr.pack(wavs, pplan), pplan, cmvn="global_accum", stats_out=pstats)
+lid.FrontEnd(n_mels=80, n_ceps=40, precise=True).featurize(wavs)
+lid.FrontEnd(n_mels=23, n_ceps=13, preemph=0.97, precise=True).featurize(wavs)
 torch.cuda.synchronize()
 print("sanitize_case ok, launches", lid.load_library().lidfe_launch_count())
