@@ -19,6 +19,7 @@
 #include "lidfe_resample_tc.cuh"
 #include "lidfe_stft_fbank.cuh"
 #include "lidfe_fbank_precise.cuh"
+#include "lidfe_mfcc_mma.cuh"
 
 using namespace lidfe;
 
@@ -85,6 +86,7 @@ struct lidfe_ctx {
   int prof_used;
   int prof_stride;   // bracket every prof_stride-th featurize call (event records between kernels cost a few us)
   int prof_calls;
+  int dct_mma;     // two-kernel MFCC path: DCT on the tensor cores (lidfe_mfcc_mma.cuh) when the shapes fit; LIDFE_DCT_MMA=0 disables
   // precise mode (lidfe_set_precision, lidfe_fbank_precise.cuh): fp64 arithmetic on the reference's fp32 tables
   int precise;
   std::vector<float>* melbank_host;   // the dense bank lidfe_create was given (uploaded when precise mode is first selected)
@@ -707,6 +709,10 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
                            static_cast<size_t>(cfg->n_mels) * kDctMaxCeps + kDctMaxCeps + 2 * kDctMaxCeps) * sizeof(float);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(mfcc_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->smem_bytes_dct));
+      c->dct_mma = (cfg->n_mels % 8 == 0) ? 1 : 0;
+      if (const char* env = getenv("LIDFE_DCT_MMA")) c->dct_mma = c->dct_mma && atoi(env) != 0;
+      if (e == cudaSuccess && c->dct_mma)
+        e = cudaFuncSetAttribute(mfcc_dct_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmSmemBytes);
     }
     fbank_fn fn = pick_kernel(c);
     if (e == cudaSuccess)
@@ -1534,7 +1540,15 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     long long groups = (p->n_tiles + 3) / 4;
     long long gd = groups < static_cast<long long>(h->num_sms) * 4 ? groups : static_cast<long long>(h->num_sms) * 4;
     if (gd < 1) gd = 1;
-    mfcc_dct_kernel<<<static_cast<unsigned>(gd), kDctThreads, h->smem_bytes_dct, st>>>(D);
+    if (h->dct_mma) {
+      // tensor-core DCT: every warp walks its own contiguous range of tiles; 2 CTAs of 8 warps per SM
+      long long gm = (p->n_tiles + kMmTM * kMmWarps - 1) / (kMmTM * kMmWarps);
+      if (gm > static_cast<long long>(h->num_sms) * 2) gm = static_cast<long long>(h->num_sms) * 2;
+      if (gm < 1) gm = 1;
+      mfcc_dct_mma_kernel<<<static_cast<unsigned>(gm), kMmThreads, kMmSmemBytes, st>>>(D);
+    } else {
+      mfcc_dct_kernel<<<static_cast<unsigned>(gd), kDctThreads, h->smem_bytes_dct, st>>>(D);
+    }
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(p->blk->ev, st));
