@@ -89,9 +89,7 @@ struct lidfe_ctx {
   int dct_mma;     // two-kernel MFCC path: DCT on the tensor cores (lidfe_mfcc_mma.cuh) when the shapes fit; LIDFE_DCT_MMA=0 disables
   // precise mode (lidfe_set_precision, lidfe_fbank_precise.cuh): fp64 arithmetic on the reference's fp32 tables
   int precise;
-  std::vector<float>* melbank_host;   // the dense bank lidfe_create was given (uploaded when precise mode is first selected)
-  float* d_melbank;                   // [n_mels][257]
-  int2* d_mel_range;                  // [n_mels] non-zero range of every filter
+  int k0_off, melw_off, total_taps;   // the segment-form mel plan inside the blob (the precise kernel reads it from there)
 };
 
 struct lidfe_plan_s {
@@ -594,11 +592,6 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   memset(c, 0, sizeof(*c));
   c->cfg = *cfg;
   c->n_out = cfg->n_ceps > 0 ? cfg->n_ceps : cfg->n_mels;
-  c->melbank_host = new (std::nothrow) std::vector<float>(melbank_host, melbank_host + static_cast<size_t>(cfg->n_mels) * kBins);
-  if (!c->melbank_host) {
-    delete c;
-    return LIDFE_E_NOMEM;
-  }
 
   // ---- dense bank -> segment plan (see build_mel_plan).  The kernel leaves the power bins scaled by 4 (it skips the
   //      1/2 of the real-FFT split), so the weights carry the exact factor 1/4.
@@ -606,7 +599,6 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   {
     const int rc = build_mel_plan(cfg->n_mels, melbank_host, mp);
     if (rc != LIDFE_OK) {
-      delete c->melbank_host;
       delete c;
       return rc;
     }
@@ -657,7 +649,10 @@ int lidfe_create(lidfe_handle* out, const lidfe_config* cfg, const float* window
   append(window.data(), window.size() * sizeof(float));
   append(tw1.data(), tw1.size() * sizeof(float2));
   append(tw2.data(), tw2.size() * sizeof(float2));
+  c->k0_off = static_cast<int>(blob.size());
   append(k0.data(), static_cast<size_t>(kMaxMels) * sizeof(int));
+  c->melw_off = static_cast<int>(blob.size());
+  c->total_taps = total_taps;
   if (total_taps > 0) append(melw.data(), static_cast<size_t>(total_taps) * 32 * sizeof(float));
   c->blob_bytes_fbank = static_cast<int>(blob.size());
   if (cfg->n_ceps > 0) {
@@ -775,9 +770,6 @@ static void free_block(PlanBlock* b) {
 
 static void destroy_now(lidfe_ctx* h) {
   cudaFree(h->d_blob);
-  cudaFree(h->d_melbank);
-  cudaFree(h->d_mel_range);
-  delete h->melbank_host;
   if (h->pool) {
     for (PlanBlock* b : *h->pool) free_block(b);
     delete h->pool;
@@ -1419,8 +1411,10 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     Q.spans = p->d_spans;
     Q.n_spans = static_cast<int>(p->n_spans);
     Q.window = reinterpret_cast<const float*>(h->d_blob);
-    Q.melbank = h->d_melbank;
-    Q.mel_range = h->d_mel_range;
+    Q.mel_k0 = reinterpret_cast<const int*>(h->d_blob + h->k0_off);
+    Q.mel_w = reinterpret_cast<const float*>(h->d_blob + h->melw_off);
+    for (int b = 0; b < kBands; ++b) Q.band_taps[b] = h->band_taps[b];
+    Q.total_taps = h->total_taps;
     Q.dct = h->cfg.n_ceps > 0 ? reinterpret_cast<const float*>(h->d_blob + h->dct_off) : nullptr;
     Q.lifter = h->cfg.n_ceps > 0 ? reinterpret_cast<const float*>(h->d_blob + h->lifter_off) : nullptr;
     Q.n_mels = h->cfg.n_mels;
@@ -1627,28 +1621,12 @@ int lidfe_set_precision(lidfe_handle h, int precise) {
   if (precise) {
     // scope of fbank_precise_kernel: the reference's Kaldi call and its relatives
     if (h->cfg.framing != LIDFE_FRAMING_KALDI || h->cfg.log_kind != LIDFE_LOG_NATURAL || h->cfg.dither != 0.f) return LIDFE_E_CONFIG;
-    if (!h->d_melbank) {
-      const int n_mels = h->cfg.n_mels;
-      std::vector<int2> range(n_mels);
-      for (int m = 0; m < n_mels; ++m) {
-        int lo = kBins, hi = 0;
-        for (int k = 0; k < kBins; ++k)
-          if ((*h->melbank_host)[static_cast<size_t>(m) * kBins + k] != 0.f) { if (k < lo) lo = k; hi = k + 1; }
-        if (hi == 0) lo = 0;
-        range[m] = make_int2(lo, hi);
-      }
-      cudaError_t e = cudaFuncSetAttribute(fbank_precise_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
-      long long nz = 0;
-      for (const int2& r : range) nz += r.y - r.x;
-      if (nz > kPMelW) return LIDFE_E_MELBANK;
-      if (e == cudaSuccess) e = upload(&h->d_melbank, h->melbank_host->data(), h->melbank_host->size());
-      if (e == cudaSuccess) e = upload(&h->d_mel_range, range.data(), range.size());
-      if (e == cudaSuccess) e = cudaDeviceSynchronize();     // landed whatever stream the caller launches on
-      if (e != cudaSuccess) {
-        cudaGetLastError();
-        return static_cast<int>(e);
-      }
+    if (h->total_taps > kPMaxTaps) return LIDFE_E_MELBANK;
+    cudaError_t e = cudaFuncSetAttribute(fbank_precise_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return static_cast<int>(e);
     }
   }
   h->precise = precise;

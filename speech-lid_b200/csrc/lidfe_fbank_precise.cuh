@@ -12,8 +12,8 @@
 // Same decomposition as the fast kernels -- the 512-point real FFT as a 256-point complex FFT of z[n] = x[2n] + i x[2n+1],
 // 16 x 16 with an in-register radix-4 x 4 DFT per lane, one transposition through shared memory, real-FFT split by
 // shuffles between lane t and lane 16 - t -- but one frame per half-warp in doubles instead of a frame pair in packed
-// floats, the dense mel bank row by row over its non-zero range, libdevice's log.  B200's FP64 pipe runs DFMA at half
-// the FFMA rate (tools/ubench.cu: 62.5 against 120 lane-ops/clk/SM), so this is a 3-4 x slower kernel, not a 30 x one.
+// floats, the mel bank in the fast kernels' segment form with fp64 accumulation, libdevice's log.  B200's FP64 pipe runs DFMA at half
+// the FFMA rate (tools/ubench.cu: 62.5 against 120 lane-ops/clk/SM), so this is a 3-4 x slower kernel, not a 30 x one (measured: 340 us against 100 us per 256 x 8 s).
 // Scope: KALDI framing, natural log, float32 / int16 input, fbank or MFCC output, every CMVN mode but top_db
 // (statistics are taken here, the normalisation / masks run in cmvn_apply_kernel as for the fast path).
 #pragma once
@@ -28,8 +28,10 @@ struct PreciseParams {
   const Span* spans;
   int n_spans;
   const float* window;      // [400]                      the handle's fp32 window (blob offset 0)
-  const float* melbank;     // [n_mels][257]              the dense fp32 bank lidfe_create was given
-  const int2* mel_range;    // [n_mels]                   (first non-zero bin, one past the last)
+  const int* mel_k0;        // [80]                       the handle's segment-form mel plan (build_mel_plan, lidfe_abi.cu):
+  const float* mel_w;       // [total_taps][16][2]        per lane its first power bin and per step the (own, next) weights,
+  int band_taps[kBands];    //                            x 0.25 (the power bins are left scaled by 4) -- exact in any precision
+  int total_taps;
   const float* dct;         // [n_mels][n_ceps] or NULL
   const float* lifter;      // [n_ceps]
   int n_mels, n_ceps, n_out;
@@ -92,23 +94,25 @@ __device__ __forceinline__ double ld_sample<short>(const short* p, float scale) 
   return static_cast<double>(static_cast<float>(__ldg(p)) * scale);      // the fp32 product torchaudio.load forms (exact for 2^-15)
 }
 
-// dynamic shared memory: tw[256] double2 | window[400] double | mel weights (compact rows) [kPMelW] double |
-// mel (first bin, count, offset) [80] int4 | acc[160] double | planes
-constexpr int kPMelW = 640;        // >= the non-zeros of a bank in which every bin feeds at most two filters (build_mel_plan insists)
-constexpr int kPOffWin = 256 * 16;
+// dynamic shared memory: tw1[16][16] double2 (stage twiddles W256^(K1 t), lane-major: conflict-free) | tw2[128] double2
+// (split twiddles W512^k) | window[400] double | mel plan weights [kPMaxTaps][16] float2 | mel first bins [80] int | planes
+constexpr int kPMaxTaps = 64;      // steps of the segment plan summed over the five bands (Kaldi-80: 23)
+constexpr int kPMelW = kPMaxTaps * 16;
+constexpr int kPOffTw2 = 256 * 16;
+constexpr int kPOffWin = kPOffTw2 + 128 * 16;
 constexpr int kPOffMelW = kPOffWin + 400 * 8;
 constexpr int kPOffMelR = kPOffMelW + kPMelW * 8;
-constexpr int kPOffAcc = kPOffMelR + kMaxMels * 16;
-constexpr int kPOffPlane = kPOffAcc + 2 * kMaxMels * 8;
+constexpr int kPOffPlane = kPOffMelR + kMaxMels * 4 + 64;
 constexpr int kPSmemBytes = kPOffPlane + kPHalfWarps * kPPlane * 16;
 
 template <typename TIn>
 __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_kernel(const PreciseParams P) {
   extern __shared__ __align__(16) unsigned char psmem[];
-  double2* const sm_tw = reinterpret_cast<double2*>(psmem);                        // W512^k = (cos, -sin)(2 pi k / 512), k = 0..255
+  double2* const sm_tw1 = reinterpret_cast<double2*>(psmem);                       // [K1][t]: W256^(K1 t) = (cos, -sin)(2 pi K1 t / 256)
+  double2* const sm_tw2 = reinterpret_cast<double2*>(psmem + kPOffTw2);            // W512^k = (cos, -sin)(2 pi k / 512), k = 0..127
   double* const sm_win = reinterpret_cast<double*>(psmem + kPOffWin);
-  double* const sm_melw = reinterpret_cast<double*>(psmem + kPOffMelW);
-  int4* const sm_melr = reinterpret_cast<int4*>(psmem + kPOffMelR);                // (first bin, bins, offset into sm_melw, -)
+  float2* const sm_melw = reinterpret_cast<float2*>(psmem + kPOffMelW);            // [step][lane] (own, next) weights
+  int* const sm_k0 = reinterpret_cast<int*>(psmem + kPOffMelR);                    // [80] first power bin of lane t, band b
   double2* const sm_plane = reinterpret_cast<double2*>(psmem + kPOffPlane);
 
   const int tid = threadIdx.x, lane = tid & 31, t = lane & 15;
@@ -122,20 +126,21 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
 
   for (int k = tid; k < 256; k += kPThreads) {
     double s, c;
-    sincospi(static_cast<double>(k) / 256.0, &s, &c);
-    sm_tw[k] = make_double2(c, -s);
-  }
-  for (int k = tid; k < kFrameLen; k += kPThreads) sm_win[k] = static_cast<double>(__ldg(P.window + k));
-  if (tid < 32) {     // compact rows of the dense bank: warp 0 lays the filters out one after the other
-    int off = 0;
-    for (int m = 0; m < P.n_mels; ++m) {
-      const int2 rg = __ldg(P.mel_range + m);
-      const int cnt = rg.y - rg.x;
-      for (int k = lane; k < cnt; k += 32) sm_melw[off + k] = static_cast<double>(__ldg(P.melbank + static_cast<long long>(m) * kBins + rg.x + k));
-      if (lane == 0) sm_melr[m] = make_int4(rg.x, cnt, off, 0);
-      off += cnt;
+    sincospi(static_cast<double>((k >> 4) * (k & 15)) / 128.0, &s, &c);
+    sm_tw1[k] = make_double2(c, -s);
+    if (k < 128) {
+      sincospi(static_cast<double>(k) / 256.0, &s, &c);
+      sm_tw2[k] = make_double2(c, -s);
     }
   }
+  for (int k = tid; k < kFrameLen; k += kPThreads) sm_win[k] = static_cast<double>(__ldg(P.window + k));
+  for (int e = tid; e < P.total_taps * 16; e += kPThreads) sm_melw[e] = __ldg(reinterpret_cast<const float2*>(P.mel_w) + e);
+  for (int e = tid; e < kMaxMels; e += kPThreads) sm_k0[e] = __ldg(P.mel_k0 + e);
+  int tap_off[kBands + 1];
+  tap_off[0] = 0;
+#pragma unroll
+  for (int b = 0; b < kBands; ++b) tap_off[b + 1] = tap_off[b] + P.band_taps[b];
+  const int src = (lane & 16) | ((t - 1) & 15);
   __syncthreads();
 
   const double cpre = static_cast<double>(P.preemph);
@@ -208,9 +213,7 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
 #pragma unroll
       for (int p = 1; p < 16; ++p) {
         const int K1 = rev4(p);
-        const int idx = 2 * K1 * t;                          // W256^(K1 t) = W512^(2 K1 t), 2 K1 t <= 450; W512^(k + 256) = -W512^k
-        double2 w = sm_tw[idx & 255];
-        if (idx & 256) { w.x = -w.x; w.y = -w.y; }
+        const double2 w = sm_tw1[K1 * 16 + t];
         cmuld(R[p], I[p], w.x, w.y);
         X_pl[K1 * kPRow + t] = make_double2(R[p], I[p]);
       }
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
       __syncwarp();       // every lane has read its row: the plane takes the power bins now
 
       // ---- real-FFT split + |X|^2 -----------------------------------------------------------------------------------
-      if (t == 0) Pw[128] = R[2] * R[2] + I[2] * I[2];
+      if (t == 0) Pw[128] = 4.0 * (R[2] * R[2] + I[2] * I[2]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int ps = rev4(15 - i);
@@ -240,33 +243,37 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
         const double e2r = ar + br, e2i = ai - bi;
         double o2r = ai + bi, o2i = br - ar;
         const int k = t + 16 * i;
-        const double2 w = sm_tw[k];
+        const double2 w = sm_tw2[k];
         cmuld(o2r, o2i, w.x, w.y);
         const double xar = e2r + o2r, xai = e2i + o2i, xbr = e2r - o2r, xbi = e2i - o2i;
-        Pw[k] = 0.25 * (xar * xar + xai * xai);
-        Pw[256 - k] = 0.25 * (xbr * xbr + xbi * xbi);
+        Pw[k] = xar * xar + xai * xai;              // 4 |X[k]|^2: the plan's weights carry the 1/4
+        Pw[256 - k] = xbr * xbr + xbi * xbi;
       }
       __syncwarp();
 
-      // ---- mel (dense rows over their non-zero range), log, optional DCT-II + lifter; ONE rounding, at the store --------
+      // ---- mel in segment form (lane t of band b walks the bins between the centres of filters m = t + 16 b and m + 1 once:
+      //      the down-slope share of its own filter and the up-slope share of the next one, handed one lane up; the same
+      //      conflict-free plan as the fast kernels), log, optional DCT-II + lifter; ONE rounding, at the store -----------
       float val[kBands];
+      double carry15 = 0.0;
 #pragma unroll
       for (int b = 0; b < kBands; ++b) {
         const int m = t + 16 * b;
+        double own = 0.0, nxt = 0.0;
+        const double* pp = Pw + sm_k0[m];
+        const float2* wp = sm_melw + tap_off[b] * 16 + t;
+        for (int i = 0; i < P.band_taps[b]; ++i) {
+          const double p = pp[i];
+          const float2 w = wp[i * 16];
+          own = fma(p, static_cast<double>(w.x), own);
+          nxt = fma(p, static_cast<double>(w.y), nxt);
+        }
+        const double got = __shfl_sync(0xffffffffu, nxt, src);
+        const double E = own + (t == 0 ? carry15 : got);
+        carry15 = got;
         double v = 0.0;
         val[b] = 0.f;
         if (m < P.n_mels) {
-          const int4 rg = sm_melr[m];
-          const double* wrow = sm_melw + rg.z;
-          const double* prow = Pw + rg.x;
-          double E0 = 0.0, E1 = 0.0;
-          int k = 0;
-          for (; k + 1 < rg.y; k += 2) {
-            E0 = fma(wrow[k], prow[k], E0);
-            E1 = fma(wrow[k + 1], prow[k + 1], E1);
-          }
-          if (k < rg.y) E0 = fma(wrow[k], prow[k], E0);
-          const double E = E0 + E1;
           const bool floored = !(E > static_cast<double>(P.log_floor));
           v = floored ? static_cast<double>(P.log_of_floor) : log(E);
           val[b] = floored ? P.log_of_floor : static_cast<float>(v);

@@ -103,7 +103,7 @@ class FrontEnd:
         by (seed, utterance, sample); 0 is the reference's ``wav2mel`` (its kaldi call passes dither=0.0, :57).
         ``precise=True`` (kaldi branch): the same formula evaluated in float64 on the same fp32 tables and rounded once
         (``lidfe_set_precision``): at least as close to the fp64 truth as the reference's own fp32 result on every mel
-        bin, at about 4 x the time of the default fast fp32 kernels."""
+        bin, at about 3 x the time of the default fast fp32 kernels."""
         if kind not in ("kaldi", "melspec_db"):
             raise ValueError("kind must be 'kaldi' or 'melspec_db'")
         self.kind = kind
