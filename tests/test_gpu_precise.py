@@ -142,3 +142,23 @@ def test_precise_scope_errors(lid):
         lid.FrontEnd(kind="melspec_db", precise=True)
     with pytest.raises(RuntimeError):
         lid.FrontEnd(dither=1e-5, precise=True)
+
+
+@gpu
+def test_dropin_wav2mel_kaldi_runs_precise(lid, fep):
+    """The single-utterance drop-in ``wav2mel(x, use_kaildi=True)`` (ref: lid/audio_processor.py:8-69) is latency-bound, so it
+    runs the float64 kernel: its output is the precise FrontEnd's, and per mel bin never further from the fp64 truth
+    than 1.5 x the reference's own fp32 result."""
+    import speech_lid_b200.audio_processor as ap
+    assert ap.PRECISE_DROPIN
+    for s in range(4):
+        w = O.synth_noise(48000, 500 + s)
+        got = ap.wav2mel(w, use_kaildi=True)                      # (1, 80, T) on the host
+        assert got.shape[0] == 1 and got.shape[1] == 80 and not got.is_cuda
+        mine = got[0].transpose(0, 1)
+        want, _ = fep.featurize([w])
+        assert torch.equal(mine, want[0, :mine.shape[0]].cpu())
+        ref, tru = O.kaldi_fbank(w), O.truth64_fbank(w)
+        eg = (mine.double() - tru).abs().max(0).values
+        er = (ref.double() - tru).abs().max(0).values
+        assert bool((eg <= 1.5 * er).all())
