@@ -381,6 +381,9 @@ class FrontEnd:
             cmvn = "topdb"
         elif cmvn == "topdb":
             raise ValueError("cmvn='topdb' belongs to kind='melspec_db'")
+        if raw and getattr(self, "precise", False):
+            raise ValueError("precise=True does not serve the fused normalize_wav load (raw=True): normalise with "
+                             "wave_stages first, or use the default arithmetic")
         if packed.dtype != self.in_dtype or not packed.is_cuda or not packed.is_contiguous():
             raise ValueError("packed must be a contiguous CUDA tensor of dtype %s" % self.in_dtype)
         if packed.numel() < plan.total_samples:
