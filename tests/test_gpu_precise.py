@@ -162,3 +162,37 @@ def test_dropin_wav2mel_kaldi_runs_precise(lid, fep):
         eg = (mine.double() - tru).abs().max(0).values
         er = (ref.double() - tru).abs().max(0).values
         assert bool((eg <= 1.5 * er).all())
+
+
+@gpu
+def test_precise_random_ragged_batches(lid, fep):
+    """Seeded random sweep over the precise kernel's scheduling (16-frame units dealt out tile-major, zero-fill spans cut
+    in eighths, one-frame utterances, long utterances spanning many spans; padded and packed): every row equals the fp64
+    truth rounded once, every padding row is zero, statistics-mode output equals the raw output."""
+    g = torch.Generator().manual_seed(2024)
+    for trial in range(6):
+        B = int(torch.randint(1, 13, (1,), generator=g))
+        lens = [int(v) for v in torch.randint(400, 60000, (B,), generator=g)]
+        if trial == 0:
+            lens[0] = 400                       # exactly one frame
+        if trial == 1:
+            lens[-1] = 400 + 160 * 700          # 701 frames: several spans
+        wavs = [O.synth_noise(n, 900 + 37 * trial + i) for i, n in enumerate(lens)]
+        padded = bool(trial % 2 == 0)
+        plan = fep.make_plan(lens, padded=padded)
+        packed = fep.pack(wavs, plan)
+        out = fep.featurize_packed(packed, plan).cpu()
+        stats = torch.zeros(161, dtype=torch.float64, device=fep.device)
+        out_acc = fep.featurize_packed(packed, plan, cmvn="global_accum", stats_out=stats).cpu()
+        assert torch.equal(out, out_acc)
+        rows = 0
+        for i, w in enumerate(wavs):
+            tru = O.truth64_fbank(w)
+            T = tru.shape[0]
+            got = out[i, :T] if padded else out[plan.out_rows[i]:plan.out_rows[i] + T]
+            assert float((got.double() - tru).abs().max()) <= 1.0e-6, (trial, i, lens[i])
+            if padded:
+                assert torch.all(out[i, T:] == 0)
+            rows += T
+        assert float(stats[160]) == rows
+        plan.close()
