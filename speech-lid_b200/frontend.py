@@ -301,7 +301,9 @@ class FrontEnd:
                 w = w.to(self.in_dtype).contiguous()
             host.append(w)
         cur = torch.cuda.current_stream(self.device)
-        if pinned is None and all(w.is_pinned() for w in host):
+        # (is_pinned() is a driver query per tensor: the first and the last item decide -- a DataLoader pins all of a
+        # batch or none; a pageable straggler would still be copied correctly by cudaMemcpyAsync, only synchronously)
+        if pinned is None and host[0].is_pinned() and host[-1].is_pinned():
             # already pinned (DataLoader(pin_memory=True)): no staging copy, one async copy per utterance straight to its
             # place; the sources are kept referenced until the stream has passed the copies
             keep = self.__dict__.setdefault("_h2d_keep", [])
