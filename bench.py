@@ -443,7 +443,7 @@ def run_gpu_arm(args):
         dist.all_reduce(ta)
     ragged = {"value": round(float(ta.item()) / rag_sec, 1), "unit": "audio-s/s", "steps": 2 * n_rag,
               "utterances_per_step": B_UTTS, "lengths": "U[1 s, 20 s], a new draw every step",
-              "note": "DeviceCollate: plan + pack + H2D (pinned items: one async copy per utterance, no staging) + fused kernel + D2H read, per step"}
+              "note": "DeviceCollate: H2D first (pinned items: zero-copy gather kernel, the SMs read the host buffers), plan + mask draw under it, fused kernels, D2H read, per step"}
 
     cfg4 = run_cfg4(lid, fe, dev, rank, world, barrier)
 

