@@ -484,15 +484,15 @@ int lidfe_h2d_gather(void* dst_dev, const void* const* src_host, const long long
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned char* const dst = static_cast<unsigned char*>(dst_dev);
-  // kernel path: every source 16-byte aligned and device-accessible (checked on the first and the last one: a DataLoader
-  // pins all of a batch or none), every destination 16-byte aligned; LIDFE_H2D_KERNEL=0 keeps the copy engine
+  // kernel path: every source 16-byte aligned and device-accessible, every destination 16-byte aligned;
+  // LIDFE_H2D_KERNEL=0 keeps the copy engine
   static const int use_kernel = [] { const char* env = getenv("LIDFE_H2D_KERNEL"); return env ? atoi(env) : 1; }();
   bool kernel_ok = use_kernel && B >= 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
   for (int i = 0; i < B && kernel_ok; ++i)
     kernel_ok = (reinterpret_cast<uintptr_t>(src_host[i]) & 15) == 0 && ((offsets[i] * elem_bytes) & 15) == 0;
-  for (int k = 0; k < 2 && kernel_ok; ++k) {
+  for (int k = 0; k < B && kernel_ok; ++k) {       // (~0.5 us per query: a source the device cannot read would be a fault, not an error code)
     cudaPointerAttributes at;
-    const void* p = src_host[k ? B - 1 : 0];
+    const void* p = src_host[k];
     if (!p) continue;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); kernel_ok = false; break; }
     kernel_ok = (at.type == cudaMemoryTypeHost) && at.devicePointer == p;

@@ -196,3 +196,28 @@ def test_precise_random_ragged_batches(lid, fep):
             rows += T
         assert float(stats[160]) == rows
         plan.close()
+
+
+@gpu
+def test_h2d_gather_kernel_and_its_fallback(lid):
+    """Pinned items go up through the zero-copy gather kernel (the SMs read the host buffers), a batch with a pageable
+    item in the middle falls back to the copy engine, int16 items and odd lengths included: all equal to the result
+    from device-resident inputs, bit for bit."""
+    fe = lid.FrontEnd(n_mels=80)
+    lens = [8000, 8161, 400, 12345, 9000, 40001, 700, 5555]
+    wavs = [O.synth_noise(n, 70 + i)[0] for i, n in enumerate(lens)]
+    want, _ = fe.featurize([w.cuda() for w in wavs])
+    n0 = lid.load_library().lidfe_launch_count()
+    got, _ = fe.featurize([w.pin_memory() for w in wavs], cache_plan=False)
+    assert lid.load_library().lidfe_launch_count() - n0 == 2          # gather kernel + fbank kernel
+    assert torch.equal(got, want)
+    mixed = [w if i == 3 else w.pin_memory() for i, w in enumerate(wavs)]
+    n0 = lid.load_library().lidfe_launch_count()
+    got, _ = fe.featurize(mixed, cache_plan=False)
+    assert lid.load_library().lidfe_launch_count() - n0 == 1          # copy engine + fbank kernel
+    assert torch.equal(got, want)
+    fe16 = lid.FrontEnd(n_mels=80, in_dtype=torch.int16, in_scale=1.0 / 32768.0)
+    pcm = [(w.clamp(-4, 4) * 8000.0).round().to(torch.int16) for w in wavs]
+    want16, _ = fe16.featurize([q.cuda() for q in pcm])
+    got16, _ = fe16.featurize([q.pin_memory() for q in pcm], cache_plan=False)
+    assert torch.equal(got16, want16)
