@@ -298,8 +298,9 @@ int lidfe_stft_mel_db(const float* g_dev, const long long* g_off_dev, const long
  * formula (ref: lid/audio_processor.py:41-69 -> ta: compliance/kaldi.py:183-217, 514-645, 648-813) evaluated in float64
  * from the samples to the logarithm (through DCT + lifter for MFCC) on the same fp32 tables, rounded once at the store:
  * within half an ulp of the fp64 truth, i.e. at least as close to it as the reference's own fp32 result on every mel bin
- * (SURVEY.md 8c metric iv).  About 3 x the time of the fast path.  Scope: KALDI framing, natural log, no in-kernel dither
- * (LIDFE_E_CONFIG otherwise); every cmvn mode except LIDFE_POST_TOPDB; lidfe_featurize_raw is not served (LIDFE_E_ARG).
+ * (SURVEY.md 8c metric iv).  About 3 x the time of the fast path.  Scope: both framings (the Kaldi call and the default
+ * MelSpectrogram + AmplitudeToDB branch, ref: lid/audio_processor.py:72-105), both logs, every cmvn mode; no in-kernel
+ * dither (LIDFE_E_CONFIG); lidfe_featurize_raw is not served (LIDFE_E_ARG).
  * No allocation, no synchronisation: the mode reads the handle's existing tables. */
 int lidfe_set_precision(lidfe_handle h, int precise);
 

@@ -22,8 +22,8 @@ from .specaug import draw_masks
 
 _frontends: Dict[Tuple, FrontEnd] = {}
 
-# The single-utterance wrappers below are latency-bound (a PCIe round trip and two launches per call), so the Kaldi
-# branch runs in the precise arithmetic mode (``FrontEnd(precise=True)``: float64 internally, one rounding): it costs
+# The single-utterance wrappers below are latency-bound (a PCIe round trip and two launches per call), so both wav2mel
+# branches run in the precise arithmetic mode (``FrontEnd(precise=True)``: float64 internally, one rounding): it costs
 # nothing measurable here and the result is never further from the fp64 truth than the reference's own.  Set to False
 # for the fast fp32 kernels (what the batched ``FrontEnd.featurize`` uses by default).
 PRECISE_DROPIN = True
@@ -31,7 +31,7 @@ PRECISE_DROPIN = True
 
 def _frontend(n_mels: int, sr: int, win_length: float, hop_length: float, device, kind: str = "kaldi",
               pad: int = 0) -> FrontEnd:
-    precise = bool(PRECISE_DROPIN) and kind == "kaldi"
+    precise = bool(PRECISE_DROPIN)
     key = (int(n_mels), int(sr), float(win_length), float(hop_length), str(device), kind, int(pad), precise)
     fe = _frontends.get(key)
     if fe is None:

@@ -1462,7 +1462,7 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
 
   if (h->precise) {
     // precise mode: fp64 arithmetic in fbank_precise_kernel (statistics included), normalisation / masks in the apply kernel
-    if (raw || cmvn_mode == LIDFE_POST_TOPDB) return LIDFE_E_ARG;
+    if (raw) return LIDFE_E_ARG;
     PreciseParams Q;
     memset(&Q, 0, sizeof(Q));
     Q.wav = wav_dev;
@@ -1483,7 +1483,14 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     Q.preemph = h->cfg.preemph;
     Q.in_scale = h->cfg.in_scale;
     Q.log_floor = h->cfg.log_floor;
-    Q.log_of_floor = logf(h->cfg.log_floor);
+    Q.log_of_floor = P.log_of_floor;
+    Q.log_mul = (h->cfg.log_kind == LIDFE_LOG_DB10) ? 4.3429448190325182765 : 1.0;     // 10 / ln 10
+    Q.center = P.center;
+    Q.pad = P.pad;
+    Q.utt_offsets = p->d_offsets;
+    Q.utt_lengths = p->d_lengths;
+    Q.utt_max = p->d_utt_max + static_cast<long long>(P.parity & 1) * P.b_cap;
+    Q.utt_min = p->d_utt_min + static_cast<long long>(P.parity & 1) * P.b_cap;
     Q.remove_dc = h->cfg.remove_dc;
     Q.mode = cmvn_mode;
     Q.utt_stats = p->d_utt_stats + static_cast<long long>(P.parity & 1) * P.b_cap * 2 * h->n_out;
@@ -1495,6 +1502,7 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
     if (cmvn_mode == LIDFE_CMVN_PER_UTT) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 1, P.parity);
+    if (cmvn_mode == LIDFE_POST_TOPDB) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 2, P.parity);
     if (cmvn_mode == LIDFE_CMVN_APPLY_GLOBAL) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, stats_in_dev, st, 1);
     if (cmvn_mode == LIDFE_CMVN_NONE && masks_dev && n_masks > 0) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 0);
     CU_TRY(cudaEventRecord(p->blk->ev, st));
@@ -1679,8 +1687,8 @@ int lidfe_set_precision(lidfe_handle h, int precise) {
   if (!h) return LIDFE_E_NULL;
   if (precise != 0 && precise != 1) return LIDFE_E_ARG;
   if (precise) {
-    // scope of fbank_precise_kernel: the reference's Kaldi call and its relatives
-    if (h->cfg.framing != LIDFE_FRAMING_KALDI || h->cfg.log_kind != LIDFE_LOG_NATURAL || h->cfg.dither != 0.f) return LIDFE_E_CONFIG;
+    // scope of fbank_precise_kernel: both framings, both logs; the dither draw stays with the fp32 kernels
+    if (h->cfg.dither != 0.f) return LIDFE_E_CONFIG;
     if (h->total_taps > kPMaxTaps) return LIDFE_E_MELBANK;
     cudaError_t e = cudaFuncSetAttribute(fbank_precise_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);

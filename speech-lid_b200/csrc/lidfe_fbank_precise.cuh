@@ -14,8 +14,10 @@
 // shuffles between lane t and lane 16 - t -- but one frame per half-warp in doubles instead of a frame pair in packed
 // floats, the mel bank in the fast kernels' segment form with fp64 accumulation, libdevice's log.  B200's FP64 pipe runs DFMA at half
 // the FFMA rate (tools/ubench.cu: 62.5 against 120 lane-ops/clk/SM), so this is a 3-4 x slower kernel, not a 30 x one (measured: 340 us against 100 us per 256 x 8 s).
-// Scope: KALDI framing, natural log, float32 / int16 input, fbank or MFCC output, every CMVN mode but top_db
-// (statistics are taken here, the normalisation / masks run in cmvn_apply_kernel as for the fast path).
+// Scope: KALDI framing (the reference's Kaldi call and its relatives) and CENTER framing (its default branch: window-only
+// framing, HTK mel, dB, per-utterance extrema for AmplitudeToDB's top_db clamp), float32 / int16 input, fbank or MFCC
+// output, every CMVN mode (statistics / extrema are taken here, the normalisation / clamp / masks run in
+// cmvn_apply_kernel as for the fast path).
 #pragma once
 #include "lidfe_kernels.cuh"
 
@@ -37,7 +39,13 @@ struct PreciseParams {
   int n_mels, n_ceps, n_out;
   float preemph, in_scale, log_floor, log_of_floor;
   int remove_dc;
-  int mode;                 // LIDFE_CMVN_*: 1 -> sums into utt_stats, 3 -> sums into stats_out
+  double log_mul;           // 1 (natural log) or 10 / ln 10 (dB)
+  int center, pad;          // LIDFE_FRAMING_CENTER: frame f covers p[160 f - 200, 160 f + 200) of the constant-padded, reflect-extended signal
+  const long long* utt_offsets;   // [B] (CENTER framing)
+  const long long* utt_lengths;   // [B]
+  unsigned* utt_max;        // this launch's half, [B_cap]: order-preserving encoding of the utterance's max / min feature
+  unsigned* utt_min;        //   (mode 4, AmplitudeToDB's top_db clamp runs in cmvn_apply_kernel)
+  int mode;                 // LIDFE_CMVN_*: 1 -> sums into utt_stats, 3 -> sums into stats_out, 4 -> extrema
   double* utt_stats;        // this launch's half: [B_cap][2][n_out]
   double* stats_out;        // [2 * n_out + 1]
 };
@@ -163,12 +171,26 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
     if (fbeg >= sp.nframes) continue;
     const int fend = min(sp.nframes, fbeg + kTileFrames);
     double ssum[kBands], qsum[kBands];      // this lane's share of the unit's sums (dims t + 16 b, frames of its half-warp)
+    float ex_max = -INFINITY, ex_min = INFINITY;
 #pragma unroll
     for (int b = 0; b < kBands; ++b) ssum[b] = qsum[b] = 0.0;
     for (int f0 = fbeg; f0 < fend; f0 += kPHalfWarps) {
       const bool active = f0 + hw < fend;
       const int f = active ? f0 + hw : fend - 1;
       const TIn* const x = wav + sp.wav_off + static_cast<long long>(kFrameShift) * f;
+      // CENTER framing (the reference's torch.stft branch, ref: lid/audio_processor.py:91-103): sample i of frame tf is
+      // p[160 tf - 200 + i], p = the utterance with `pad` zeros on either side, mirrored once at either end
+      const long long cN = P.center ? __ldg(P.utt_lengths + sp.utt) : 0;
+      const TIn* const cx = P.center ? wav + __ldg(P.utt_offsets + sp.utt) : wav;
+      const long long cLp = cN + 2 * P.pad;
+      const long long cu0 = static_cast<long long>(kFrameShift) * (sp.t0 + f) - (kFrameLen / 2);
+      auto sample = [&](int i) -> double {
+        if (!P.center) return ld_sample<TIn>(x + i, P.in_scale);
+        long long u = cu0 + i;
+        u = u < 0 ? -u : (u >= cLp ? 2 * (cLp - 1) - u : u);
+        const long long r = u - P.pad;
+        return (r >= 0 && r < cN) ? ld_sample<TIn>(cx + r, P.in_scale) : 0.0;
+      };
 
       // ---- framing in fp64: DC removal, pre-emphasis with replicate-left, window (ta: compliance/kaldi.py:183-204) ----
       double R[16], I[16];
@@ -177,8 +199,8 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
       for (int j = 0; j < 13; ++j) {
         const int n = t + 16 * j;
         const bool valid = (j < 12 || t < 8);
-        a0[j] = valid ? ld_sample<TIn>(x + 2 * n, P.in_scale) : 0.0;
-        a1[j] = valid ? ld_sample<TIn>(x + 2 * n + 1, P.in_scale) : 0.0;
+        a0[j] = valid ? sample(2 * n) : 0.0;
+        a1[j] = valid ? sample(2 * n + 1) : 0.0;
       }
 #pragma unroll
       for (int j = 0; j < 13; ++j) {      // x[2n - 1] sits in lane t - 1 (lane 15 of the previous j for t = 0); x[-1] := x[0]
@@ -275,7 +297,7 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
         val[b] = 0.f;
         if (m < P.n_mels) {
           const bool floored = !(E > static_cast<double>(P.log_floor));
-          v = floored ? static_cast<double>(P.log_of_floor) : log(E);
+          v = floored ? static_cast<double>(P.log_of_floor) : log(E) * P.log_mul;
           val[b] = floored ? P.log_of_floor : static_cast<float>(v);
           if (P.n_ceps > 0) LM[m] = v;
         }
@@ -303,10 +325,23 @@ __global__ void __launch_bounds__(kPThreads, LIDFE_PRECISE_CTAS) fbank_precise_k
             const double xv = static_cast<double>(val[b]);
             ssum[b] += xv;
             qsum[b] = fma(xv, xv, qsum[b]);
+            ex_max = fmaxf(ex_max, val[b]);
+            ex_min = fminf(ex_min, val[b]);
           }
         }
       }
       __syncwarp();       // the power bins / log-mels have been read: the plane is free for the next frame
+    }
+    if (P.mode == 4) {        // AmplitudeToDB(top_db): the utterance's extrema (ta: functional/functional.py:391-403)
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        ex_max = fmaxf(ex_max, __shfl_xor_sync(0xffffffffu, ex_max, o));
+        ex_min = fminf(ex_min, __shfl_xor_sync(0xffffffffu, ex_min, o));
+      }
+      if (lane == 0) {
+        atomicMax(P.utt_max + sp.utt, f2ord(ex_max));
+        atomicMin(P.utt_min + sp.utt, f2ord(ex_min));
+      }
     }
     if (stats) {
       // the half-warps park their sums in their (now idle) planes; 160 threads-worth of adds, then one atomic per dim

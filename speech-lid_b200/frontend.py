@@ -101,7 +101,7 @@ class FrontEnd:
         "rectangular", "blackman" (ta: compliance/kaldi.py:86-113); kaldi branch only.
         ``dither`` > 0: ``wav += dither * U[0,1)`` (ref: lid/audio_processor.py:129) inside the fused kernel, Philox keyed
         by (seed, utterance, sample); 0 is the reference's ``wav2mel`` (its kaldi call passes dither=0.0, :57).
-        ``precise=True`` (kaldi branch): the same formula evaluated in float64 on the same fp32 tables and rounded once
+        ``precise=True`` (either kind; not with in-kernel dither): the same formula evaluated in float64 on the same fp32 tables and rounded once
         (``lidfe_set_precision``): at least as close to the fp64 truth as the reference's own fp32 result on every mel
         bin, at about 3 x the time of the default fast fp32 kernels."""
         if kind not in ("kaldi", "melspec_db"):

@@ -139,9 +139,49 @@ def test_precise_cmvn_modes_and_masks(lid, fep):
 @gpu
 def test_precise_scope_errors(lid):
     with pytest.raises(RuntimeError):
-        lid.FrontEnd(kind="melspec_db", precise=True)
-    with pytest.raises(RuntimeError):
-        lid.FrontEnd(dither=1e-5, precise=True)
+        lid.FrontEnd(dither=1e-5, precise=True)       # the in-kernel dither draw stays with the fp32 kernels
+
+
+def _truth64_melspec_db(x, pad=0, top_db=80.0):
+    """The reference's default branch (ref: lid/audio_processor.py:72-105 -> torch.stft(center=True, reflect), HTK mel,
+    AmplitudeToDB(top_db)) in float64 on the fp32 tables: (T, 80)."""
+    w = x[0].double()
+    if pad:
+        w = torch.nn.functional.pad(w, (pad, pad))
+    wp = torch.nn.functional.pad(w[None, None], (256, 256), mode="reflect")[0, 0]
+    T = 1 + w.numel() // 160
+    fr = wp[torch.arange(T)[:, None] * 160 + torch.arange(512)[None]]
+    win = torch.zeros(512, dtype=torch.float64)
+    win[56:456] = torch.hann_window(400).double()
+    X = torch.fft.rfft(fr * win)
+    mel = (X.real ** 2 + X.imag ** 2) @ O.htk_mel_fbanks(257, 0.0, 8000.0, 80, 16000).double()
+    db = 10.0 * torch.log10(mel.clamp_min(1e-10))
+    return torch.maximum(db, db.max() - top_db)
+
+
+@gpu
+def test_precise_default_branch_melspec_db(lid):
+    """The precise mode on the reference's DEFAULT branch (row A9): CENTER framing with reflection, periodic Hann window,
+    HTK mel, 10 log10, top_db clamp -- the fp64 truth rounded once, and per mel bin never further from it than 1.5 x the
+    reference's own fp32 result."""
+    for pad in (0, 16):
+        fe = lid.FrontEnd(kind="melspec_db", pad=pad, precise=True)
+        wavs = [O.synth_noise(n, 600 + i) for i, n in enumerate([48000, 4000, 12345])]
+        # the last quarter of the first utterance 100 dB down: the top_db clamp becomes active there
+        wavs[0] = torch.cat([wavs[0][:, :36000], wavs[0][:, 36000:] * 1e-5], 1)
+        feats, _ = fe.featurize(wavs)
+        feats = feats.cpu()
+        for i, w in enumerate(wavs):
+            tru = _truth64_melspec_db(w, pad=pad)
+            T = tru.shape[0]
+            got = feats[i, :T]
+            assert float((got.double() - tru).abs().max()) <= 1.0e-5, (pad, i)
+            assert torch.all(feats[i, T:] == 0)
+            ref = O.melspec_db(w, pad=pad)[0].transpose(0, 1)
+            eg = (got.double() - tru).abs().max(0).values
+            er = (ref.double() - tru).abs().max(0).values
+            assert bool((eg <= 1.5 * er + 1e-12).all()), (pad, i)
+        assert float((feats[0, :301].max() - feats[0, :301].min())) <= 80.0 + 1e-4      # the clamp was active
 
 
 @gpu
