@@ -1497,8 +1497,12 @@ static int featurize_impl(lidfe_handle h, lidfe_plan p, const void* wav_dev, flo
     Q.stats_out = stats_out_dev;
     long long gp = p->n_spans * kMaxSpanTiles < static_cast<long long>(h->num_sms) * LIDFE_PRECISE_CTAS ? p->n_spans * kMaxSpanTiles : static_cast<long long>(h->num_sms) * LIDFE_PRECISE_CTAS;
     if (gp < 1) gp = 1;
-    if (h->cfg.in_dtype == LIDFE_IN_I16) fbank_precise_kernel<short><<<static_cast<unsigned>(gp), kPThreads, kPSmemBytes, st>>>(Q);
-    else fbank_precise_kernel<float><<<static_cast<unsigned>(gp), kPThreads, kPSmemBytes, st>>>(Q);
+    {
+      void (*pk)(const PreciseParams) =
+          (h->cfg.in_dtype == LIDFE_IN_I16) ? (Q.center ? fbank_precise_kernel<short, true> : fbank_precise_kernel<short, false>)
+                                            : (Q.center ? fbank_precise_kernel<float, true> : fbank_precise_kernel<float, false>);
+      pk<<<static_cast<unsigned>(gp), kPThreads, kPSmemBytes, st>>>(Q);
+    }
     g_launches.fetch_add(1);
     CU_TRY(cudaGetLastError());
     if (cmvn_mode == LIDFE_CMVN_PER_UTT) return launch_apply(h, p, out_dev, out_ld, masks_dev, n_masks, nullptr, st, 1, P.parity);
@@ -1690,8 +1694,10 @@ int lidfe_set_precision(lidfe_handle h, int precise) {
     // scope of fbank_precise_kernel: both framings, both logs; the dither draw stays with the fp32 kernels
     if (h->cfg.dither != 0.f) return LIDFE_E_CONFIG;
     if (h->total_taps > kPMaxTaps) return LIDFE_E_MELBANK;
-    cudaError_t e = cudaFuncSetAttribute(fbank_precise_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<short>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(fbank_precise_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<short, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_precise_kernel<short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
       return static_cast<int>(e);

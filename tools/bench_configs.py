@@ -62,6 +62,12 @@ def main():
         128000, quiet_tail=True)
     i16 = lid.FrontEnd(n_mels=80, in_dtype=torch.int16, in_scale=1.0 / 32768.0)
     run("kaldi fbank from int16 samples (2 B/sample read), 256 x 8 s", i16, 256, 128000, dtype=torch.int16)
+    pf = lid.FrontEnd(n_mels=80, precise=True)
+    run("precise mode (float64 kernel): kaldi fbank only, 256 x 8 s", pf, 256, 128000)
+    run("precise mode: cfg2 (fbank + SpecAugment + per-utterance CMVN), 256 x 8 s", pf, 256, 128000, masks=masks, cmvn="utt")
+    run("precise mode: cfg3 (40 MFCC of 80 mel), 512 x 4 s", lid.FrontEnd(n_mels=80, n_ceps=40, precise=True), 512, 64000)
+    run("precise mode: default branch (MelSpectrogram + AmplitudeToDB), pad 16, 256 x 8 s", lid.FrontEnd(kind="melspec_db", pad=16, precise=True),
+        256, 128000)
     run_resample("resample 44.1 kHz -> 16 kHz (475-tap polyphase FIR), 256 x 8 s", 44100, 256, 8.0)
     run_resample("resample 22.05 kHz -> 16 kHz (459-tap polyphase FIR), 256 x 8 s", 22050, 256, 8.0)
 

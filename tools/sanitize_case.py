@@ -50,5 +50,6 @@ pplan = pr.make_plan(lens, padded=False)
 pr.featurize_packed(pr.pack(wavs, pplan), pplan, cmvn="global_accum", stats_out=pstats)
 lid.FrontEnd(n_mels=80, n_ceps=40, precise=True).featurize(wavs)
 lid.FrontEnd(n_mels=23, n_ceps=13, preemph=0.97, precise=True).featurize(wavs)
+lid.FrontEnd(kind="melspec_db", pad=16, precise=True).featurize(wavs, masks=masks)
 torch.cuda.synchronize()
 print("sanitize_case ok, launches", lid.load_library().lidfe_launch_count())
